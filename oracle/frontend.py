@@ -1,0 +1,350 @@
+"""CPU restatement of the reference's own front-end Python, on in-memory arrays.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Every function cites the
+reference lines it follows (``/root/reference``).  File decode + resample
+(``librosa.load``) is outside these functions: they start from the float32 array
+``librosa.load`` would have returned.
+
+Pinned by ``tests/golden/*.npz``: fixtures produced by executing the real
+``src/util.py`` (``tests/golden/make_golden.py``).
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+
+from . import librosa_restated as lr
+
+# ----------------------------------------------------------------------------- band-pass
+
+
+def butter_bandpass(lowcut, highcut, fs, order=5):
+    """src/util.py:113-119 - scipy Butterworth band-pass, transfer-function form."""
+    from scipy.signal import butter
+
+    nyq = 0.5 * fs
+    return butter(order, [lowcut / nyq, highcut / nyq], btype="band")
+
+
+def butter_bandpass_filter(data, lowcut, highcut, fs, order=5):
+    """src/util.py:122-126 - causal single-pass ``lfilter``; float64 result."""
+    from scipy.signal import lfilter
+
+    b, a = butter_bandpass(lowcut, highcut, fs, order=order)
+    return lfilter(b, a, data)
+
+
+# ----------------------------------------------------------------------------- silence trim
+
+
+def trim_silence(data, sample_rate=16000):
+    """src/util.py:170-172,237-244,338-340,820-822 - 100 ms frames, 50 ms hop, top_db 60."""
+    frame_len = int(sample_rate / 10)
+    hop = int(frame_len / 2)
+    return lr.trim(data, frame_length=frame_len, hop_length=hop)
+
+
+# ----------------------------------------------------------------------------- pad / split
+
+
+def zero_padding(source, output_length):
+    """src/util.py:504-519 - right zero-pad, or tile forward while a whole copy still fits
+    strictly inside, when the source is shorter than half the target."""
+    out = np.zeros(output_length, dtype=np.float32)
+    n = len(source)
+    if n / output_length < 0.5:
+        pos = 0
+        while pos + n < output_length:
+            out[pos : pos + n] = source
+            pos += n
+    else:
+        out[:n] = source
+    return out
+
+
+def equally_slice_pad(clip, desired_length, sample_rate):
+    """src/util.py:522-547 - ceil(duration/desired) equal slices, each through zero_padding."""
+    L = int(desired_length * sample_rate)
+    clip = np.array(clip, copy=True)
+    n = len(clip)
+    n_slices = int(math.ceil((n / sample_rate) / desired_length))
+    per = n // n_slices
+    out = []
+    lo = 0
+    for _ in range(n_slices):
+        hi = min(lo + per, n)
+        out.append(zero_padding(clip[lo:hi], L))
+        lo = hi
+    return out
+
+
+def duplicate_padding(clip, source, output_length):
+    """src/util.py:550-575 - 'repeat' padding.
+
+    The reference reseeds Python's global RNG with 7456 on every call and draws one
+    number (0.0617...) so the branch taken is always "source at the end, tail of the
+    doubled clip in front".  The reseed is a visible side effect and is reproduced.
+    """
+    out = np.zeros(output_length, dtype=np.float32)
+    left = output_length - len(source)
+    aug = clip
+    while len(aug) < left:
+        aug = np.concatenate([aug, aug])
+    random.seed(7456)
+    if random.random() < 0.5:
+        out[left:] = source
+        out[:left] = aug[len(aug) - left :]
+    else:
+        out[: len(source)] = source
+        out[len(source) :] = aug[:left]
+    return out
+
+
+def split_pad_sample(clip, desired_length, sample_rate, types="repeat"):
+    """src/util.py:578-620 - returns the list of padded chunks (arrays only)."""
+    if types == "zero":
+        return equally_slice_pad(clip, desired_length, sample_rate)
+    L = int(desired_length * sample_rate)
+    clip = np.array(clip, copy=True)
+    n = len(clip)
+    out = []
+    if n > L:
+        hop = L // 2
+        n_full = 1 + (n - L) // hop
+        for j in range(n_full):
+            out.append(clip[j * hop : j * hop + L])
+        tail = clip[n_full * hop :]
+        out.append(duplicate_padding(clip, tail, L))
+    else:
+        out.append(duplicate_padding(clip, clip, L))
+    return out
+
+
+def split_sample(clip, desired_length, sample_rate):
+    """extract_feature.py:250-259 - non-overlapping chunks, last one short."""
+    L = int(desired_length * sample_rate)
+    clip = np.array(clip, copy=True)
+    n_chunks = int(np.ceil(len(clip) / L))
+    return [clip[L * i : L * (i + 1)] for i in range(n_chunks)]
+
+
+def decide_droplast(yt, sr, input_sec):
+    """src/util.py:369-371."""
+    duration = lr.get_duration(y=yt, sr=sr)
+    return duration > input_sec and (duration % input_sec) * 2 < input_sec
+
+
+# ----------------------------------------------------------------------------- log-mel
+
+
+def log_mel(audio, sample_rate=16000, n_mels=64, f_min=50, f_max=2000, nfft=1024, hop=512, return_parts=False):
+    """src/util.py:481-501 - mel power -> dB re clip max (floor -80) -> clip min-max -> [T, n_mels]."""
+    S = lr.melspectrogram(y=audio, sr=sample_rate, n_mels=n_mels, fmin=f_min, fmax=f_max, n_fft=nfft, hop_length=hop)
+    db = lr.power_to_db(S, ref=np.max)
+    lo, hi = db.min(), db.max()
+    if hi != lo:
+        norm = (db - lo) / (hi - lo)
+    else:
+        norm = db
+    if return_parts:
+        return norm.T, db.T, S.T
+    return norm.T
+
+
+# ----------------------------------------------------------------------------- kaldi fbank
+
+
+def kaldi_fbank_chunk(chunk, sample_rate=16000):
+    """src/util.py:841-856 / extract_feature.py:228-243 - mean-removed chunk -> kaldi fbank
+    (live ``torchaudio.compliance.kaldi.fbank``, the library the reference calls).
+    Returns ``None`` for chunks of <= 400 samples (skipped by the reference)."""
+    import torch
+    import torchaudio
+
+    w = chunk - chunk.mean()
+    w = torch.tensor(w).reshape([1, -1])
+    if w.shape[1] <= 400:
+        return None
+    return torchaudio.compliance.kaldi.fbank(
+        w,
+        channel=0,
+        frame_length=25,
+        htk_compat=True,
+        sample_frequency=sample_rate,
+        use_energy=False,
+        window_type="hanning",
+        num_mel_bins=128,
+        dither=0.0,
+        frame_shift=10,
+    )
+
+
+def pad_to_model(x, n_frames=1024, n_mels=128):
+    """audioMAE/models_mae.py:1178-1181, mae_training.py:88-109 - zero rows/cols appended, crop if longer."""
+    x = np.asarray(x)
+    x = x[:n_frames, :n_mels]
+    return np.pad(x, ((0, n_frames - x.shape[0]), (0, n_mels - x.shape[1])))
+
+
+# ----------------------------------------------------------------------------- composite entry points
+
+
+def _maybe_filter(data, butterworth_filter, lowcut, highcut, sample_rate):
+    if butterworth_filter:
+        return butter_bandpass_filter(data, lowcut, highcut, sample_rate, order=butterworth_filter)
+    return data
+
+
+def entire_signal(
+    data,
+    input_sec=8,
+    sample_rate=16000,
+    butterworth_filter=None,
+    spectrogram=False,
+    pad=False,
+    types="repeat",
+    lowcut=200,
+    highcut=1800,
+    max_sec=None,
+):
+    """src/util.py:205-267 (get_entire_signal_librosa) after ``librosa.load``."""
+    data = _maybe_filter(data, butterworth_filter, lowcut, highcut, sample_rate)
+    yt, _ = trim_silence(data, sample_rate)
+    duration = lr.get_duration(y=yt, sr=sample_rate)
+    if duration < input_sec:
+        if not pad:
+            return None
+        yt = split_pad_sample(yt, input_sec, sample_rate, types)[0]
+    if max_sec and duration > max_sec:
+        yt = yt[: int(max_sec * sample_rate)]
+    if spectrogram:
+        return log_mel(yt.squeeze(), f_max=8000)
+    return yt
+
+
+def split_signal(
+    data,
+    input_sec=8,
+    sample_rate=16000,
+    butterworth_filter=None,
+    spectrogram=False,
+    trim_tail=False,
+    lowcut=200,
+    highcut=1800,
+):
+    """src/util.py:309-364 (get_split_signal_librosa) after ``librosa.load``."""
+    data = _maybe_filter(data, butterworth_filter, lowcut, highcut, sample_rate)
+    yt, _ = trim_silence(data, sample_rate)
+    drop_last = decide_droplast(yt, sample_rate, input_sec) if trim_tail else False
+    chunks = split_pad_sample(yt, input_sec, sample_rate)
+    if drop_last:
+        chunks.pop()
+    if not spectrogram:
+        return chunks
+    return [log_mel(c.squeeze(), f_max=8000) for c in chunks]
+
+
+def split_signal_fbank_pad(
+    data, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False, trim_tail=False
+):
+    """src/util.py:794-860 (get_split_signal_fbank_pad) after ``librosa.load``."""
+    data = _maybe_filter(data, butterworth_filter, 200, 1800, sample_rate)
+    yt, _ = trim_silence(data, sample_rate)
+    drop_last = decide_droplast(yt, sample_rate, input_sec) if trim_tail else False
+    chunks = split_pad_sample(yt, input_sec, sample_rate)
+    if drop_last:
+        chunks.pop()
+    if not spectrogram:
+        return chunks
+    out = []
+    for c in chunks:
+        fb = kaldi_fbank_chunk(c, sample_rate)
+        if fb is not None:
+            out.append(fb)
+    return out
+
+
+def split_signal_fbank(data, input_sec=10, sample_rate=16000):
+    """extract_feature.py:213-247 (get_split_signal_fbank) after ``librosa.load``."""
+    yt, _ = trim_silence(data, sample_rate)
+    out = []
+    for c in split_sample(yt, input_sec, sample_rate):
+        fb = kaldi_fbank_chunk(c, sample_rate)
+        if fb is not None:
+            out.append(fb)
+    return out
+
+
+def individual_segments(
+    data, input_sec=8, sample_rate=16000, hop_sec=2, butterworth_filter=None, spectrogram=False
+):
+    """src/util.py:141-202 (get_individual_segments_librosa) after ``librosa.load``."""
+    data = _maybe_filter(data, butterworth_filter, 200, 1800, sample_rate)
+    yt, _ = trim_silence(data, sample_rate)
+    duration = lr.get_duration(y=yt, sr=sample_rate)
+    if duration < 2:
+        return []
+
+    def cut(t0, t1):  # src/util.py:129-138
+        a = min(int(t0 * sample_rate), len(yt))
+        b = min(int(t1 * sample_rate), len(yt))
+        return yt[a:b]
+
+    segs = []
+    start, end = 0, input_sec
+    while end <= duration:
+        segs.append(cut(start, end))
+        start += hop_sec
+        end += hop_sec
+    if start + 2 < duration:
+        segs.append(split_pad_sample(cut(start, end), 8, sample_rate)[0])
+    if spectrogram:
+        return [log_mel(s.squeeze()) for s in segs]
+    return segs
+
+
+# ----------------------------------------------------------------------------- spectrogram-domain ops
+
+
+def crop_first(data, crop_size=128):
+    """src/util.py:26-27."""
+    return data[0:crop_size, :]
+
+
+def random_crop(data, crop_size=128):
+    """src/util.py:30-32 - one draw from Python's global RNG."""
+    start = int(random.random() * (data.shape[0] - crop_size))
+    return data[start : start + crop_size, :]
+
+
+def random_mask(data, rate_start=0.1, rate_seq=0.2):
+    """src/util.py:35-46 - Markov frame masking with the global mean; the second draw
+    happens only when the first fails and the previous frame was masked."""
+    out = data.copy()
+    mean = out.mean()
+    prev = False
+    for i in range(out.shape[0]):
+        if random.random() < rate_start or (prev and random.random() < rate_seq):
+            prev = True
+            out[i, :] = mean
+        else:
+            prev = False
+    return out
+
+
+def random_multiply(data):
+    """src/util.py:49-51."""
+    return data.copy() * (0.9 + random.random() / 5.0)
+
+
+def resample_torchaudio(wave, orig_sr, new_sr):
+    """Pinned resampler oracle: ``torchaudio.functional.resample`` (Hann-windowed sinc,
+    the resampler used at src/model/models_eval.py:964-968).  ``librosa.load``'s soxr_hq
+    resampler (src/util.py:153,222,...) is not installable here: parity unpinned."""
+    import torch
+    import torchaudio
+
+    w = torch.as_tensor(np.asarray(wave, dtype=np.float32))
+    return torchaudio.functional.resample(w, int(orig_sr), int(new_sr)).numpy()

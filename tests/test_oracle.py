@@ -1,0 +1,177 @@
+"""The oracle against (a) the golden fixtures produced by executing the real
+reference ``src/util.py`` (tests/golden/make_golden.py) and (b) independent
+third-party implementations (torchaudio's librosa-compatible ops, scipy)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torchaudio
+
+from cases import PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, check_digest, hash_spec, sha, sha_list
+from signals import golden_signal
+
+from oracle import frontend as F
+from oracle import librosa_restated as lr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "ref_util.json")))["cases"]
+ARR = {k.replace("|", "/"): v for k, v in np.load(os.path.join(HERE, "golden", "ref_util.npz")).items()}
+
+
+def rng_fingerprint():
+    return sha(np.array(random.getstate()[1], dtype=np.uint64))
+
+
+@pytest.fixture(scope="module")
+def store():
+    return {name: golden_signal(n, seed, SR, lead, tail) for name, n, seed, lead, tail in RECORDINGS}
+
+
+# ----------------------------------------------------------------- index work: bit exact vs reference
+
+
+@pytest.mark.parametrize("sec", PAD_SPLIT_SECS)
+def test_split_pad_matches_reference(sec):
+    for n in PAD_SPLIT_LENGTHS:
+        x = golden_signal(n, seed=n % 97, sr=SR, lead=0, tail=0)
+        for types_ in ("repeat", "zero"):
+            random.seed(99)
+            out = F.split_pad_sample(x, sec, SR, types=types_)
+            g = META[f"split_pad/{sec}/{n}/{types_}"]
+            assert len(out) == g["n_chunks"]
+            assert sha_list(out) == g["sha"], (sec, n, types_)
+            assert rng_fingerprint() == g["rng_after"]
+        out = F.split_sample(x, sec, SR)
+        g = META[f"split_sample/{sec}/{n}"]
+        assert [len(o) for o in out] == g["lens"] and sha_list(out) == g["sha"]
+        assert bool(F.decide_droplast(x, SR, sec)) == META[f"droplast/{sec}/{n}"]
+
+
+@pytest.mark.parametrize("T,Fq,crop", [(251, 64, 251), (400, 64, 251), (1022, 128, 512), (63, 64, 32), (3750, 64, 251)])
+def test_spec_ops_match_reference(T, Fq, crop):
+    g = META[f"specops/{T}x{Fq}/{crop}"]
+    spec = hash_spec(T, Fq, seed=T)
+    random.seed(1000 + T)
+    m = F.random_mask(spec)
+    assert sha(m) == g["mask_sha"]
+    c1 = F.random_crop(m, crop_size=crop)
+    c2 = F.random_crop(m, crop_size=crop)
+    assert [sha(c1), sha(c2)] == g["crop_sha"]
+    assert [sha(F.random_multiply(c1)), sha(F.random_multiply(c2))] == g["mul_sha"]
+    assert sha(F.crop_first(spec, crop_size=crop)) == g["first_sha"]
+    assert rng_fingerprint() == g["rng_after"]
+
+
+def test_trim_indices(store):
+    for name in store:
+        _, idx = F.trim_silence(store[name], SR)
+        assert [int(idx[0]), int(idx[1])] == META[f"trim/{name}"]
+
+
+# ----------------------------------------------------------------- composite entry points
+
+
+def _check(key, out):
+    g = META[key]
+    if g.get("none"):
+        assert out is None
+        return
+    if isinstance(out, np.ndarray):
+        assert list(out.shape) == g["shape"] and str(out.dtype) == g["dtype"]
+        if out.ndim == 1:
+            assert sha(out) == g["sha"]
+        else:
+            check_digest(out, g["digest"])
+        return
+    outs = [o.numpy() if hasattr(o, "numpy") else np.asarray(o) for o in out]
+    assert len(outs) == g["n"] and [list(o.shape) for o in outs] == g["shapes"]
+    if outs and outs[0].ndim == 1:
+        assert sha_list(outs) == g["sha"]
+    for o, d in zip([o for o in outs if o.ndim == 2], g["digests"]):
+        check_digest(o, d, rtol=2e-6, atol=2e-6)
+
+
+def test_composites_match_reference(store):
+    for name in store:
+        x = store[name]
+        for kw in (
+            dict(input_sec=8, spectrogram=True, pad=True, types="zero", max_sec=32),
+            dict(input_sec=8, spectrogram=True, pad=True),
+            dict(input_sec=8, spectrogram=True),
+            dict(input_sec=2, spectrogram=False, pad=True),
+            dict(input_sec=8, spectrogram=True, pad=True, types="zero", max_sec=32, butterworth_filter=5),
+        ):
+            tag = ",".join(f"{k}={v}" for k, v in kw.items())
+            _check(f"entire/{name}/{tag}", F.entire_signal(x, **kw))
+        for kw in (
+            dict(input_sec=8.18, spectrogram=True),
+            dict(input_sec=4.09, spectrogram=True, trim_tail=True),
+            dict(input_sec=2, spectrogram=False),
+        ):
+            tag = ",".join(f"{k}={v}" for k, v in kw.items())
+            _check(f"split/{name}/{tag}", F.split_signal(x, **kw))
+        _check(f"fbank_pad/{name}/10", F.split_signal_fbank_pad(x, input_sec=10, spectrogram=True))
+        _check(f"fbank_pad/{name}/2", F.split_signal_fbank_pad(x, input_sec=2, spectrogram=True))
+        _check(f"fbank/{name}/10", F.split_signal_fbank(x, input_sec=10))
+        _check(f"segments/{name}/8", F.individual_segments(x, input_sec=8, spectrogram=True))
+        _check(f"segments_audio/{name}/4", F.individual_segments(x, input_sec=4))
+
+
+def test_logmel_and_bandpass_fixtures(store):
+    for name, fmax in (("r_mid", 8000), ("r_8s", 8000), ("r_8s", 2000), ("r_short", 8000)):
+        out = F.log_mel(store[name], f_max=fmax)
+        check_digest(out, META[f"logmel/{name}/{fmax}"])
+        if f"logmel/{name}/{fmax}" in ARR:
+            np.testing.assert_allclose(out, ARR[f"logmel/{name}/{fmax}"], atol=1e-6)
+    z = F.log_mel(np.zeros(4000, dtype=np.float32), f_max=8000)
+    np.testing.assert_array_equal(z, ARR["logmel/zeros"])  # max == min branch: unnormalised zeros
+    for name in ("r_mid", "r_8s"):
+        y = F.butter_bandpass_filter(store[name], 200, 1800, SR, order=5)
+        check_digest(y, META[f"bandpass/{name}"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(y[:4096], ARR[f"bandpass/{name}/head"], rtol=1e-9, atol=1e-14)
+
+
+# ----------------------------------------------------------------- independent cross-checks (librosa half is unpinned)
+
+
+def test_mel_filterbank_vs_torchaudio():
+    for fmax in (8000.0, 2000.0):
+        ours = lr.mel_filterbank(16000, 1024, n_mels=64, fmin=50, fmax=fmax)
+        ta = torchaudio.functional.melscale_fbanks(513, 50.0, fmax, 64, 16000, norm="slaney", mel_scale="slaney").numpy().T
+        assert np.abs(ours - ta).max() <= 1e-5 * ours.max()  # torchaudio builds the bank in float32
+        np.testing.assert_array_equal(ours == 0, ta == 0)
+    fb = lr.mel_filterbank(16000, 1024, n_mels=64, fmin=50, fmax=8000)
+    assert int((fb != 0).sum()) == 990 and (fb != 0).sum(0).max() <= 2
+    assert not fb[:, :4].any() and not fb[:, 512].any()
+
+
+def test_logmel_vs_torchaudio(store):
+    tf = torchaudio.transforms.MelSpectrogram(
+        16000, n_fft=1024, hop_length=512, f_min=50.0, f_max=8000.0, n_mels=64, norm="slaney", mel_scale="slaney",
+        center=True, pad_mode="constant", power=2.0,
+    )
+    for name in ("r_mid", "r_8s"):
+        x = store[name]
+        _, db, S = F.log_mel(x, f_max=8000, return_parts=True)
+        St = tf(torch.from_numpy(x)).numpy().T
+        assert S.shape == St.shape == (1 + len(x) // 512, 64)
+        assert np.abs(S - St).max() <= 1e-4 * np.abs(S).max()
+        dbt = 10 * np.log10(np.maximum(1e-10, St)) - 10 * np.log10(max(1e-10, St.max()))
+        dbt = np.maximum(dbt, dbt.max() - 80)
+        assert np.abs(db - dbt).max() <= 1e-2
+
+
+def test_frame_counts():
+    for n in (1, 511, 512, 513, 32000, 65440, 128000, 130880, 512000):
+        T = F.log_mel(golden_signal(n, 1), f_max=8000).shape[0]
+        assert T == 1 + n // 512
+    assert F.log_mel(golden_signal(128000, 1), f_max=8000).shape == (251, 64)
+
+
+def test_resample_lengths():
+    for sr_in, n in ((4000, 32000), (2000, 5001), (8000, 12345), (44100, 44100)):
+        y = F.resample_torchaudio(golden_signal(n, 2, sr=sr_in), sr_in, 16000)
+        assert len(y) == int(np.ceil(n * 16000 / sr_in))
