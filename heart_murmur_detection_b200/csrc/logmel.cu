@@ -1,0 +1,469 @@
+// Fused framing + Hann window + 1024-point real FFT (two real frames per complex FFT)
+// + power + banded mel projection, then a per-clip dB / min-max epilogue.
+// Replaces pre_process_audio_mel_t (/root/reference/src/util.py:481-501).
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "api_common.h"
+#include "logmel_core.cuh"
+#include "tables.h"
+
+namespace hmfe {
+
+constexpr int kMaxSlots = 8;
+constexpr int kTileElems = 32 * kXStride;  // 1056 >= kBinsPad
+
+struct MelMeta {
+    int n_slots, total_trip, n_mels;
+    int trip[kMaxSlots], wbase[kMaxSlots];
+};
+
+struct LogmelBatch {
+    const float* wav;
+    float* out;
+    const int64_t* clip_off;     // [n_clips+1] ragged only
+    const int64_t* frame_off;    // [n_clips+1] ragged only
+    const int64_t* item_prefix;  // [n_clips+1] ragged only
+    unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
+    int64_t n_clips, n_items;
+    int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
+    int hop;
+};
+
+struct LogmelTables {
+    const float* win;   // 1024, 0.5 * Hann
+    const float2* tw;   // [32][32]
+    const float* melw;  // [total_trip][32]
+    const int* start;   // [n_slots][32]
+    const int* row;     // [n_slots][32]
+};
+
+HMFE_D float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+HMFE_D f32x2 shfl(f32x2 v, int src) {
+    return f32x2{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
+}
+
+template <typename V, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm) {
+    constexpr int NV = lanes_of<V>::value;
+    constexpr int FR = 2 * NV;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* s_tw = reinterpret_cast<float2*>(smem);
+    float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+    float* s_melw = s_win + 1024;
+    int* s_start = reinterpret_cast<int*>(s_melw + mm.total_trip * 32);
+    int* s_row = s_start + mm.n_slots * 32;
+    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + mm.total_trip * 128 + mm.n_slots * 256);
+    tbytes = (tbytes + 15) & ~(size_t)15;
+    xelem<V>* tile = reinterpret_cast<xelem<V>*>(smem + tbytes) + (threadIdx.x >> 5) * kTileElems;
+
+    for (int i = threadIdx.x; i < 1024; i += WARPS * 32) {
+        s_tw[i] = tb.tw[i];
+        s_win[i] = tb.win[i];
+    }
+    for (int i = threadIdx.x; i < mm.total_trip * 32; i += WARPS * 32) s_melw[i] = tb.melw[i];
+    for (int i = threadIdx.x; i < mm.n_slots * 32; i += WARPS * 32) {
+        s_start[i] = tb.start[i];
+        s_row[i] = tb.row[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t per_cta = (b.n_items + gridDim.x - 1) / gridDim.x;
+    const int64_t it_begin = (int64_t)blockIdx.x * per_cta;
+    const int64_t it_end = min(b.n_items, it_begin + per_cta);
+    int64_t clip = -1;
+
+    for (int64_t item = it_begin + warp; item < it_end; item += WARPS) {
+        int64_t q;
+        int nsamp, T;
+        const float* x;
+        float* o;
+        if (b.uniform_items > 0) {
+            clip = item / b.uniform_items;
+            q = item - clip * b.uniform_items;
+            nsamp = b.uniform_n;
+            T = b.uniform_T;
+            x = b.wav + clip * (int64_t)nsamp;
+            o = b.out + clip * (int64_t)T * mm.n_mels;
+        } else {
+            if (clip < 0) {  // first item of this warp: binary search, largest c with prefix[c] <= item
+                int64_t lo = 0, hi = b.n_clips;
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (b.item_prefix[mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                clip = lo;
+            }
+            while (item >= b.item_prefix[clip + 1]) ++clip;
+            q = item - b.item_prefix[clip];
+            const int64_t c0 = b.clip_off[clip];
+            nsamp = (int)(b.clip_off[clip + 1] - c0);
+            const int64_t f0g = b.frame_off[clip];
+            T = (int)(b.frame_off[clip + 1] - f0g);
+            x = b.wav + c0;
+            o = b.out + f0g * mm.n_mels;
+        }
+        const int f0 = (int)q * FR;
+
+        V re[32], im[32];
+        {
+            // frame f covers clip samples [f*hop - 512, f*hop + 512); outside the clip -> 0
+            int base[NV][2];
+            bool interior = true;
+#pragma unroll
+            for (int t = 0; t < NV; ++t)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int f = f0 + 2 * t + h;
+                    base[t][h] = f * b.hop - kNfft / 2;
+                    interior = interior && f < T && base[t][h] >= 0 && base[t][h] + kNfft <= nsamp;
+                    if (f >= T) base[t][h] = nsamp;  // every sample out of range -> zeros
+                }
+            if (interior) {
+                auto fetch = [&](int t, bool second, int n) -> float { return __ldg(x + base[t][second ? 1 : 0] + n); };
+                load_window<V>(lane, s_win, fetch, re, im);
+            } else {
+                auto fetch = [&](int t, bool second, int n) -> float {
+                    const int i = base[t][second ? 1 : 0] + n;
+                    return (i >= 0 && i < nsamp) ? __ldg(x + i) : 0.0f;
+                };
+                load_window<V>(lane, s_win, fetch, re, im);
+            }
+        }
+        fft_dit<32, V>(re, im);
+        apply_twiddle<V>(lane, s_tw, re, im);
+        exchange_store<V>(lane, tile, re, im);
+        __syncwarp();
+        exchange_load<V>(lane, tile, re, im);
+        __syncwarp();
+        fft_dit<32, V>(re, im);
+
+        {
+            const int src = (32 - lane) & 31;
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const V give_r = lane == 0 ? re[(32 - k1) & 31] : re[31 - k1];
+                const V give_i = lane == 0 ? im[(32 - k1) & 31] : im[31 - k1];
+                const V pr = shfl(give_r, src), pi = shfl(give_i, src);
+                tile[lane + 32 * k1] = frame_powers<V>(re[k1], im[k1], pr, pi);
+            }
+            if (lane == 0) tile[512] = frame_powers<V>(re[16], im[16], re[16], im[16]);
+        }
+        __syncwarp();
+
+        float vmax = 0.0f, vmin = INFINITY;
+        for (int s = 0; s < mm.n_slots; ++s) {
+            V aa, ab;
+            mel_slot<V>(lane, tile, s_melw + mm.wbase[s] * 32, s_start[s * 32 + lane], mm.trip[s], aa, ab);
+            const int row = s_row[s * 32 + lane];
+            if (row >= 0) {
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    const int fa = f0 + 2 * t;
+                    if (fa < T) {
+                        const float v = vget(aa, t);
+                        o[(int64_t)fa * mm.n_mels + row] = v;
+                        vmax = fmaxf(vmax, v);
+                        vmin = fminf(vmin, v);
+                    }
+                    if (fa + 1 < T) {
+                        const float v = vget(ab, t);
+                        o[(int64_t)(fa + 1) * mm.n_mels + row] = v;
+                        vmax = fmaxf(vmax, v);
+                        vmin = fminf(vmin, v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+        }
+        if (lane == 0) {
+            atomicMax(b.stats + 2 * clip, __float_as_uint(vmax));
+            atomicMin(b.stats + 2 * clip + 1, __float_as_uint(vmin));
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void logmel_init_stats_kernel(unsigned* stats, int64_t n_clips) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_clips) {
+        stats[2 * i] = 0u;
+        stats[2 * i + 1] = 0x7f800000u;  // +inf
+    }
+}
+
+// dB re clip max, floor at max - top_db, optional clip-wide min-max normalisation, in place.
+__global__ void __launch_bounds__(256)
+logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin, float top_db) {
+    for (int64_t clip = blockIdx.x; clip < b.n_clips; clip += gridDim.x) {
+        float* o;
+        int64_t count;
+        if (b.uniform_items > 0) {
+            o = b.out + clip * (int64_t)b.uniform_T * n_mels;
+            count = (int64_t)b.uniform_T * n_mels;
+        } else {
+            const int64_t f0 = b.frame_off[clip];
+            o = b.out + f0 * n_mels;
+            count = (b.frame_off[clip + 1] - f0) * n_mels;
+        }
+        const float pmax = __uint_as_float(b.stats[2 * clip]);
+        const float pmin = __uint_as_float(b.stats[2 * clip + 1]);
+        // numpy evaluates the scalar reference term in float64 and rounds once (oracle/librosa_restated.py)
+        const float ref_db = (float)(10.0 * log10(fmax((double)amin, (double)pmax)));
+        const float smax = 10.0f * log10f(fmaxf(amin, pmax)) - ref_db;
+        const float floor_db = smax - top_db;
+        const float smin = fmaxf(10.0f * log10f(fmaxf(amin, pmin)) - ref_db, floor_db);
+        const bool normalise = out_mode == HMFE_LOGMEL_OUT_NORMALISED && smax != smin;
+        const float denom = smax - smin;
+        float4* o4 = reinterpret_cast<float4*>(o);
+        const int64_t n4 = count >> 2;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 v = o4[i];
+            float* p = reinterpret_cast<float*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d = fmaxf(10.0f * log10f(fmaxf(amin, p[j])) - ref_db, floor_db);
+                if (normalise) d = (d - smin) / denom;
+                p[j] = d;
+            }
+            o4[i] = v;
+        }
+    }
+}
+
+}  // namespace hmfe
+
+using namespace hmfe;
+
+struct hmfe_logmel_plan {
+    int sample_rate, n_fft, hop, n_mels, n_bins, variant;
+    double f_min, f_max;
+    std::vector<float> mel_dense;
+    MelMeta meta;
+    float *d_win = nullptr, *d_melw = nullptr;
+    float2* d_tw = nullptr;
+    int *d_start = nullptr, *d_row = nullptr;
+    size_t table_smem = 0;
+    DescRing ring;
+    int last_launches = 0;
+    int sm_count = 148;
+    // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;  // triples: before power, after power, after finalize
+};
+
+template <typename T>
+static int upload_vec(const std::vector<T>& v, T** dptr) {
+    HMFE_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(1, v.size()) * sizeof(T)));
+    HMFE_CHECK_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return HMFE_OK;
+}
+
+template <typename V, int WARPS>
+static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    const size_t smem = p->table_smem + (size_t)WARPS * kTileElems * sizeof(xelem<V>);
+    auto kern = logmel_power_kernel<V, WARPS>;
+    HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (b.n_items + WARPS - 1) / WARPS;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));
+    LogmelTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
+    kern<<<grid, WARPS * 32, smem, st>>>(b, tb, p->meta);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
+extern "C" {
+
+int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
+                            double f_max, int variant) {
+    HMFE_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    if (n_fft != kNfft) {
+        set_error("n_fft=%d unsupported: the kernel is specialised for n_fft=1024 (src/util.py:482)", n_fft);
+        return HMFE_ERR_UNSUPPORTED;
+    }
+    HMFE_REQUIRE(hop >= 1 && hop <= 4096, "hop=%d out of range", hop);
+    HMFE_REQUIRE(n_mels >= 32 && n_mels % 32 == 0 && n_mels <= 32 * kMaxSlots, "n_mels=%d must be a multiple of 32 <= %d",
+                 n_mels, 32 * kMaxSlots);
+    HMFE_REQUIRE(sample_rate > 0 && f_min >= 0 && f_max > f_min && f_max <= 0.5 * sample_rate + 1e-9,
+                 "bad frequency range [%g, %g] for sr=%d", f_min, f_max, sample_rate);
+    HMFE_REQUIRE(variant >= 0 && variant <= 2, "bad variant %d", variant);
+    hmfe_logmel_plan* p = new (std::nothrow) hmfe_logmel_plan();
+    HMFE_REQUIRE(p != nullptr, "out of host memory");
+    p->sample_rate = sample_rate;
+    p->n_fft = n_fft;
+    p->hop = hop;
+    p->n_mels = n_mels;
+    p->n_bins = n_fft / 2 + 1;
+    p->f_min = f_min;
+    p->f_max = f_max;
+    p->variant = variant == HMFE_VARIANT_AUTO ? HMFE_VARIANT_PACKED : variant;
+    p->sm_count = device_sm_count();
+    p->mel_dense = mel_filterbank_slaney(sample_rate, n_fft, n_mels, f_min, f_max);
+    const BandedMel bm = build_banded(p->mel_dense, n_mels, p->n_bins);
+    p->meta.n_slots = bm.n_slots;
+    p->meta.total_trip = bm.total_trip;
+    p->meta.n_mels = n_mels;
+    for (int s = 0; s < bm.n_slots; ++s) {
+        p->meta.trip[s] = bm.trip[s];
+        p->meta.wbase[s] = bm.wbase[s];
+    }
+    const std::vector<float> win = half_hann_periodic(n_fft);
+    const std::vector<float> tw = twiddle_plane(n_fft, 32);
+    int rc = upload_vec(win, &p->d_win);
+    if (rc == HMFE_OK) rc = upload_vec(tw, reinterpret_cast<float**>(&p->d_tw));
+    if (rc == HMFE_OK) rc = upload_vec(bm.w, &p->d_melw);
+    if (rc == HMFE_OK) rc = upload_vec(bm.start, &p->d_start);
+    if (rc == HMFE_OK) rc = upload_vec(bm.row, &p->d_row);
+    if (rc != HMFE_OK) {
+        hmfe_logmel_plan_destroy(p);
+        return rc;
+    }
+    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + bm.total_trip * 128 + bm.n_slots * 256);
+    p->table_smem = (tbytes + 15) & ~(size_t)15;
+    *plan = p;
+    return HMFE_OK;
+}
+
+void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_win);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_melw);
+    cudaFree(p->d_start);
+    cudaFree(p->d_row);
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    delete p;
+}
+
+int64_t hmfe_logmel_num_frames(int64_t n_samples, int hop) { return hop > 0 && n_samples >= 0 ? 1 + n_samples / hop : -1; }
+
+int hmfe_logmel_mel_basis(const hmfe_logmel_plan* p, float* h_out) {
+    HMFE_REQUIRE(p && h_out, "NULL argument");
+    std::copy(p->mel_dense.begin(), p->mel_dense.end(), h_out);
+    return HMFE_OK;
+}
+
+int hmfe_logmel_last_launches(const hmfe_logmel_plan* p) { return p ? p->last_launches : 0; }
+
+int hmfe_logmel_set_profile(hmfe_logmel_plan* p, int enable) {
+    HMFE_REQUIRE(p, "NULL plan");
+    p->profile = enable != 0;
+    return HMFE_OK;
+}
+
+int hmfe_logmel_profile_ms(hmfe_logmel_plan* p, double* power_ms, double* finalize_ms, int* n_calls) {
+    HMFE_REQUIRE(p, "NULL plan");
+    double a = 0, f = 0;
+    const int n = (int)(p->prof_events.size() / 3);
+    for (int i = 0; i < n; ++i) {
+        float t0 = 0, t1 = 0;
+        HMFE_CHECK_CUDA(cudaEventSynchronize(p->prof_events[3 * i + 2]));
+        HMFE_CHECK_CUDA(cudaEventElapsedTime(&t0, p->prof_events[3 * i], p->prof_events[3 * i + 1]));
+        HMFE_CHECK_CUDA(cudaEventElapsedTime(&t1, p->prof_events[3 * i + 1], p->prof_events[3 * i + 2]));
+        a += t0;
+        f += t1;
+    }
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    p->prof_events.clear();
+    if (power_ms) *power_ms = a;
+    if (finalize_ms) *finalize_ms = f;
+    if (n_calls) *n_calls = n;
+    return HMFE_OK;
+}
+
+int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, float* d_out,
+                      int out_mode, void* stream) {
+    HMFE_REQUIRE(p && h_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
+    HMFE_REQUIRE(out_mode >= 0 && out_mode <= 2, "bad out_mode %d", out_mode);
+    p->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_wav && d_out, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int FR = p->variant == HMFE_VARIANT_PACKED ? 4 : 2;
+
+    bool uniform = true;
+    const int64_t n0 = h_offsets[1] - h_offsets[0];
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30, "clip %lld has invalid length %lld", (long long)i, (long long)n);
+        uniform = uniform && n == n0;
+    }
+    uniform = uniform && h_offsets[0] == 0;
+
+    LogmelBatch b{};
+    b.wav = d_wav;
+    b.out = d_out;
+    b.n_clips = n_clips;
+    b.hop = p->hop;
+    const size_t desc_bytes = uniform ? 0 : 3 * (size_t)(n_clips + 1) * sizeof(int64_t);
+    const size_t total_bytes = desc_bytes + (size_t)n_clips * 2 * sizeof(unsigned);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = p->ring.acquire(total_bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    if (uniform) {
+        const int64_t T = 1 + n0 / p->hop;
+        b.uniform_n = (int)n0;
+        b.uniform_T = (int)T;
+        b.uniform_items = (int)((T + FR - 1) / FR);
+        b.n_items = (int64_t)b.uniform_items * n_clips;
+    } else {
+        int64_t* hc = static_cast<int64_t*>(hbuf);
+        int64_t* hf = hc + (n_clips + 1);
+        int64_t* hi = hf + (n_clips + 1);
+        hf[0] = hi[0] = 0;
+        for (int64_t i = 0; i < n_clips; ++i) {
+            const int64_t T = 1 + (h_offsets[i + 1] - h_offsets[i]) / p->hop;
+            hc[i] = h_offsets[i];
+            hf[i + 1] = hf[i] + T;
+            hi[i + 1] = hi[i] + (T + FR - 1) / FR;
+        }
+        hc[n_clips] = h_offsets[n_clips];
+        b.n_items = hi[n_clips];
+        int64_t* dc = static_cast<int64_t*>(dbuf);
+        b.clip_off = dc;
+        b.frame_off = dc + (n_clips + 1);
+        b.item_prefix = dc + 2 * (n_clips + 1);
+        int rc = p->ring.upload(slot, desc_bytes, st);
+        if (rc != HMFE_OK) return rc;
+    }
+    b.stats = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dbuf) + desc_bytes);
+
+    logmel_init_stats_kernel<<<(unsigned)((n_clips + 255) / 256), 256, 0, st>>>(b.stats, n_clips);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (p->profile) {
+        for (int i = 0; i < 3; ++i) {
+            HMFE_CHECK_CUDA(cudaEventCreate(&ev[i]));
+            p->prof_events.push_back(ev[i]);
+        }
+        HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
+    }
+    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 4>(p, b, st) : launch_power<float, 8>(p, b, st);
+    if (rc != HMFE_OK) return rc;
+    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
+    p->last_launches = 2;
+    if (out_mode != HMFE_LOGMEL_OUT_POWER) {
+        const int grid = (int)std::min<int64_t>(n_clips, (int64_t)p->sm_count * 8);
+        logmel_finalize_kernel<<<grid, 256, 0, st>>>(b, p->n_mels, out_mode, 1e-10f, 80.0f);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        p->last_launches = 3;
+    }
+    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[2], st));
+    return p->ring.release(slot, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Lane-level phases of the fused STFT-power + mel kernel (n_fft = 1024).
+//
+// One warp transforms 2*NV consecutive frames per iteration (NV = 1 for V=float,
+// 2 for V=f32x2): frames (a, b) are packed as real / imaginary part of one complex
+// 1024-point FFT, split 1024 = 32 x 32:
+//   pass 1  lane = n1, registers = n2 : 32-point FFT over n2 (in registers)
+//   twiddle W_1024^(n1*k2), per-lane plane read from shared memory
+//   exchange through a padded [32][33] shared-memory tile (conflict free)
+//   pass 2  lane = k2, registers = n1 : 32-point FFT over n1 -> bin k = k2 + 32*k1
+//   separation |X_a[k]|^2, |X_b[k]|^2 from Z[k] and Z[1024-k] (partner lane via shuffle)
+//   sparse banded mel projection from the power tile in shared memory
+// Every phase is a __host__ __device__ template taking the lane id explicitly, so
+// csrc/host_check.cu can run the identical arithmetic on the CPU.
+#pragma once
+#include "fft_core.cuh"
+
+namespace hmfe {
+
+constexpr int kNfft = 1024;
+constexpr int kBinsPad = 576;   // power tile rows (>= 513 + slack), in exchange-tile elements
+constexpr int kXStride = 33;    // exchange tile row stride (elements)
+
+// exchange / power tile element: (re, im) or (p_a, p_b)
+template <typename V>
+struct xelem;
+template <>
+struct __align__(8) xelem<float> {
+    float a, b;
+};
+template <>
+struct __align__(16) xelem<f32x2> {
+    f32x2 a, b;
+};
+
+// ---- phase 1: windowed samples -> bit-reversed registers.  `fetch(t, n)` returns sample n
+// (0..1023) of transform t's frame a (im=false) / frame b (im=true), already bounds-handled.
+template <typename V, typename Fetch>
+HMFE_HD void load_window(int lane, const float* __restrict__ win, Fetch fetch, V (&re)[32], V (&im)[32]) {
+    constexpr int NV = lanes_of<V>::value;
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+        const int n = lane + 32 * n2;
+        const float w = win[n];
+        V xa, xb;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            vput(xa, t, fetch(t, false, n));
+            vput(xb, t, fetch(t, true, n));
+        }
+        re[brev(n2, 5)] = vmuls(xa, w);
+        im[brev(n2, 5)] = vmuls(xb, w);
+    }
+}
+
+// ---- twiddle: Y[k2] *= W^(lane*k2), plane[k2*32 + lane] = (cos, -sin)
+template <typename V>
+HMFE_HD void apply_twiddle(int lane, const float2* __restrict__ plane, V (&re)[32], V (&im)[32]) {
+#pragma unroll
+    for (int k2 = 1; k2 < 32; ++k2) {
+        const float2 w = plane[k2 * 32 + lane];
+        const V nr = vfnmas(im[k2], w.y, vmuls(re[k2], w.x));  // re*wr - im*wi
+        const V ni = vfmas(im[k2], w.x, vmuls(re[k2], w.y));   // re*wi + im*wr
+        re[k2] = nr;
+        im[k2] = ni;
+    }
+}
+
+template <typename V>
+HMFE_HD void exchange_store(int lane, xelem<V>* tile, const V (&re)[32], const V (&im)[32]) {
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) tile[k2 * kXStride + lane] = xelem<V>{re[k2], im[k2]};
+}
+// loads into bit-reversed positions, ready for the second DIT pass
+template <typename V>
+HMFE_HD void exchange_load(int lane, const xelem<V>* tile, V (&re)[32], V (&im)[32]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+        const xelem<V> e = tile[lane * kXStride + n1];
+        re[brev(n1, 5)] = e.a;
+        im[brev(n1, 5)] = e.b;
+    }
+}
+
+// ---- separation
+// power of both packed frames at bin lane + 32*k1 given own (zr, zi) and partner (pr, pi)
+template <typename V>
+HMFE_HD xelem<V> frame_powers(V zr, V zi, V pr, V pi) {
+    const V u = vadd(zr, pr), v = vsub(zi, pi);
+    const V s = vadd(zi, pi), d = vsub(pr, zr);
+    xelem<V> o;
+    o.a = vfma(v, v, vmul(u, u));
+    o.b = vfma(d, d, vmul(s, s));
+    return o;
+}
+
+// ---- mel: accumulate one slot for this lane from the power tile
+template <typename V>
+HMFE_HD void mel_slot(int lane, const xelem<V>* __restrict__ ptile, const float* __restrict__ w, int start, int trip,
+                      V& acc_a, V& acc_b) {
+    acc_a = V{};
+    acc_b = V{};
+    const xelem<V>* p = ptile + start;
+    const float* wl = w + lane;
+#pragma unroll 4
+    for (int i = 0; i < trip; ++i) {
+        const float wi = wl[i * 32];
+        const xelem<V> e = p[i];
+        acc_a = vfmas(e.a, wi, acc_a);
+        acc_b = vfmas(e.b, wi, acc_b);
+    }
+}
+
+}  // namespace hmfe

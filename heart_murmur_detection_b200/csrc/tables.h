@@ -1,0 +1,179 @@
+// Host-side constant tables (float64 math, rounded once to float32).
+//
+// The formulas are the published definitions the reference's libraries use:
+//   * periodic Hann window + Slaney mel scale / Slaney-normalised triangles
+//     (librosa 0.10.1 filters.mel, called from /root/reference/src/util.py:484-492)
+//   * Kaldi HTK-mel triangles and symmetric Hann window
+//     (torchaudio.compliance.kaldi.get_mel_banks / _feature_window_function,
+//      called from /root/reference/src/util.py:845-856)
+// plus the layouts the kernels consume (per-lane twiddle planes, banded mel slots).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace hmfe {
+
+static const double kPi = 3.14159265358979323846;
+
+// ------------------------------------------------------------------ windows
+// 0.5 * periodic Hann(n).  The 0.5 folds the 1/4 of the two-real-frames-in-one-complex-FFT
+// separation |X|^2 = |Z[k] +- conj Z[N-k]|^2 / 4 into the window (exact: power of two).
+inline std::vector<float> half_hann_periodic(int n) {
+    std::vector<float> w(n);
+    for (int k = 0; k < n; ++k) {
+        const double h = 0.5 - 0.5 * cos(2.0 * kPi * k / n);
+        w[k] = 0.5f * (float)h;
+    }
+    return w;
+}
+// torch.hann_window(n, periodic=False) scaled by 0.5 (same folding as above)
+inline std::vector<float> half_hann_symmetric(int n) {
+    std::vector<float> w(n);
+    for (int k = 0; k < n; ++k) {
+        const double h = 0.5 - 0.5 * cos(2.0 * kPi * k / (n - 1));
+        w[k] = 0.5f * (float)h;
+    }
+    return w;
+}
+
+// ------------------------------------------------------------------ Slaney mel (librosa)
+inline double hz_to_mel_slaney(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+inline double mel_to_hz_slaney(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// dense [n_mels][n_fft/2+1], float32, Slaney norm
+inline std::vector<float> mel_filterbank_slaney(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+    const int n_bins = n_fft / 2 + 1;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel_slaney(fmin), m_hi = hz_to_mel_slaney(fmax);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        // numpy.linspace: start + i*step, last point exact
+        const double step = (m_hi - m_lo) / (n_mels + 1);
+        const double m = (i == n_mels + 1) ? m_hi : m_lo + i * step;
+        mel_f[i] = mel_to_hz_slaney(m);
+    }
+    std::vector<float> w((size_t)n_mels * n_bins, 0.0f);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < n_bins; ++k) {
+            const double f = (double)k * sr / n_fft;
+            const double lower = -(mel_f[i] - f) / fd0;
+            const double upper = (mel_f[i + 2] - f) / fd1;
+            const float tri = (float)std::max(0.0, std::min(lower, upper));  // float32 store
+            w[(size_t)i * n_bins + k] = (float)((double)tri * enorm);         // float32 *= float64
+        }
+    }
+    return w;
+}
+
+// ------------------------------------------------------------------ Kaldi HTK mel (torchaudio)
+inline double mel_htk(double f) { return 1127.0 * log(1.0 + f / 700.0); }
+
+// dense [n_mels][padded/2 + 1]; last column (Nyquist) is zero as in kaldi.fbank
+inline std::vector<float> mel_banks_kaldi(int n_mels, int padded, double sr, double low, double high) {
+    const int n_fft_bins = padded / 2, n_bins = n_fft_bins + 1;
+    const double nyq = 0.5 * sr;
+    if (high <= 0.0) high += nyq;
+    const double bin_w = sr / padded;
+    const double mlo = mel_htk(low), mhi = mel_htk(high);
+    const double delta = (mhi - mlo) / (n_mels + 1);
+    std::vector<float> w((size_t)n_mels * n_bins, 0.0f);
+    for (int i = 0; i < n_mels; ++i) {
+        const double left = mlo + i * delta, center = mlo + (i + 1.0) * delta, right = mlo + (i + 2.0) * delta;
+        for (int k = 0; k < n_fft_bins; ++k) {
+            const double m = mel_htk(bin_w * k);
+            const double up = (m - left) / (center - left), down = (right - m) / (right - center);
+            w[(size_t)i * n_bins + k] = (float)std::max(0.0, std::min(up, down));
+        }
+    }
+    return w;
+}
+
+// ------------------------------------------------------------------ banded mel slots
+// The kernels evaluate the sparse mel projection with one mel row per lane per "slot".
+// Rows are sorted by support length so the 32 rows of a slot have similar trip counts;
+// every (slot, lane) gets a window [start, start+trip) inside [0, n_bins) that covers the
+// row's support, zero weights elsewhere.  Weight plane layout: w[(wbase[s] + i)*32 + lane].
+struct BandedMel {
+    int n_mels = 0, n_bins = 0, n_slots = 0;
+    std::vector<int> trip, wbase;   // per slot
+    std::vector<int> start, row;    // per (slot, lane); row = -1 for padding lanes
+    std::vector<float> w;
+    int total_trip = 0;
+};
+
+inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n_bins) {
+    BandedMel b;
+    b.n_mels = n_mels;
+    b.n_bins = n_bins;
+    std::vector<int> first(n_mels, 0), len(n_mels, 0), order(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < n_bins; ++k)
+            if (dense[(size_t)m * n_bins + k] != 0.0f) {
+                if (lo < 0) lo = k;
+                hi = k;
+            }
+        first[m] = lo < 0 ? 0 : lo;
+        len[m] = lo < 0 ? 0 : hi - lo + 1;
+        order[m] = m;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return len[a] > len[c]; });
+    b.n_slots = (n_mels + 31) / 32;
+    b.trip.assign(b.n_slots, 1);
+    b.wbase.assign(b.n_slots, 0);
+    b.start.assign((size_t)b.n_slots * 32, 0);
+    b.row.assign((size_t)b.n_slots * 32, -1);
+    for (int s = 0; s < b.n_slots; ++s) {
+        int t = 1;
+        for (int l = 0; l < 32; ++l) {
+            const int idx = s * 32 + l;
+            if (idx < n_mels) t = std::max(t, len[order[idx]]);
+        }
+        b.trip[s] = t;
+        b.wbase[s] = b.total_trip;
+        b.total_trip += t;
+    }
+    b.w.assign((size_t)b.total_trip * 32, 0.0f);
+    for (int s = 0; s < b.n_slots; ++s)
+        for (int l = 0; l < 32; ++l) {
+            const int idx = s * 32 + l;
+            if (idx >= n_mels) continue;
+            const int m = order[idx];
+            const int st = std::max(0, std::min(first[m], n_bins - b.trip[s]));
+            b.start[idx] = st;
+            b.row[idx] = m;
+            for (int i = 0; i < b.trip[s]; ++i) {
+                const int k = st + i;
+                if (k < n_bins) b.w[((size_t)b.wbase[s] + i) * 32 + l] = dense[(size_t)m * n_bins + k];
+            }
+        }
+    return b;
+}
+
+// ------------------------------------------------------------------ inter-pass twiddles
+// N = 32 * n2 point transform split as n = n1 + 32*n2, k = n2_count*k1 + k2:
+// plane[k2][lane] = exp(-2*pi*i*lane*k2/N) stored as (cos, -sin).
+inline std::vector<float> twiddle_plane(int n, int n_k2) {
+    std::vector<float> t((size_t)n_k2 * 32 * 2);
+    for (int k2 = 0; k2 < n_k2; ++k2)
+        for (int l = 0; l < 32; ++l) {
+            const double a = 2.0 * kPi * ((double)l * k2) / n;
+            t[((size_t)k2 * 32 + l) * 2 + 0] = (float)cos(a);
+            t[((size_t)k2 * 32 + l) * 2 + 1] = (float)(-sin(a));
+        }
+    return t;
+}
+
+}  // namespace hmfe

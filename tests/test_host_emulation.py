@@ -1,0 +1,34 @@
+"""CPU emulation of the warp algorithm (csrc/host_check.cu: same __host__ __device__ templates
+as the kernels, lanes looped on the host) against the oracle.  Validates the FFT index math,
+twiddle planes, partner-lane separation, banded mel and float32 accuracy without a GPU."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from signals import golden_signal
+
+
+@pytest.fixture(scope="module")
+def host_check():
+    from heart_murmur_detection_b200 import build
+
+    return build.build_host_check()
+
+
+@pytest.mark.parametrize("variant", ["scalar", "packed"])
+def test_logmel_power_emulation(host_check, variant, tmp_path):
+    from oracle import frontend as F
+
+    for n, seed, fmax in [(128000, 5, 8000), (20000, 3, 8000), (1, 1, 8000), (513, 2, 2000), (40001, 4, 2000)]:
+        x = golden_signal(n, seed)
+        fin, fout = tmp_path / "in.f32", tmp_path / "out.f32"
+        x.tofile(fin)
+        subprocess.check_call([host_check, "logmel", variant, "512", "64", "50", str(fmax), str(fin), str(fout)])
+        P = np.fromfile(fout, dtype=np.float32).reshape(-1, 64)
+        _, db, S = F.log_mel(x, f_max=fmax, return_parts=True)
+        assert P.shape == S.shape
+        assert np.abs(P - S).max() <= 1e-4 * np.abs(S).max()
+        dbp = 10 * np.log10(np.maximum(1e-10, P)) - 10 * np.log10(max(1e-10, P.max()))
+        dbp = np.maximum(dbp, dbp.max() - 80)
+        assert np.abs(dbp - db).max() <= 1e-2

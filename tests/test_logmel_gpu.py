@@ -1,0 +1,137 @@
+"""Parity of the CUDA log-mel path (through the C ABI) with the oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8c):
+  mel power (linear spectrum): |delta| <= 1e-4 * max|S| per clip
+  dB after top_db clipping:    <= 1e-2 dB max-abs
+  normalised [0,1] output:     <= 2e-4 max-abs
+  frame counts / layout:       exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from signals import golden_signal
+
+pytestmark = pytest.mark.gpu
+
+POWER_RTOL = 1e-4
+DB_TOL = 1e-2
+NORM_TOL = 2e-4
+
+
+def _oracle(x, f_max=8000, n_mels=64, hop=512):
+    from oracle import frontend as F
+
+    return F.log_mel(x, f_max=f_max, n_mels=n_mels, hop=hop, return_parts=True)
+
+
+def _run(plan, clips, mode):
+    offsets = np.zeros(len(clips) + 1, dtype=np.int64)
+    np.cumsum([len(c) for c in clips], out=offsets[1:])
+    wav = torch.from_numpy(np.concatenate(clips).astype(np.float32)).cuda()
+    out, fo = plan(wav, offsets, mode=mode)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    return [out[fo[i] : fo[i + 1]] for i in range(len(clips))]
+
+
+def _check(plan, clips, f_max=8000, hop=512):
+    P = _run(plan, clips, "power")
+    D = _run(plan, clips, "db")
+    N = _run(plan, clips, "normalised")
+    for x, p, d, n in zip(clips, P, D, N):
+        norm, db, S = _oracle(x, f_max=f_max, n_mels=plan.n_mels, hop=hop)
+        assert p.shape == S.shape == (1 + len(x) // hop, plan.n_mels)
+        assert np.abs(p - S).max() <= POWER_RTOL * max(np.abs(S).max(), 1e-30)
+        assert np.abs(d - db).max() <= DB_TOL
+        assert np.abs(n - norm).max() <= NORM_TOL
+
+
+@pytest.mark.parametrize("variant", ["scalar", "packed"])
+def test_ragged_batch_matches_oracle(variant):
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    plan = LogMelPlan(f_max=8000, variant=variant)
+    lens = [128000, 20000, 1, 511, 512, 513, 1023, 1024, 1025, 2047, 2049, 90000, 32000, 65440, 130880, 300000]
+    clips = [golden_signal(n, seed=7 + i) for i, n in enumerate(lens)]
+    _check(plan, clips)
+
+
+@pytest.mark.parametrize("variant", ["scalar", "packed"])
+def test_uniform_batch_matches_oracle(variant):
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    plan = LogMelPlan(f_max=8000, variant=variant)
+    clips = [golden_signal(128000, seed=100 + i) for i in range(9)]
+    _check(plan, clips)
+    # CirCor-shaped: 8 s -> [251, 64]
+    assert _run(plan, clips[:1], "normalised")[0].shape == (251, 64)
+
+
+def test_default_fmax_2000_and_other_hop():
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    clips = [golden_signal(n, seed=3 + n % 11) for n in (48000, 7777, 128000)]
+    _check(LogMelPlan(f_max=2000), clips, f_max=2000)
+    _check(LogMelPlan(f_max=8000, hop=256), clips, hop=256)
+    _check(LogMelPlan(f_max=8000, hop=320, n_mels=128), clips, hop=320)
+
+
+def test_mel_basis_matches_oracle():
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+    from oracle import librosa_restated as lr
+
+    for fmax in (8000, 2000):
+        ours = LogMelPlan(f_max=fmax).mel_basis()
+        ref = lr.mel_filterbank(16000, 1024, n_mels=64, fmin=50, fmax=fmax)
+        assert np.abs(ours - ref).max() <= 1e-6 * ref.max()
+        np.testing.assert_array_equal(ours == 0, ref == 0)
+
+
+def test_silent_and_constant_clips():
+    """All-zero clip takes the reference's max == min branch (src/util.py:495-499): zeros out."""
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    plan = LogMelPlan(f_max=8000)
+    clips = [np.zeros(4000, np.float32), golden_signal(30000, 5), np.zeros(1, np.float32), np.full(9000, 0.25, np.float32)]
+    N = _run(plan, clips, "normalised")
+    np.testing.assert_array_equal(N[0], np.zeros((8, 64), np.float32))
+    np.testing.assert_array_equal(N[2], np.zeros((1, 64), np.float32))
+    _check(plan, clips[1:2] + clips[3:])
+
+
+def test_golden_fixture_r8s():
+    """Committed fixture produced by executing the reference's pre_process_audio_mel_t."""
+    import json
+    import os
+
+    from cases import RECORDINGS, SR
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    arr = {k.replace("|", "/"): v for k, v in np.load(os.path.join(here, "golden", "ref_util.npz")).items()}
+    rec = {name: golden_signal(n, seed, SR, lead, tail) for name, n, seed, lead, tail in RECORDINGS}
+    for name, fmax in (("r_8s", 8000), ("r_8s", 2000), ("r_short", 8000)):
+        got = _run(LogMelPlan(f_max=fmax), [rec[name]], "normalised")[0]
+        assert np.abs(got - arr[f"logmel/{name}/{fmax}"]).max() <= NORM_TOL
+
+
+def test_size_independent_properties_at_full_size():
+    """C1 at full size (1000 x 8 s): every clip's normalised output spans exactly [0, 1], and a
+    batch result equals the per-clip results (batching must not couple clips)."""
+    from heart_murmur_detection_b200 import synth
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    plan = LogMelPlan(f_max=8000)
+    lens = synth.clip_lengths("c1", 1000)
+    wav, off = synth.make_batch(lens, base_seed=11, device="cuda")
+    out, fo = plan(wav, off)
+    out = out.view(1000, 251, 64)
+    assert torch.all(out.amax(dim=(1, 2)) == 1.0) and torch.all(out.amin(dim=(1, 2)) == 0.0)
+    assert torch.isfinite(out).all()
+    for i in (0, 499, 999):
+        single, _ = plan(wav[off[i] : off[i + 1]].clone(), np.array([0, lens[i]]))
+        assert torch.equal(single, out[i])
+    # scale invariance of the normalised output (dB re max): x -> 4x only shifts the floor
+    out4, _ = plan(wav[: off[8]] * 4.0, off[:9])
+    assert (out4.view(8, 251, 64) - out[:8]).abs().max() <= 1e-5
