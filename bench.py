@@ -36,6 +36,23 @@ WORKLOADS = {
 # ----------------------------------------------------------------------------- CPU reference arm
 
 
+_BLAS_LIMIT = None
+
+
+def _cpu_worker_init():
+    """One BLAS thread per worker process: the pool already uses every core."""
+    global _BLAS_LIMIT
+    try:
+        from threadpoolctl import threadpool_limits
+
+        _BLAS_LIMIT = threadpool_limits(1)
+    except Exception:  # pragma: no cover
+        pass
+    import torch
+
+    torch.set_num_threads(1)
+
+
 def _cpu_logmel_one(x):
     from oracle import frontend as F
 
@@ -56,7 +73,7 @@ def cpu_reference_c1(n_clips: int, repeats: int = 1):
     ctx = mp.get_context("fork")
     torch.set_num_threads(1)
     best = None
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
         pool.map(_cpu_logmel_one, clips[: 2 * cores])  # warm-up (imports, page-in)
         for _ in range(repeats):
             t0 = time.perf_counter()

@@ -49,10 +49,75 @@ hmfe_logmel_mel_basis = _sig("hmfe_logmel_mel_basis", C.c_int, c_voidp, c_voidp)
 hmfe_logmel_batch = _sig(
     "hmfe_logmel_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
 )
+hmfe_logmel_batch_views = _sig(
+    "hmfe_logmel_batch_views", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
+)
 hmfe_logmel_last_launches = _sig("hmfe_logmel_last_launches", C.c_int, c_voidp)
 hmfe_logmel_set_profile = _sig("hmfe_logmel_set_profile", C.c_int, c_voidp, C.c_int)
 hmfe_logmel_profile_ms = _sig(
     "hmfe_logmel_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)
+)
+
+
+hmfe_ctx_create = _sig("hmfe_ctx_create", C.c_int, C.POINTER(c_voidp))
+hmfe_ctx_destroy = _sig("hmfe_ctx_destroy", None, c_voidp)
+hmfe_ctx_last_launches = _sig("hmfe_ctx_last_launches", C.c_int, c_voidp)
+
+hmfe_trim_num_frames = _sig("hmfe_trim_num_frames", C.c_int64, C.c_int64, C.c_int, C.c_int)
+hmfe_trim_batch = _sig(
+    "hmfe_trim_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, C.c_int, C.c_float, c_voidp, c_voidp
+)
+
+
+class GatherDesc(C.Structure):
+    """struct hmfe_gather_desc (include/hmfe.h)."""
+
+    _fields_ = [
+        ("src_off", C.c_int64), ("dst_off", C.c_int64), ("len", C.c_int32), ("period", C.c_int32),
+        ("a_end", C.c_int32), ("a_phase", C.c_int32), ("b_end", C.c_int32), ("b_start", C.c_int32),
+    ]
+
+
+class CropDesc(C.Structure):
+    """struct hmfe_crop_desc (include/hmfe.h)."""
+
+    _fields_ = [("src_row", C.c_int64), ("n_rows", C.c_int32), ("spec_id", C.c_int32), ("gain", C.c_float),
+                ("reserved", C.c_int32)]
+
+
+hmfe_gather_batch = _sig("hmfe_gather_batch", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp)
+hmfe_iir_sos_batch = _sig(
+    "hmfe_iir_sos_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, c_voidp
+)
+
+hmfe_fbank_plan_create = _sig(
+    "hmfe_fbank_plan_create", C.c_int, C.POINTER(c_voidp), C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+    C.c_double, C.c_double,
+)
+hmfe_fbank_plan_destroy = _sig("hmfe_fbank_plan_destroy", None, c_voidp)
+hmfe_fbank_num_frames = _sig("hmfe_fbank_num_frames", C.c_int64, c_voidp, C.c_int64)
+hmfe_fbank_mel_basis = _sig("hmfe_fbank_mel_basis", C.c_int, c_voidp, c_voidp)
+hmfe_fbank_batch = _sig("hmfe_fbank_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp)
+hmfe_fbank_batch_views = _sig(
+    "hmfe_fbank_batch_views", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
+)
+hmfe_fbank_last_launches = _sig("hmfe_fbank_last_launches", C.c_int, c_voidp)
+
+hmfe_resample_plan_create = _sig(
+    "hmfe_resample_plan_create", C.c_int, C.POINTER(c_voidp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double
+)
+hmfe_resample_plan_destroy = _sig("hmfe_resample_plan_destroy", None, c_voidp)
+hmfe_resample_out_len = _sig("hmfe_resample_out_len", C.c_int64, c_voidp, C.c_int64)
+hmfe_resample_taps = _sig("hmfe_resample_taps", C.c_int, c_voidp, C.POINTER(C.c_int), C.POINTER(C.c_int), c_voidp)
+hmfe_resample_batch = _sig("hmfe_resample_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp)
+hmfe_resample_last_launches = _sig("hmfe_resample_last_launches", C.c_int, c_voidp)
+
+hmfe_spec_mean_batch = _sig(
+    "hmfe_spec_mean_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp, c_voidp
+)
+hmfe_spec_crop_batch = _sig(
+    "hmfe_spec_crop_batch", C.c_int, c_voidp, c_voidp, C.c_int, c_voidp, C.c_int64, c_voidp, c_voidp, c_voidp, C.c_int,
+    c_voidp,
 )
 
 

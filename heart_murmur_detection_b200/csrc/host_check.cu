@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <math.h>
+
 #include "logmel_core.cuh"
 #include "tables.h"
 
@@ -77,6 +79,100 @@ static void run_logmel(const std::vector<float>& x, int hop, int n_mels, double 
     }
 }
 
+// Mirrors fbank_kernel (kaldi_fbank.cu) lane for lane.
+static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float>& out) {
+    const int win = 400, shift = 160, nsamp = (int)x.size();
+    const float preemph = 0.97f;
+    const int m = nsamp >= win ? 1 + (nsamp - win) / shift : 0;
+    const std::vector<float> dense = mel_banks_kaldi(n_mels, 512, 16000.0, 20.0, 0.0);
+    const BandedMel bm = build_banded(dense, n_mels, 257);
+    const std::vector<float> w = half_hann_symmetric(win);
+    const std::vector<float> twv = twiddle_plane(512, 16);
+    const float2* tw = reinterpret_cast<const float2*>(twv.data());
+    out.assign((size_t)m * n_mels, 0.0f);
+    const int PS = 320;
+    std::vector<xelem<float>> tile(32 * kXStride);
+    struct Lane {
+        f32x2 re[16], im[16];
+        float zr[32], zi[32];
+    };
+    std::vector<Lane> L(32);
+    for (int f0 = 0; f0 < m; f0 += 4) {
+        float mean[4];
+        for (int t = 0; t < 4; ++t) {
+            float acc = 0.0f;
+            if (f0 + t < m)
+                for (int n = 0; n < win; ++n) acc += x[(size_t)(f0 + t) * shift + n];
+            mean[t] = acc / (float)win;
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            Lane& l = L[lane];
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int n = lane + 32 * n2;
+                float y[4];
+                for (int t = 0; t < 4; ++t) {
+                    float v = 0.0f;
+                    if (f0 + t < m && n < win) {
+                        const float* xf = x.data() + (size_t)(f0 + t) * shift;
+                        const float a = xf[n] - mean[t], pv = xf[n > 0 ? n - 1 : 0] - mean[t];
+                        v = (a - preemph * pv) * w[n];
+                    }
+                    y[t] = v;
+                }
+                l.re[brev(n2, 4)] = f32x2{y[0], y[2]};
+                l.im[brev(n2, 4)] = f32x2{y[1], y[3]};
+            }
+            fft_dit<16, f32x2>(l.re, l.im);
+            for (int k2 = 1; k2 < 16; ++k2) {
+                const float2 t2 = tw[k2 * 32 + lane];
+                const f32x2 nr = vfnmas(l.im[k2], t2.y, vmuls(l.re[k2], t2.x));
+                const f32x2 ni = vfmas(l.im[k2], t2.x, vmuls(l.re[k2], t2.y));
+                l.re[k2] = nr;
+                l.im[k2] = ni;
+            }
+            for (int k2 = 0; k2 < 16; ++k2) {
+                tile[k2 * kXStride + lane] = xelem<float>{l.re[k2].x, l.im[k2].x};
+                tile[(16 + k2) * kXStride + lane] = xelem<float>{l.re[k2].y, l.im[k2].y};
+            }
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            Lane& l = L[lane];
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const xelem<float> e = tile[lane * kXStride + n1];
+                l.zr[brev(n1, 5)] = e.a;
+                l.zi[brev(n1, 5)] = e.b;
+            }
+            fft_dit<32, float>(l.zr, l.zi);
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            const int k2 = lane & 15, src = (lane & 16) | ((16 - k2) & 15);
+            xelem<float>* pt = tile.data() + (lane >> 4) * PS;
+            const int src_k2 = src & 15;
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const int preg = src_k2 == 0 ? ((32 - k1) & 31) : 31 - k1;
+                pt[16 * k1 + k2] = frame_powers<float>(L[lane].zr[k1], L[lane].zi[k1], L[src].zr[preg], L[src].zi[preg]);
+            }
+            if (k2 == 0) pt[256] = frame_powers<float>(L[lane].zr[16], L[lane].zi[16], L[lane].zr[16], L[lane].zi[16]);
+        }
+        for (int lane = 0; lane < 32; ++lane)
+            for (int s = 0; s < bm.n_slots; ++s) {
+                const int start = bm.start[s * 32 + lane], row = bm.row[s * 32 + lane];
+                float a[4] = {0, 0, 0, 0};
+                for (int i = 0; i < bm.trip[s]; ++i) {
+                    const float wt = bm.w[((size_t)bm.wbase[s] + i) * 32 + lane];
+                    const xelem<float> ea = tile[start + i], eb = tile[PS + start + i];
+                    a[0] = fmaf(ea.a, wt, a[0]);
+                    a[1] = fmaf(ea.b, wt, a[1]);
+                    a[2] = fmaf(eb.a, wt, a[2]);
+                    a[3] = fmaf(eb.b, wt, a[3]);
+                }
+                if (row < 0) continue;
+                for (int t = 0; t < 4; ++t)
+                    if (f0 + t < m) out[(size_t)(f0 + t) * n_mels + row] = logf(fmaxf(a[t], 1.1920929e-7f));
+            }
+    }
+}
+
 static std::vector<float> read_f32(const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) {
@@ -113,6 +209,13 @@ int main(int argc, char** argv) {
         else
             run_logmel<float>(x, hop, n_mels, fmin, fmax, out);
         write_f32(argv[8], out);
+        return 0;
+    }
+    if (argc >= 5 && !strcmp(argv[1], "fbank")) {
+        const std::vector<float> x = read_f32(argv[3]);
+        std::vector<float> out;
+        run_fbank(x, atoi(argv[2]), out);
+        write_f32(argv[4], out);
         return 0;
     }
     fprintf(stderr, "usage: host_check logmel <scalar|packed> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>\n");

@@ -1,0 +1,418 @@
+// Kaldi-style log mel filterbank (Audio-MAE front-end).
+// Replaces torchaudio.compliance.kaldi.fbank(waveform, htk_compat=True, sample_frequency=16000,
+// use_energy=False, window_type="hanning", num_mel_bins=128, dither=0.0, frame_shift=10,
+// frame_length=25) as called at /root/reference/src/util.py:845-856 and
+// src/benchmark/baseline/extract_feature.py:232-243.
+//
+// Per frame (snip_edges): 400 samples at shift 160 -> subtract frame mean -> pre-emphasis 0.97
+// (replicate pad) -> symmetric Hann -> zero pad to 512 -> |rFFT|^2 -> 128 HTK-mel triangles
+// (20 Hz .. Nyquist, Nyquist column zero) -> log(max(., FLT_EPSILON)).
+//
+// A warp handles 4 consecutive frames as two complex 512-point FFTs (frame pairs packed as
+// re/im), 512 = 32 (lanes) x 16 (registers): pass 1 is a packed (FFMA2) 16-point FFT over the
+// two transforms, pass 2 one scalar 32-point FFT per lane (lane = transform*16 + k2).
+// The per-chunk waveform mean subtraction the reference does before fbank cancels exactly
+// against the per-frame DC removal and is not materialised.
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "api_common.h"
+#include "logmel_core.cuh"
+#include "tables.h"
+
+namespace hmfe {
+
+constexpr int kFbPad = 512;
+constexpr int kFbMaxSlots = 8;
+constexpr int kFbPStride = 320;  // power tile stride per transform (>= 257 + banded slack)
+constexpr int kFbWarps = 8;
+
+struct FbMeta {
+    int n_slots, total_trip, n_mels;
+    int trip[kFbMaxSlots], wbase[kFbMaxSlots];
+    int win, shift;
+    float preemph;
+};
+
+struct FbBatch {
+    const float* wav;
+    float* out;
+    const int64_t* clip_start;   // [n_clips]
+    const int64_t* clip_len;     // [n_clips]
+    const int64_t* frame_off;    // [n_clips+1] output row offsets
+    const int64_t* item_prefix;  // [n_clips+1]
+    int64_t n_clips, n_items;
+    int uniform_n, uniform_m, uniform_items, uniform_rows;
+    int row_cap;  // > 0: frames beyond this row count are dropped (padded layout)
+};
+
+struct FbTables {
+    const float* win;   // [win] 0.5 * window
+    const float2* tw;   // [16][32]
+    const float* melw;  // [total_trip][32]
+    const int* start;
+    const int* row;
+};
+
+__global__ void __launch_bounds__(kFbWarps * 32, 2)
+fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* s_tw = reinterpret_cast<float2*>(smem);                   // 512
+    float* s_win = reinterpret_cast<float*>(s_tw + 512);              // 512 (zero padded)
+    float* s_melw = s_win + 512;
+    int* s_start = reinterpret_cast<int*>(s_melw + mm.total_trip * 32);
+    int* s_row = s_start + mm.n_slots * 32;
+    size_t tbytes = (size_t)(512 * 8 + 512 * 4 + mm.total_trip * 128 + mm.n_slots * 256);
+    tbytes = (tbytes + 15) & ~(size_t)15;
+    xelem<float>* tile = reinterpret_cast<xelem<float>*>(smem + tbytes) + (threadIdx.x >> 5) * (32 * kXStride);
+
+    for (int i = threadIdx.x; i < 512; i += kFbWarps * 32) {
+        s_tw[i] = tb.tw[i];
+        s_win[i] = i < mm.win ? tb.win[i] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < mm.total_trip * 32; i += kFbWarps * 32) s_melw[i] = tb.melw[i];
+    for (int i = threadIdx.x; i < mm.n_slots * 32; i += kFbWarps * 32) {
+        s_start[i] = tb.start[i];
+        s_row[i] = tb.row[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t per_cta = (b.n_items + gridDim.x - 1) / gridDim.x;
+    const int64_t it_begin = (int64_t)blockIdx.x * per_cta;
+    const int64_t it_end = min(b.n_items, it_begin + per_cta);
+    int64_t clip = -1;
+
+    for (int64_t item = it_begin + warp; item < it_end; item += kFbWarps) {
+        int64_t q;
+        int nsamp, m;
+        const float* x;
+        float* o;
+        if (b.uniform_items > 0) {
+            clip = item / b.uniform_items;
+            q = item - clip * b.uniform_items;
+            nsamp = b.uniform_n;
+            m = b.uniform_m;
+            x = b.wav + clip * (int64_t)nsamp;
+            o = b.out + clip * (int64_t)b.uniform_rows * mm.n_mels;
+        } else {
+            if (clip < 0) {
+                int64_t lo = 0, hi = b.n_clips;
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (b.item_prefix[mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                clip = lo;
+            }
+            while (item >= b.item_prefix[clip + 1]) ++clip;
+            q = item - b.item_prefix[clip];
+            const int64_t c0 = b.clip_start[clip];
+            nsamp = (int)b.clip_len[clip];
+            m = nsamp >= mm.win ? 1 + (nsamp - mm.win) / mm.shift : 0;
+            if (b.row_cap > 0) m = min(m, b.row_cap);
+            x = b.wav + c0;
+            o = b.out + b.frame_off[clip] * mm.n_mels;
+        }
+        const int f0 = (int)q * 4;
+
+        // ---- load 4 frames: DC removal, pre-emphasis, window; pack (A = f0,f0+1 | B = f0+2,f0+3)
+        f32x2 re[16], im[16];
+        {
+            // pass 1 over the frame: mean (DC removal); pass 2 re-reads the samples (L1 hits)
+            float mean[4];
+            const float* xf[4];
+            bool ok[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int f = f0 + t;
+                ok[t] = f < m;
+                xf[t] = x + (int64_t)(ok[t] ? f : 0) * mm.shift;
+                float acc = 0.0f;
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) {
+                    const int n = lane + 32 * n2;
+                    if (ok[t] && n < mm.win) acc += __ldg(xf[t] + n);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                mean[t] = acc / (float)mm.win;
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int n = lane + 32 * n2;
+                const float w = s_win[n];
+                float y[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float v = 0.0f;
+                    if (ok[t] && n < mm.win) {
+                        const float a = __ldg(xf[t] + n) - mean[t];
+                        const float pv = __ldg(xf[t] + max(n - 1, 0)) - mean[t];
+                        v = (a - mm.preemph * pv) * w;
+                    }
+                    y[t] = v;
+                }
+                re[brev(n2, 4)] = f32x2{y[0], y[2]};
+                im[brev(n2, 4)] = f32x2{y[1], y[3]};
+            }
+        }
+        fft_dit<16, f32x2>(re, im);
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) {
+            const float2 w = s_tw[k2 * 32 + lane];
+            const f32x2 nr = vfnmas(im[k2], w.y, vmuls(re[k2], w.x));
+            const f32x2 ni = vfmas(im[k2], w.x, vmuls(re[k2], w.y));
+            re[k2] = nr;
+            im[k2] = ni;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            tile[k2 * kXStride + lane] = xelem<float>{re[k2].x, im[k2].x};
+            tile[(16 + k2) * kXStride + lane] = xelem<float>{re[k2].y, im[k2].y};
+        }
+        __syncwarp();
+        float zr[32], zi[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const xelem<float> e = tile[lane * kXStride + n1];
+            zr[brev(n1, 5)] = e.a;
+            zi[brev(n1, 5)] = e.b;
+        }
+        __syncwarp();
+        fft_dit<32, float>(zr, zi);  // lane = t*16 + k2 ; bin k = 16*k1 + k2
+
+        {
+            const int k2 = lane & 15;
+            const int src = (lane & 16) | ((16 - k2) & 15);
+            xelem<float>* pt = tile + (lane >> 4) * kFbPStride;
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const float give_r = k2 == 0 ? zr[(32 - k1) & 31] : zr[31 - k1];
+                const float give_i = k2 == 0 ? zi[(32 - k1) & 31] : zi[31 - k1];
+                const float pr = __shfl_sync(0xffffffffu, give_r, src), pi = __shfl_sync(0xffffffffu, give_i, src);
+                pt[16 * k1 + k2] = frame_powers<float>(zr[k1], zi[k1], pr, pi);
+            }
+            if (k2 == 0) pt[256] = frame_powers<float>(zr[16], zi[16], zr[16], zi[16]);
+        }
+        __syncwarp();
+
+        for (int s = 0; s < mm.n_slots; ++s) {
+            const int start = s_start[s * 32 + lane], trip = mm.trip[s];
+            const float* wl = s_melw + mm.wbase[s] * 32 + lane;
+            const xelem<float>* pa = tile + start;
+            const xelem<float>* pb = tile + kFbPStride + start;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < trip; ++i) {
+                const float w = wl[i * 32];
+                const xelem<float> ea = pa[i], eb = pb[i];
+                a0 = fmaf(ea.a, w, a0);
+                a1 = fmaf(ea.b, w, a1);
+                a2 = fmaf(eb.a, w, a2);
+                a3 = fmaf(eb.b, w, a3);
+            }
+            const int row = s_row[s * 32 + lane];
+            if (row >= 0) {
+                const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (f0 + t < m) o[(int64_t)(f0 + t) * mm.n_mels + row] = logf(fmaxf(acc[t], FLT_EPSILON));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace hmfe
+
+using namespace hmfe;
+
+struct hmfe_fbank_plan {
+    int sample_rate, win, shift, n_mels;
+    std::vector<float> mel_dense;
+    FbMeta meta;
+    float *d_win = nullptr, *d_melw = nullptr;
+    float2* d_tw = nullptr;
+    int *d_start = nullptr, *d_row = nullptr;
+    size_t table_smem = 0;
+    DescRing ring;
+    int last_launches = 0, sm_count = 148;
+};
+
+template <typename T>
+static int fb_upload(const std::vector<T>& v, T** dptr) {
+    HMFE_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(1, v.size()) * sizeof(T)));
+    HMFE_CHECK_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return HMFE_OK;
+}
+
+extern "C" {
+
+void hmfe_fbank_plan_destroy(hmfe_fbank_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_win);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_melw);
+    cudaFree(p->d_start);
+    cudaFree(p->d_row);
+    delete p;
+}
+
+int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame_length_ms, double frame_shift_ms,
+                           int n_mels, double low_freq, double high_freq, double preemph) {
+    HMFE_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    HMFE_REQUIRE(sample_rate > 0 && frame_length_ms > 0 && frame_shift_ms > 0, "bad frame parameters");
+    const int win = (int)(sample_rate * frame_length_ms * 0.001), shift = (int)(sample_rate * frame_shift_ms * 0.001);
+    if (win <= 256 || win > kFbPad || shift < 1) {
+        set_error("window of %d samples unsupported: the kernel is specialised for a 512-point padded FFT "
+                  "(25 ms at 16 kHz, src/util.py:845-856)", win);
+        return HMFE_ERR_UNSUPPORTED;
+    }
+    HMFE_REQUIRE(n_mels >= 32 && n_mels % 32 == 0 && n_mels <= 32 * kFbMaxSlots, "n_mels=%d must be a multiple of 32 <= %d",
+                 n_mels, 32 * kFbMaxSlots);
+    hmfe_fbank_plan* p = new (std::nothrow) hmfe_fbank_plan();
+    HMFE_REQUIRE(p != nullptr, "out of host memory");
+    p->sample_rate = sample_rate;
+    p->win = win;
+    p->shift = shift;
+    p->n_mels = n_mels;
+    p->sm_count = device_sm_count();
+    p->mel_dense = mel_banks_kaldi(n_mels, kFbPad, sample_rate, low_freq, high_freq);
+    const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1);
+    p->meta.n_slots = bm.n_slots;
+    p->meta.total_trip = bm.total_trip;
+    p->meta.n_mels = n_mels;
+    p->meta.win = win;
+    p->meta.shift = shift;
+    p->meta.preemph = (float)preemph;
+    for (int s = 0; s < bm.n_slots; ++s) {
+        p->meta.trip[s] = bm.trip[s];
+        p->meta.wbase[s] = bm.wbase[s];
+    }
+    int rc = fb_upload(half_hann_symmetric(win), &p->d_win);
+    if (rc == HMFE_OK) rc = fb_upload(twiddle_plane(kFbPad, 16), reinterpret_cast<float**>(&p->d_tw));
+    if (rc == HMFE_OK) rc = fb_upload(bm.w, &p->d_melw);
+    if (rc == HMFE_OK) rc = fb_upload(bm.start, &p->d_start);
+    if (rc == HMFE_OK) rc = fb_upload(bm.row, &p->d_row);
+    if (rc != HMFE_OK) {
+        hmfe_fbank_plan_destroy(p);
+        return rc;
+    }
+    size_t tbytes = (size_t)(512 * 8 + 512 * 4 + bm.total_trip * 128 + bm.n_slots * 256);
+    p->table_smem = (tbytes + 15) & ~(size_t)15;
+    *plan = p;
+    return HMFE_OK;
+}
+
+int64_t hmfe_fbank_num_frames(const hmfe_fbank_plan* p, int64_t n_samples) {
+    if (!p || n_samples < 0) return -1;
+    return n_samples >= p->win ? 1 + (n_samples - p->win) / p->shift : 0;
+}
+
+int hmfe_fbank_mel_basis(const hmfe_fbank_plan* p, float* h_out) {
+    HMFE_REQUIRE(p && h_out, "NULL argument");
+    std::copy(p->mel_dense.begin(), p->mel_dense.end(), h_out);
+    return HMFE_OK;
+}
+
+int hmfe_fbank_last_launches(const hmfe_fbank_plan* p) { return p ? p->last_launches : 0; }
+
+// rows_per_clip == 0: clips' frames are packed back to back ([sum m_i, n_mels]);
+// rows_per_clip  > 0: clip i owns rows [i*rows_per_clip, (i+1)*rows_per_clip), frames beyond
+// rows_per_clip are dropped and missing rows are zero (the model-side pad to 1024 rows,
+// audioMAE/models_mae.py:1178-1181).
+int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t* h_starts, const int64_t* h_lengths,
+                           int64_t n_clips, float* d_out, int rows_per_clip, void* stream) {
+    HMFE_REQUIRE(p && h_starts && h_lengths, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0 && rows_per_clip >= 0, "bad arguments");
+    p->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_wav && d_out, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool uniform = true;
+    const int64_t n0 = h_lengths[0];
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_lengths[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30 && h_starts[i] >= 0, "clip %lld has invalid start/length", (long long)i);
+        uniform = uniform && n == n0 && h_starts[i] == i * n0;
+    }
+    FbBatch b{};
+    b.wav = d_wav;
+    b.out = d_out;
+    b.n_clips = n_clips;
+    b.row_cap = rows_per_clip;
+    auto frames_of = [&](int64_t n) {
+        int64_t m = n >= p->win ? 1 + (n - p->win) / p->shift : 0;
+        return rows_per_clip > 0 ? std::min<int64_t>(m, rows_per_clip) : m;
+    };
+    const size_t desc_bytes = uniform ? 0 : (4 * (size_t)n_clips + 2) * sizeof(int64_t);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = p->ring.acquire(std::max<size_t>(desc_bytes, 16), &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    int64_t total_rows = 0;
+    if (uniform) {
+        const int64_t m = frames_of(n0);
+        b.uniform_n = (int)n0;
+        b.uniform_m = (int)m;
+        b.uniform_items = (int)std::max<int64_t>(1, (m + 3) / 4);
+        b.uniform_rows = rows_per_clip > 0 ? rows_per_clip : (int)m;
+        b.n_items = m > 0 ? (int64_t)b.uniform_items * n_clips : 0;
+        total_rows = (int64_t)b.uniform_rows * n_clips;
+    } else {
+        int64_t* hs = static_cast<int64_t*>(hbuf);
+        int64_t* hl = hs + n_clips;
+        int64_t* hf = hl + n_clips;
+        int64_t* hi = hf + (n_clips + 1);
+        hf[0] = hi[0] = 0;
+        for (int64_t i = 0; i < n_clips; ++i) {
+            const int64_t m = frames_of(h_lengths[i]);
+            hs[i] = h_starts[i];
+            hl[i] = h_lengths[i];
+            hf[i + 1] = hf[i] + (rows_per_clip > 0 ? rows_per_clip : m);
+            hi[i + 1] = hi[i] + (m + 3) / 4;
+        }
+        b.n_items = hi[n_clips];
+        total_rows = hf[n_clips];
+        int64_t* dc = static_cast<int64_t*>(dbuf);
+        b.clip_start = dc;
+        b.clip_len = dc + n_clips;
+        b.frame_off = dc + 2 * n_clips;
+        b.item_prefix = dc + 3 * n_clips + 1;
+        int rc = p->ring.upload(slot, desc_bytes, st);
+        if (rc != HMFE_OK) return rc;
+    }
+    if (rows_per_clip > 0 && total_rows > 0) {
+        HMFE_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)total_rows * p->n_mels * sizeof(float), st));
+    }
+    if (b.n_items > 0) {
+        FbMeta mm = p->meta;
+        const size_t smem = p->table_smem + (size_t)kFbWarps * 32 * kXStride * sizeof(xelem<float>);
+        HMFE_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t want = (b.n_items + kFbWarps - 1) / kFbWarps;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));
+        FbTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
+        fbank_kernel<<<grid, kFbWarps * 32, smem, st>>>(b, tb, mm);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        p->last_launches = 1;
+    }
+    return p->ring.release(slot, st);
+}
+
+int hmfe_fbank_batch(hmfe_fbank_plan* p, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, float* d_out,
+                     int rows_per_clip, void* stream) {
+    HMFE_REQUIRE(p && h_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
+    std::vector<int64_t> len((size_t)n_clips);
+    for (int64_t i = 0; i < n_clips; ++i) len[i] = h_offsets[i + 1] - h_offsets[i];
+    return hmfe_fbank_batch_views(p, d_wav, h_offsets, len.data(), n_clips, d_out, rows_per_clip, stream);
+}
+
+}  // extern "C"

@@ -2,6 +2,7 @@
 // + power + banded mel projection, then a per-clip dB / min-max epilogue.
 // Replaces pre_process_audio_mel_t (/root/reference/src/util.py:481-501).
 #include <math.h>
+#include <stdint.h>
 
 #include <algorithm>
 #include <new>
@@ -24,7 +25,8 @@ struct MelMeta {
 struct LogmelBatch {
     const float* wav;
     float* out;
-    const int64_t* clip_off;     // [n_clips+1] ragged only
+    const int64_t* clip_start;   // [n_clips] ragged only: first sample of each clip in wav
+    const int64_t* clip_len;     // [n_clips] ragged only
     const int64_t* frame_off;    // [n_clips+1] ragged only
     const int64_t* item_prefix;  // [n_clips+1] ragged only
     unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
@@ -46,8 +48,8 @@ HMFE_D f32x2 shfl(f32x2 v, int src) {
     return f32x2{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
 }
 
-template <typename V, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <typename V, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm) {
     constexpr int NV = lanes_of<V>::value;
     constexpr int FR = 2 * NV;
@@ -104,8 +106,8 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
             }
             while (item >= b.item_prefix[clip + 1]) ++clip;
             q = item - b.item_prefix[clip];
-            const int64_t c0 = b.clip_off[clip];
-            nsamp = (int)(b.clip_off[clip + 1] - c0);
+            const int64_t c0 = b.clip_start[clip];
+            nsamp = (int)b.clip_len[clip];
             const int64_t f0g = b.frame_off[clip];
             T = (int)(b.frame_off[clip + 1] - f0g);
             x = b.wav + c0;
@@ -271,13 +273,13 @@ static int upload_vec(const std::vector<T>& v, T** dptr) {
     return HMFE_OK;
 }
 
-template <typename V, int WARPS>
+template <typename V, int WARPS, int MINB>
 static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
     const size_t smem = p->table_smem + (size_t)WARPS * kTileElems * sizeof(xelem<V>);
-    auto kern = logmel_power_kernel<V, WARPS>;
+    auto kern = logmel_power_kernel<V, WARPS, MINB>;
     HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (b.n_items + WARPS - 1) / WARPS;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * MINB));
     LogmelTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
     kern<<<grid, WARPS * 32, smem, st>>>(b, tb, p->meta);
     HMFE_CHECK_CUDA(cudaGetLastError());
@@ -384,32 +386,33 @@ int hmfe_logmel_profile_ms(hmfe_logmel_plan* p, double* power_ms, double* finali
     return HMFE_OK;
 }
 
-int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, float* d_out,
-                      int out_mode, void* stream) {
-    HMFE_REQUIRE(p && h_offsets, "NULL argument");
+int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_starts, const int64_t* h_lengths,
+                            int64_t n_clips, float* d_out, int out_mode, void* stream) {
+    HMFE_REQUIRE(p && h_starts && h_lengths, "NULL argument");
     HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
     HMFE_REQUIRE(out_mode >= 0 && out_mode <= 2, "bad out_mode %d", out_mode);
     p->last_launches = 0;
     if (n_clips == 0) return HMFE_OK;
     HMFE_REQUIRE(d_wav && d_out, "NULL device pointer");
+    HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "d_out must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int FR = p->variant == HMFE_VARIANT_PACKED ? 4 : 2;
 
     bool uniform = true;
-    const int64_t n0 = h_offsets[1] - h_offsets[0];
+    const int64_t n0 = h_lengths[0];
     for (int64_t i = 0; i < n_clips; ++i) {
-        const int64_t n = h_offsets[i + 1] - h_offsets[i];
-        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30, "clip %lld has invalid length %lld", (long long)i, (long long)n);
-        uniform = uniform && n == n0;
+        const int64_t n = h_lengths[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30 && h_starts[i] >= 0, "clip %lld has invalid start/length %lld/%lld",
+                     (long long)i, (long long)h_starts[i], (long long)n);
+        uniform = uniform && n == n0 && h_starts[i] == i * n0;
     }
-    uniform = uniform && h_offsets[0] == 0;
 
     LogmelBatch b{};
     b.wav = d_wav;
     b.out = d_out;
     b.n_clips = n_clips;
     b.hop = p->hop;
-    const size_t desc_bytes = uniform ? 0 : 3 * (size_t)(n_clips + 1) * sizeof(int64_t);
+    const size_t desc_bytes = uniform ? 0 : (4 * (size_t)n_clips + 2) * sizeof(int64_t);
     const size_t total_bytes = desc_bytes + (size_t)n_clips * 2 * sizeof(unsigned);
     void *hbuf = nullptr, *dbuf = nullptr;
     const int slot = p->ring.acquire(total_bytes, &hbuf, &dbuf);
@@ -421,22 +424,24 @@ int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_
         b.uniform_items = (int)((T + FR - 1) / FR);
         b.n_items = (int64_t)b.uniform_items * n_clips;
     } else {
-        int64_t* hc = static_cast<int64_t*>(hbuf);
-        int64_t* hf = hc + (n_clips + 1);
+        int64_t* hs = static_cast<int64_t*>(hbuf);
+        int64_t* hl = hs + n_clips;
+        int64_t* hf = hl + n_clips;
         int64_t* hi = hf + (n_clips + 1);
         hf[0] = hi[0] = 0;
         for (int64_t i = 0; i < n_clips; ++i) {
-            const int64_t T = 1 + (h_offsets[i + 1] - h_offsets[i]) / p->hop;
-            hc[i] = h_offsets[i];
+            const int64_t T = 1 + h_lengths[i] / p->hop;
+            hs[i] = h_starts[i];
+            hl[i] = h_lengths[i];
             hf[i + 1] = hf[i] + T;
             hi[i + 1] = hi[i] + (T + FR - 1) / FR;
         }
-        hc[n_clips] = h_offsets[n_clips];
         b.n_items = hi[n_clips];
         int64_t* dc = static_cast<int64_t*>(dbuf);
-        b.clip_off = dc;
-        b.frame_off = dc + (n_clips + 1);
-        b.item_prefix = dc + 2 * (n_clips + 1);
+        b.clip_start = dc;
+        b.clip_len = dc + n_clips;
+        b.frame_off = dc + 2 * n_clips;
+        b.item_prefix = dc + 3 * n_clips + 1;
         int rc = p->ring.upload(slot, desc_bytes, st);
         if (rc != HMFE_OK) return rc;
     }
@@ -452,7 +457,7 @@ int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_
         }
         HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
     }
-    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 4>(p, b, st) : launch_power<float, 8>(p, b, st);
+    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st) : launch_power<float, 8, 2>(p, b, st);
     if (rc != HMFE_OK) return rc;
     if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
     p->last_launches = 2;
@@ -464,6 +469,15 @@ int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_
     }
     if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[2], st));
     return p->ring.release(slot, st);
+}
+
+int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, float* d_out,
+                      int out_mode, void* stream) {
+    HMFE_REQUIRE(p && h_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
+    std::vector<int64_t> len((size_t)n_clips);
+    for (int64_t i = 0; i < n_clips; ++i) len[i] = h_offsets[i + 1] - h_offsets[i];
+    return hmfe_logmel_batch_views(p, d_wav, h_offsets, len.data(), n_clips, d_out, out_mode, stream);
 }
 
 }  // extern "C"

@@ -101,7 +101,7 @@ HMFE_HD void mel_slot(int lane, const xelem<V>* __restrict__ ptile, const float*
     acc_b = V{};
     const xelem<V>* p = ptile + start;
     const float* wl = w + lane;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < trip; ++i) {
         const float wi = wl[i * 32];
         const xelem<V> e = p[i];

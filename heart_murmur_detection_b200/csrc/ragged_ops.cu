@@ -1,0 +1,269 @@
+// Ragged-batch utility kernels: silence trim (frame RMS + first/last index) and the
+// pad / split / tile / repeat gather.  All index work is integer and bit-exact; the index
+// tables for the gather are computed on the host (frontend.py) and only applied here.
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+
+#include "api_common.h"
+#include "ctx.h"
+
+namespace hmfe {
+
+// ---------------------------------------------------------------------------------- trim
+// librosa.effects.trim(y, top_db, ref=np.max, frame_length=L, hop_length=h)
+// (/root/reference/src/util.py:170-172,237-244,338-340,820-822; extract_feature.py:219-221):
+// centred frames (zero pad L/2 each side), p_t = mean(x^2) over frame t (float32),
+// rms = sqrt(p), db = 10 log10(max(amin^2, rms^2)) - 10 log10(max(amin^2, max rms ^2)),
+// non-silent = db > -top_db; start = h * first, end = min(N, h * (last + 1)); none -> (0, 0).
+
+struct TrimBatch {
+    const float* wav;
+    const int64_t* clip_off;   // [n_clips+1]
+    const int64_t* frame_off;  // [n_clips+1]
+    float* power;              // [total frames] rms^2 per frame
+    int64_t* start_end;        // [n_clips][2]
+    int64_t n_clips, n_frames_total;
+    int frame_length, hop;
+    float top_db;
+};
+
+// one warp per frame
+__global__ void __launch_bounds__(256) trim_frame_power_kernel(const TrimBatch b) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t per = (b.n_frames_total + n_warps - 1) / n_warps;
+    const int64_t f_begin = warp_global * per, f_end = min(b.n_frames_total, f_begin + per);
+    if (f_begin >= f_end) return;
+    int64_t lo = 0, hi = b.n_clips;  // largest clip with frame_off[clip] <= f_begin
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (b.frame_off[mid] <= f_begin)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    int64_t clip = lo;
+    const int half = b.frame_length / 2;
+    for (int64_t f = f_begin; f < f_end; ++f) {
+        while (f >= b.frame_off[clip + 1]) ++clip;
+        const int64_t c0 = b.clip_off[clip];
+        const int n = (int)(b.clip_off[clip + 1] - c0);
+        const int t = (int)(f - b.frame_off[clip]);
+        const int s0 = t * b.hop - half;
+        const float* x = b.wav + c0;
+        float acc = 0.0f;
+        for (int i = lane; i < b.frame_length; i += 32) {
+            const int j = s0 + i;
+            const float v = (j >= 0 && j < n) ? __ldg(x + j) : 0.0f;
+            acc = fmaf(v, v, acc);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            const float rms = sqrtf(acc / (float)b.frame_length);
+            b.power[f] = rms * rms;
+        }
+    }
+}
+
+// one CTA per clip: clip max, then first / last frame above the threshold
+__global__ void __launch_bounds__(256) trim_index_kernel(const TrimBatch b) {
+    __shared__ float s_f[8];
+    __shared__ int s_i[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t clip = blockIdx.x; clip < b.n_clips; clip += gridDim.x) {
+        const int64_t f0 = b.frame_off[clip];
+        const int T = (int)(b.frame_off[clip + 1] - f0);
+        const int n = (int)(b.clip_off[clip + 1] - b.clip_off[clip]);
+        const float* p = b.power + f0;
+        float m = 0.0f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) m = fmaxf(m, p[t]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) s_f[warp] = m;
+        __syncthreads();
+        m = s_f[0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_f[w]);
+        // amplitude_to_db(rms, ref=max, amin=1e-5): power_to_db(rms^2, ref=max^2, amin=1e-10).
+        // The scalar reference term is evaluated in float64 and rounded once (numpy scalar rules).
+        const float amin2 = 1e-10f;
+        const float ref_db = (float)(10.0 * log10(fmax(1e-10, (double)m)));
+        int first = INT_MAX, last = -1;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const float db = 10.0f * log10f(fmaxf(amin2, p[t])) - ref_db;
+            if (db > -b.top_db) {
+                first = min(first, t);
+                last = max(last, t);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+        }
+        if (lane == 0) {
+            s_i[warp] = first;
+            s_i[8 + warp] = last;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                first = min(first, s_i[w]);
+                last = max(last, s_i[8 + w]);
+            }
+            int64_t st = 0, en = 0;
+            if (last >= 0) {
+                st = (int64_t)first * b.hop;
+                en = min((int64_t)n, (int64_t)(last + 1) * b.hop);
+            }
+            b.start_end[2 * clip] = st;
+            b.start_end[2 * clip + 1] = en;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------- gather
+// out chunk c, element i:
+//   i <  a_end : src[src_off + (a_phase + i) mod period]           (tiled / repeated part)
+//   i <  b_end : src[src_off + b_start + (i - a_end)]              (straight copy)
+//   else       : 0
+// covers _zero_padding, _duplicate_padding, 50 %-overlap framing, truncation and
+// non-overlapping chunking (/root/reference/src/util.py:504-620, 257-259; extract_feature.py:250-259).
+constexpr int kGatherTile = 4096;
+
+__global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                     const hmfe_gather_desc* __restrict__ descs, int tiles_per_chunk) {
+    const int64_t chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = (int)(blockIdx.x - chunk * tiles_per_chunk);
+    const hmfe_gather_desc d = descs[chunk];
+    const int t0 = tile * kGatherTile;
+    if (t0 >= d.len) return;
+    const float* s = src + d.src_off;
+    float* o = dst + d.dst_off;
+    const int t1 = min(d.len, t0 + kGatherTile);
+    for (int i = t0 + threadIdx.x; i < t1; i += 256) {
+        float v = 0.0f;
+        if (i < d.a_end) {
+            v = __ldg(s + (int)(((int64_t)d.a_phase + i) % d.period));
+        } else if (i < d.b_end) {
+            v = __ldg(s + d.b_start + (i - d.a_end));
+        }
+        o[i] = v;
+    }
+}
+
+}  // namespace hmfe
+
+using namespace hmfe;
+
+extern "C" {
+
+int hmfe_ctx_create(hmfe_ctx** ctx) {
+    HMFE_REQUIRE(ctx != nullptr, "ctx is NULL");
+    *ctx = new (std::nothrow) hmfe_ctx();
+    HMFE_REQUIRE(*ctx != nullptr, "out of host memory");
+    (*ctx)->sm_count = device_sm_count();
+    return HMFE_OK;
+}
+
+void hmfe_ctx_destroy(hmfe_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    delete ctx;
+}
+
+int hmfe_ctx_last_launches(const hmfe_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int64_t hmfe_trim_num_frames(int64_t n_samples, int frame_length, int hop_length) {
+    if (n_samples < 0 || frame_length < 1 || hop_length < 1) return -1;
+    const int64_t padded = n_samples + 2 * (int64_t)(frame_length / 2);
+    return padded < frame_length ? 0 : 1 + (padded - frame_length) / hop_length;
+}
+
+int hmfe_trim_batch(hmfe_ctx* ctx, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, int frame_length,
+                    int hop_length, float top_db, int64_t* d_start_end, void* stream) {
+    HMFE_REQUIRE(ctx && h_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0 && frame_length >= 2 && hop_length >= 1, "bad trim arguments");
+    ctx->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_wav && d_start_end, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t desc_bytes = 2 * (size_t)(n_clips + 1) * sizeof(int64_t);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = ctx->ring.acquire(desc_bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    int64_t* hc = static_cast<int64_t*>(hbuf);
+    int64_t* hf = hc + (n_clips + 1);
+    hf[0] = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30, "clip %lld has invalid length %lld", (long long)i, (long long)n);
+        hc[i] = h_offsets[i];
+        hf[i + 1] = hf[i] + hmfe_trim_num_frames(n, frame_length, hop_length);
+    }
+    hc[n_clips] = h_offsets[n_clips];
+    int rc = ctx->ring.upload(slot, desc_bytes, st);
+    if (rc != HMFE_OK) return rc;
+    TrimBatch b{};
+    b.wav = d_wav;
+    b.clip_off = static_cast<int64_t*>(dbuf);
+    b.frame_off = b.clip_off + (n_clips + 1);
+    b.n_clips = n_clips;
+    b.n_frames_total = hf[n_clips];
+    b.frame_length = frame_length;
+    b.hop = hop_length;
+    b.top_db = top_db;
+    b.start_end = d_start_end;
+    rc = ctx->reserve_scratch((size_t)std::max<int64_t>(1, b.n_frames_total) * sizeof(float));
+    if (rc != HMFE_OK) return rc;
+    b.power = static_cast<float*>(ctx->scratch);
+    if (b.n_frames_total > 0) {
+        const int64_t warps_wanted = b.n_frames_total;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_wanted + 7) / 8, (int64_t)ctx->sm_count * 8));
+        trim_frame_power_kernel<<<grid, 256, 0, st>>>(b);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        ctx->last_launches++;
+    }
+    trim_index_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(b);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->last_launches++;
+    return ctx->ring.release(slot, st);
+}
+
+int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* h_descs,
+                      int64_t n_chunks, void* stream) {
+    HMFE_REQUIRE(ctx && (h_descs || n_chunks == 0), "NULL argument");
+    HMFE_REQUIRE(n_chunks >= 0, "n_chunks < 0");
+    ctx->last_launches = 0;
+    if (n_chunks == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_src && d_dst, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int max_len = 0;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        const hmfe_gather_desc& d = h_descs[i];
+        HMFE_REQUIRE(d.len >= 0 && d.a_end >= 0 && d.a_end <= d.b_end && d.b_end <= d.len && d.period >= 1 &&
+                         d.a_phase >= 0 && d.b_start >= 0 && d.src_off >= 0 && d.dst_off >= 0,
+                     "gather descriptor %lld is inconsistent", (long long)i);
+        max_len = std::max(max_len, d.len);
+    }
+    if (max_len == 0) return HMFE_OK;
+    const size_t bytes = (size_t)n_chunks * sizeof(hmfe_gather_desc);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = ctx->ring.acquire(bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    memcpy(hbuf, h_descs, bytes);
+    int rc = ctx->ring.upload(slot, bytes, st);
+    if (rc != HMFE_OK) return rc;
+    const int tiles = (max_len + kGatherTile - 1) / kGatherTile;
+    HMFE_REQUIRE(n_chunks * tiles < (int64_t)INT32_MAX, "gather grid too large");
+    gather_kernel<<<(unsigned)(n_chunks * tiles), 256, 0, st>>>(d_src, d_dst, static_cast<hmfe_gather_desc*>(dbuf), tiles);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->last_launches = 1;
+    return ctx->ring.release(slot, st);
+}
+
+}  // extern "C"

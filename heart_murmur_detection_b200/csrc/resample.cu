@@ -1,0 +1,215 @@
+// Batched polyphase FIR resampler (to 16 kHz).
+//
+// The reference resamples inside librosa.load(path, sr=16000) (src/util.py:153,222,323,391,805;
+// extract_feature.py:214) with libsoxr's HQ filter - a third-party C library that is not
+// vendored and not installable here (parity unpinned) - and with
+// torchaudio.transforms.Resample at src/model/models_eval.py:964-968.  This kernel implements
+// the latter's published algorithm (Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99,
+// or the Kaiser variant), which is the pinned oracle:
+//   out[j] = sum_k  kern[j mod U][k] * xpad[(j div U) * D + k],   k in [0, 2*width + D)
+//   U = new/gcd, D = orig/gcd, xpad = x left-padded by `width` zeros, out length ceil(U*n/D).
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "api_common.h"
+#include "tables.h"
+
+namespace hmfe {
+
+struct ResampleBatch {
+    const float* x;
+    float* y;
+    const int64_t* in_off;   // [n_clips+1]
+    const int64_t* out_off;  // [n_clips+1]
+    const float* kern;       // [U][W]
+    int64_t n_clips, n_out_total;
+    int U, D, W, width;
+};
+
+constexpr int kRsTile = 1024;  // outputs per CTA
+
+__global__ void __launch_bounds__(256) resample_kernel(const ResampleBatch b, const int64_t* tile_prefix) {
+    // tile -> clip (binary search over per-clip tile prefix)
+    const int64_t tile = blockIdx.x;
+    int64_t lo = 0, hi = b.n_clips;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (tile_prefix[mid] <= tile)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const int64_t clip = lo;
+    const int64_t i0 = b.in_off[clip];
+    const int n_in = (int)(b.in_off[clip + 1] - i0);
+    const int64_t o0 = b.out_off[clip];
+    const int n_out = (int)(b.out_off[clip + 1] - o0);
+    const float* x = b.x + i0;
+    const int j0 = (int)(tile - tile_prefix[clip]) * kRsTile;
+    for (int j = j0 + threadIdx.x; j < min(n_out, j0 + kRsTile); j += 256) {
+        const int p = j % b.U, q = j / b.U;
+        const float* k = b.kern + (size_t)p * b.W;
+        const int base = q * b.D - b.width;
+        float acc = 0.0f;
+        const int k_lo = max(0, -base), k_hi = min(b.W, n_in - base);
+        for (int t = k_lo; t < k_hi; ++t) acc = fmaf(__ldg(k + t), __ldg(x + base + t), acc);
+        b.y[o0 + j] = acc;
+    }
+}
+
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = x * x / 4.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / ((double)k * k);
+        sum += term;
+        if (term < 1e-17 * sum) break;
+    }
+    return sum;
+}
+
+}  // namespace hmfe
+
+using namespace hmfe;
+
+struct hmfe_resample_plan {
+    int orig, target, U, D, W, width;
+    std::vector<float> kern;
+    float* d_kern = nullptr;
+    DescRing ring;
+    int last_launches = 0;
+};
+
+static int gcd_int(int a, int b) {
+    while (b) {
+        const int t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+extern "C" {
+
+void hmfe_resample_plan_destroy(hmfe_resample_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_kern);
+    delete p;
+}
+
+// method 0: sinc_interp_hann, 1: sinc_interp_kaiser (beta <= 0 -> torchaudio default 14.769656459379492)
+int hmfe_resample_plan_create(hmfe_resample_plan** plan, int orig_freq, int new_freq, int lowpass_filter_width,
+                              double rolloff, int method, double beta) {
+    HMFE_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    HMFE_REQUIRE(orig_freq > 0 && new_freq > 0 && lowpass_filter_width > 0 && rolloff > 0 && rolloff <= 1.0,
+                 "bad resample parameters");
+    HMFE_REQUIRE(method == 0 || method == 1, "bad method %d", method);
+    hmfe_resample_plan* p = new (std::nothrow) hmfe_resample_plan();
+    HMFE_REQUIRE(p != nullptr, "out of host memory");
+    const int g = gcd_int(orig_freq, new_freq);
+    p->orig = orig_freq;
+    p->target = new_freq;
+    p->D = orig_freq / g;
+    p->U = new_freq / g;
+    const double base_freq = std::min(p->D, p->U) * rolloff;
+    p->width = (int)ceil(lowpass_filter_width * (double)p->D / base_freq);
+    p->W = 2 * p->width + p->D;
+    p->kern.assign((size_t)p->U * p->W, 0.0f);
+    if (beta <= 0) beta = 14.769656459379492;
+    const double scale = base_freq / p->D, i0b = bessel_i0(beta);
+    for (int ph = 0; ph < p->U; ++ph)
+        for (int k = 0; k < p->W; ++k) {
+            double t = (-(double)ph / p->U + (double)(k - p->width) / p->D) * base_freq;
+            t = std::max(-(double)lowpass_filter_width, std::min((double)lowpass_filter_width, t));
+            double window;
+            if (method == 0) {
+                const double c = cos(t * kPi / lowpass_filter_width / 2.0);
+                window = c * c;
+            } else {
+                const double r = t / lowpass_filter_width;
+                window = bessel_i0(beta * sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+            }
+            t *= kPi;
+            const double sinc = t == 0.0 ? 1.0 : sin(t) / t;
+            p->kern[(size_t)ph * p->W + k] = (float)(sinc * window * scale);
+        }
+    if (cudaMalloc(reinterpret_cast<void**>(&p->d_kern), p->kern.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(p->d_kern, p->kern.data(), p->kern.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("cudaMalloc/cudaMemcpy of the resampling kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        hmfe_resample_plan_destroy(p);
+        return HMFE_ERR_CUDA;
+    }
+    *plan = p;
+    return HMFE_OK;
+}
+
+// librosa / torchaudio output length: ceil(n * new / orig)
+int64_t hmfe_resample_out_len(const hmfe_resample_plan* p, int64_t n_in) {
+    if (!p || n_in < 0) return -1;
+    return (n_in * p->U + p->D - 1) / p->D;
+}
+
+int hmfe_resample_last_launches(const hmfe_resample_plan* p) { return p ? p->last_launches : 0; }
+
+int hmfe_resample_taps(const hmfe_resample_plan* p, int* n_phases, int* n_taps, float* h_out) {
+    HMFE_REQUIRE(p, "NULL plan");
+    if (n_phases) *n_phases = p->U;
+    if (n_taps) *n_taps = p->W;
+    if (h_out) std::copy(p->kern.begin(), p->kern.end(), h_out);
+    return HMFE_OK;
+}
+
+int hmfe_resample_batch(hmfe_resample_plan* p, const float* d_in, const int64_t* h_in_offsets, int64_t n_clips,
+                        float* d_out, void* stream) {
+    HMFE_REQUIRE(p && h_in_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
+    p->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_in && d_out, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = 3 * (size_t)(n_clips + 1) * sizeof(int64_t);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = p->ring.acquire(bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    int64_t* hi = static_cast<int64_t*>(hbuf);
+    int64_t* ho = hi + (n_clips + 1);
+    int64_t* ht = ho + (n_clips + 1);
+    ho[0] = ht[0] = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_in_offsets[i + 1] - h_in_offsets[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 28, "clip %lld has invalid length %lld", (long long)i, (long long)n);
+        const int64_t m = hmfe_resample_out_len(p, n);
+        hi[i] = h_in_offsets[i];
+        ho[i + 1] = ho[i] + m;
+        ht[i + 1] = ht[i] + (m + kRsTile - 1) / kRsTile;
+    }
+    hi[n_clips] = h_in_offsets[n_clips];
+    int rc = p->ring.upload(slot, bytes, st);
+    if (rc != HMFE_OK) return rc;
+    ResampleBatch b{};
+    b.x = d_in;
+    b.y = d_out;
+    b.in_off = static_cast<int64_t*>(dbuf);
+    b.out_off = b.in_off + (n_clips + 1);
+    b.kern = p->d_kern;
+    b.n_clips = n_clips;
+    b.n_out_total = ho[n_clips];
+    b.U = p->U;
+    b.D = p->D;
+    b.W = p->W;
+    b.width = p->width;
+    const int64_t tiles = ht[n_clips];
+    if (tiles > 0) {
+        HMFE_REQUIRE(tiles < (int64_t)INT32_MAX, "resample grid too large");
+        resample_kernel<<<(unsigned)tiles, 256, 0, st>>>(b, b.in_off + 2 * (n_clips + 1));
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        p->last_launches = 1;
+    }
+    return p->ring.release(slot, st);
+}
+
+}  // extern "C"

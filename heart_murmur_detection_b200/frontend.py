@@ -162,3 +162,475 @@ def logmel_from_host(plan: LogMelPlan, h_wav: torch.Tensor, offsets, h_out: torc
     for s in cache["streams"]:
         s.synchronize()
     return h_out, fo
+
+
+# =============================================================================================
+# Context for plan-less stages
+# =============================================================================================
+
+
+class Context:
+    """hmfe_ctx: descriptor staging + device scratch for trim / gather / IIR / spectrogram ops."""
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.hmfe_ctx_create(C.byref(self._h)), "hmfe_ctx_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.hmfe_ctx_destroy(h)
+            self._h = None
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.hmfe_ctx_last_launches(self._h))
+
+
+_ctxs: dict = {}
+
+
+def default_ctx() -> Context:
+    key = (torch.cuda.current_device(), threading.get_ident())
+    with _plans_lock:
+        c = _ctxs.get(key)
+        if c is None:
+            c = _ctxs[key] = Context()
+        return c
+
+
+# =============================================================================================
+# Butterworth band-pass design (host, float64) - the coefficients scipy.signal.butter returns
+# for src/util.py:113-119, derived from the textbook construction (analog prototype ->
+# band-pass transform -> bilinear transform).
+# =============================================================================================
+
+
+def butter_bandpass_zpk(lowcut, highcut, fs, order=5):
+    nyq = 0.5 * fs
+    wn = np.array([lowcut / nyq, highcut / nyq], dtype=np.float64)
+    if not (0 < wn[0] < wn[1] < 1):
+        raise ValueError("band edges must satisfy 0 < low < high < fs/2")
+    n = int(order)
+    m = np.arange(-n + 1, n, 2)
+    p = -np.exp(1j * np.pi * m / (2 * n))  # analog Butterworth prototype, unit cutoff
+    fs_d = 2.0
+    warped = 2 * fs_d * np.tan(np.pi * wn / fs_d)
+    bw, wo = warped[1] - warped[0], np.sqrt(warped[0] * warped[1])
+    p_lp = p * bw / 2
+    root = np.sqrt(p_lp.astype(complex) ** 2 - wo**2)
+    p_bp = np.concatenate([p_lp + root, p_lp - root])
+    z_bp = np.zeros(n)
+    k_bp = bw**n
+    fs2 = 2 * fs_d
+    z_d = np.concatenate([(fs2 + z_bp) / (fs2 - z_bp), -np.ones(len(p_bp) - len(z_bp))])
+    p_d = (fs2 + p_bp) / (fs2 - p_bp)
+    k_d = k_bp * np.real(np.prod(fs2 - z_bp) / np.prod(fs2 - p_bp))
+    return z_d, p_d, float(k_d)
+
+
+def butter_bandpass_ba(lowcut, highcut, fs, order=5):
+    """(b, a) transfer-function coefficients - what ``_butter_bandpass`` returns."""
+    z, p, k = butter_bandpass_zpk(lowcut, highcut, fs, order)
+    b = k * np.real(np.poly(z))
+    a = np.real(np.poly(p))
+    return b, a
+
+
+def butter_bandpass_sos(lowcut, highcut, fs, order=5) -> np.ndarray:
+    """Second-order sections [order, 6]: zeros (+1, -1) and one conjugate pole pair per section."""
+    z, p, k = butter_bandpass_zpk(lowcut, highcut, fs, order)
+    tol = 1e-12
+    upper = p[np.imag(p) > tol]
+    upper = upper[np.argsort(np.abs(upper))]
+    real = np.sort(np.real(p[np.abs(np.imag(p)) <= tol]))
+    if 2 * len(upper) + len(real) != len(p) or len(real) % 2:
+        raise ValueError("unexpected pole layout in a Butterworth band-pass design")
+    dens = [[1.0, -2.0 * np.real(q), np.abs(q) ** 2] for q in upper]
+    dens += [[1.0, -(real[i] + real[i + 1]), real[i] * real[i + 1]] for i in range(0, len(real), 2)]
+    sos = np.zeros((len(dens), 6), dtype=np.float64)
+    for i, den in enumerate(dens):
+        sos[i] = [1.0, 0.0, -1.0] + den
+    sos[0, :3] *= k
+    return sos
+
+
+# =============================================================================================
+# Device stages
+# =============================================================================================
+
+
+def iir_sos(wav: torch.Tensor, offsets, sos: np.ndarray, out: torch.Tensor | None = None, out_dtype=torch.float32,
+            ctx: Context | None = None, stream=None) -> torch.Tensor:
+    """Causal zero-state SOS cascade in float64 (``lfilter`` semantics) over a ragged batch."""
+    _require_cuda_f32(wav, "wav")
+    o = _as_offsets(offsets)
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    ctx = ctx or default_ctx()
+    if out is None:
+        out = torch.empty(wav.numel(), dtype=out_dtype, device=wav.device)
+    y32 = C.c_void_p(out.data_ptr()) if out.dtype == torch.float32 else C.c_void_p()
+    y64 = C.c_void_p(out.data_ptr()) if out.dtype == torch.float64 else C.c_void_p()
+    if not (y32 or y64):
+        raise TypeError("out must be float32 or float64")
+    with torch.cuda.device(wav.device):
+        check(
+            _lib.hmfe_iir_sos_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
+                                    sos.ctypes.data_as(C.c_void_p), sos.shape[0], y32, y64, _stream_ptr(stream)),
+            "hmfe_iir_sos_batch",
+        )
+    return out
+
+
+def trim_indices(wav: torch.Tensor, offsets, frame_length=1600, hop_length=800, top_db=60.0, ctx: Context | None = None,
+                 stream=None) -> torch.Tensor:
+    """int64 CUDA tensor [n_clips, 2] of clip-relative (start, end) - ``librosa.effects.trim`` indices."""
+    _require_cuda_f32(wav, "wav")
+    o = _as_offsets(offsets)
+    ctx = ctx or default_ctx()
+    se = torch.empty((o.size - 1, 2), dtype=torch.int64, device=wav.device)
+    with torch.cuda.device(wav.device):
+        check(
+            _lib.hmfe_trim_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
+                                 int(frame_length), int(hop_length), float(top_db), C.c_void_p(se.data_ptr()),
+                                 _stream_ptr(stream)),
+            "hmfe_trim_batch",
+        )
+    return se
+
+
+GATHER_DTYPE = np.dtype(
+    [("src_off", "<i8"), ("dst_off", "<i8"), ("len", "<i4"), ("period", "<i4"), ("a_end", "<i4"), ("a_phase", "<i4"),
+     ("b_end", "<i4"), ("b_start", "<i4")]
+)
+assert GATHER_DTYPE.itemsize == C.sizeof(_lib.GatherDesc)
+
+CROP_DTYPE = np.dtype([("src_row", "<i8"), ("n_rows", "<i4"), ("spec_id", "<i4"), ("gain", "<f4"), ("reserved", "<i4")])
+assert CROP_DTYPE.itemsize == C.sizeof(_lib.CropDesc)
+
+
+def gather(src: torch.Tensor, dst: torch.Tensor, descs: np.ndarray, ctx: Context | None = None, stream=None):
+    """Apply host-built ``hmfe_gather_desc`` records (offsets are element offsets into src / dst)."""
+    _require_cuda_f32(src, "src")
+    _require_cuda_f32(dst, "dst")
+    descs = np.ascontiguousarray(descs, dtype=GATHER_DTYPE)
+    ctx = ctx or default_ctx()
+    with torch.cuda.device(src.device):
+        check(
+            _lib.hmfe_gather_batch(ctx._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                   descs.ctypes.data_as(C.c_void_p), descs.size, _stream_ptr(stream)),
+            "hmfe_gather_batch",
+        )
+    return dst
+
+
+class FbankPlan:
+    """Kaldi fbank for ragged batches (src/util.py:845-856; extract_feature.py:232-243)."""
+
+    def __init__(self, sample_rate=16000, frame_length=25.0, frame_shift=10.0, num_mel_bins=128, low_freq=20.0,
+                 high_freq=0.0, preemphasis=0.97, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_mels = int(num_mel_bins)
+        self.win = int(sample_rate * frame_length * 0.001)
+        self.shift = int(sample_rate * frame_shift * 0.001)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(
+                _lib.hmfe_fbank_plan_create(C.byref(self._h), int(sample_rate), float(frame_length), float(frame_shift),
+                                            self.n_mels, float(low_freq), float(high_freq), float(preemphasis)),
+                "hmfe_fbank_plan_create",
+            )
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.hmfe_fbank_plan_destroy(h)
+            self._h = None
+
+    def num_frames(self, lengths) -> np.ndarray:
+        n = np.asarray(lengths, dtype=np.int64)
+        return np.where(n >= self.win, 1 + (n - self.win) // self.shift, 0)
+
+    def mel_basis(self) -> np.ndarray:
+        out = np.empty((self.n_mels, 257), dtype=np.float32)
+        check(_lib.hmfe_fbank_mel_basis(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.hmfe_fbank_last_launches(self._h))
+
+    def views(self, wav: torch.Tensor, starts, lengths, rows_per_clip=0, out: torch.Tensor | None = None, stream=None):
+        """fbank of the clips wav[starts[i] : starts[i]+lengths[i]].  Returns (out, row_offsets)."""
+        _require_cuda_f32(wav, "wav")
+        st = np.ascontiguousarray(starts, dtype=np.int64)
+        ln = np.ascontiguousarray(lengths, dtype=np.int64)
+        m = self.num_frames(ln)
+        rows = np.full_like(m, rows_per_clip) if rows_per_clip else m
+        ro = np.zeros(len(m) + 1, dtype=np.int64)
+        np.cumsum(rows, out=ro[1:])
+        if out is None:
+            out = torch.empty((int(ro[-1]), self.n_mels), dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            check(
+                _lib.hmfe_fbank_batch_views(self._h, C.c_void_p(wav.data_ptr()), st.ctypes.data_as(C.c_void_p),
+                                            ln.ctypes.data_as(C.c_void_p), len(ln), C.c_void_p(out.data_ptr()),
+                                            int(rows_per_clip), _stream_ptr(stream)),
+                "hmfe_fbank_batch_views",
+            )
+        return out, ro
+
+    def __call__(self, wav: torch.Tensor, offsets, rows_per_clip=0, out=None, stream=None):
+        o = _as_offsets(offsets)
+        return self.views(wav, o[:-1], np.diff(o), rows_per_clip, out, stream)
+
+
+class ResamplePlan:
+    """Polyphase windowed-sinc resampler (torchaudio.transforms.Resample algorithm)."""
+
+    def __init__(self, orig_freq, new_freq=16000, lowpass_filter_width=6, rolloff=0.99, method="sinc_interp_hann",
+                 beta=None, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.orig, self.new = int(orig_freq), int(new_freq)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(
+                _lib.hmfe_resample_plan_create(C.byref(self._h), self.orig, self.new, int(lowpass_filter_width),
+                                               float(rolloff), {"sinc_interp_hann": 0, "sinc_interp_kaiser": 1}[method],
+                                               float(beta or 0.0)),
+                "hmfe_resample_plan_create",
+            )
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.hmfe_resample_plan_destroy(h)
+            self._h = None
+
+    def out_lengths(self, lengths) -> np.ndarray:
+        n = np.asarray(lengths, dtype=np.int64)
+        g = np.gcd(self.orig, self.new)
+        u, d = self.new // g, self.orig // g
+        return (n * u + d - 1) // d
+
+    def taps(self) -> np.ndarray:
+        u, w = C.c_int(), C.c_int()
+        check(_lib.hmfe_resample_taps(self._h, C.byref(u), C.byref(w), None))
+        out = np.empty((u.value, w.value), dtype=np.float32)
+        check(_lib.hmfe_resample_taps(self._h, None, None, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.hmfe_resample_last_launches(self._h))
+
+    def __call__(self, wav: torch.Tensor, offsets, stream=None):
+        """Returns (resampled wav, new offsets)."""
+        _require_cuda_f32(wav, "wav")
+        o = _as_offsets(offsets)
+        no = np.zeros(o.size, dtype=np.int64)
+        np.cumsum(self.out_lengths(np.diff(o)), out=no[1:])
+        out = torch.empty(int(no[-1]), dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            check(
+                _lib.hmfe_resample_batch(self._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
+                                         C.c_void_p(out.data_ptr()), _stream_ptr(stream)),
+                "hmfe_resample_batch",
+            )
+        return out, no
+
+
+def fbank_plan(**kw) -> FbankPlan:
+    key = ("fbank", torch.cuda.current_device(), tuple(sorted(kw.items())))
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is None:
+            p = _plans[key] = FbankPlan(**kw)
+        return p
+
+
+def resample_plan(orig_freq, new_freq=16000, **kw) -> ResamplePlan:
+    key = ("resample", torch.cuda.current_device(), int(orig_freq), int(new_freq), tuple(sorted(kw.items())))
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is None:
+            p = _plans[key] = ResamplePlan(orig_freq, new_freq, **kw)
+        return p
+
+
+def logmel_views(plan: LogMelPlan, wav: torch.Tensor, starts, lengths, out=None, mode="normalised", stream=None):
+    """Log-mel of the clips wav[starts[i] : starts[i]+lengths[i]].  Returns (out, frame_offsets)."""
+    _require_cuda_f32(wav, "wav")
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    ln = np.ascontiguousarray(lengths, dtype=np.int64)
+    fo = np.zeros(len(ln) + 1, dtype=np.int64)
+    np.cumsum(1 + ln // plan.hop, out=fo[1:])
+    if out is None:
+        out = torch.empty((int(fo[-1]), plan.n_mels), dtype=torch.float32, device=wav.device)
+    with torch.cuda.device(wav.device):
+        check(
+            _lib.hmfe_logmel_batch_views(plan._h, C.c_void_p(wav.data_ptr()), st.ctypes.data_as(C.c_void_p),
+                                         ln.ctypes.data_as(C.c_void_p), len(ln), C.c_void_p(out.data_ptr()),
+                                         OUT_MODES[mode], _stream_ptr(stream)),
+            "hmfe_logmel_batch_views",
+        )
+    return out, fo
+
+
+# =============================================================================================
+# Spectrogram-domain dataset ops (src/util.py:26-51)
+# =============================================================================================
+
+
+def spec_means(spec: torch.Tensor, row_offsets, ctx: Context | None = None, stream=None) -> torch.Tensor:
+    _require_cuda_f32(spec, "spec")
+    ro = _as_offsets(row_offsets)
+    ctx = ctx or default_ctx()
+    mean = torch.empty(ro.size - 1, dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        check(
+            _lib.hmfe_spec_mean_batch(ctx._h, C.c_void_p(spec.data_ptr()), ro.ctypes.data_as(C.c_void_p), ro.size - 1,
+                                      int(spec.shape[-1]), C.c_void_p(mean.data_ptr()), _stream_ptr(stream)),
+            "hmfe_spec_mean_batch",
+        )
+    return mean
+
+
+def spec_crop(spec: torch.Tensor, descs: np.ndarray, out_rows: int, row_mask: torch.Tensor | None = None,
+              means: torch.Tensor | None = None, ctx: Context | None = None, stream=None) -> torch.Tensor:
+    """Apply ``hmfe_crop_desc`` records: returns [n_items, out_rows, n_cols]."""
+    _require_cuda_f32(spec, "spec")
+    descs = np.ascontiguousarray(descs, dtype=CROP_DTYPE)
+    ctx = ctx or default_ctx()
+    n_cols = int(spec.shape[-1])
+    out = torch.empty((descs.size, int(out_rows), n_cols), dtype=torch.float32, device=spec.device)
+    if row_mask is not None and not (row_mask.is_cuda and row_mask.dtype == torch.uint8 and row_mask.is_contiguous()):
+        raise TypeError("row_mask must be a contiguous uint8 CUDA tensor")
+    with torch.cuda.device(spec.device):
+        check(
+            _lib.hmfe_spec_crop_batch(ctx._h, C.c_void_p(spec.data_ptr()), n_cols, descs.ctypes.data_as(C.c_void_p),
+                                      descs.size, C.c_void_p(row_mask.data_ptr()) if row_mask is not None else None,
+                                      C.c_void_p(means.data_ptr()) if means is not None else None,
+                                      C.c_void_p(out.data_ptr()), int(out_rows), _stream_ptr(stream)),
+            "hmfe_spec_crop_batch",
+        )
+    return out
+
+
+# =============================================================================================
+# Host index planners - integer work, bit-exact with the reference
+# (src/util.py:504-620, 257-259; extract_feature.py:250-259).  A chunk is either a straight
+# VIEW of the (trimmed) clip or a GATHER record (tile / repeat / zero pad).
+# =============================================================================================
+
+import math
+import random as _random
+
+
+def _view(start, length):
+    return ("view", int(start), int(length))
+
+
+def _gather(length, src_start=0, period=1, a_end=0, a_phase=0, b_end=0, b_start=0):
+    return ("gather", int(length), int(src_start), int(period), int(a_end), int(a_phase), int(b_end), int(b_start))
+
+
+def plan_zero_padding(src_start, src_len, L):
+    """_zero_padding (src/util.py:504-519) of clip[src_start : src_start+src_len] to L samples."""
+    if src_len > L:
+        raise ValueError("slice longer than the padded length (the reference would raise here too)")
+    if src_len / L < 0.5:
+        copies = (L - 1) // src_len if src_len > 0 else 0  # while cursor + len < L
+        return _gather(L, src_start=src_start, period=max(1, src_len), a_end=copies * src_len, a_phase=0,
+                       b_end=copies * src_len)
+    if src_len == L:
+        return _view(src_start, L)
+    return _gather(L, src_start=src_start, period=max(1, src_len), a_end=0, b_end=src_len, b_start=0)
+
+
+def plan_equally_slice_pad(n, desired_length, sample_rate):
+    """_equally_slice_pad_sample (src/util.py:522-547)."""
+    L = int(desired_length * sample_rate)
+    n_slices = int(math.ceil((n / sample_rate) / desired_length))
+    per = n // n_slices
+    out, lo = [], 0
+    for _ in range(n_slices):
+        hi = min(lo + per, n)
+        out.append(plan_zero_padding(lo, hi - lo, L))
+        lo = hi
+    return out
+
+
+def plan_duplicate_padding(n, src_start, src_len, L):
+    """_duplicate_padding (src/util.py:550-575): source at the end, tail of the doubled clip in
+    front (the reference's seeded draw 0.0617 < 0.5 always selects this branch).  The reseed of
+    Python's global RNG is reproduced by the caller (``reseed_like_reference``)."""
+    left = L - src_len
+    if left == 0:
+        return _view(src_start, L)
+    len_aug = n
+    while len_aug < left:
+        len_aug *= 2
+    return _gather(L, src_start=0, period=n, a_end=left, a_phase=(len_aug - left) % n, b_end=L, b_start=src_start)
+
+
+def reseed_like_reference():
+    """Side effect of every _duplicate_padding call (src/util.py:564-565)."""
+    _random.seed(7456)
+    _random.random()
+
+
+def plan_split_pad(n, desired_length, sample_rate, types="repeat"):
+    """split_pad_sample (src/util.py:578-620) for a clip of n samples -> list of chunks."""
+    if types == "zero":
+        return plan_equally_slice_pad(n, desired_length, sample_rate)
+    L = int(desired_length * sample_rate)
+    out = []
+    if n > L:
+        hop = L // 2
+        n_full = 1 + (n - L) // hop
+        out += [_view(j * hop, L) for j in range(n_full)]
+        last = n_full * hop
+        out.append(plan_duplicate_padding(n, last, n - last, L))
+    else:
+        out.append(plan_duplicate_padding(n, 0, n, L))
+    return out
+
+
+def plan_split_sample(n, desired_length, sample_rate):
+    """split_sample (extract_feature.py:250-259): non-overlapping views, last one short."""
+    L = int(desired_length * sample_rate)
+    return [_view(L * i, min(L, n - L * i)) for i in range(int(np.ceil(n / L)))]
+
+
+def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, ctx: Context | None = None, stream=None):
+    """Turn per-clip chunk plans into (starts, lengths, clip_ids) views into ``work``.
+
+    ``work[:used]`` holds the signal; gather chunks are written behind it (the buffer is
+    re-allocated with the signal copied if its spare capacity is too small).
+    Returns (work, starts, lengths, clip_ids).
+    """
+    starts, lengths, clip_ids, recs = [], [], [], []
+    tail = used
+    for cid, (c0, chunks) in enumerate(zip(clip_starts, chunk_lists)):
+        for ch in chunks or ():
+            if ch[0] == "view":
+                starts.append(c0 + ch[1])
+                lengths.append(ch[2])
+            else:
+                _, length, src_start, period, a_end, a_phase, b_end, b_start = ch
+                recs.append((c0 + src_start, tail, length, period, a_end, a_phase, b_end, b_start))
+                starts.append(tail)
+                lengths.append(length)
+                tail += length
+            clip_ids.append(cid)
+    if recs:
+        if tail > work.numel():
+            bigger = torch.empty(tail, dtype=torch.float32, device=work.device)
+            bigger[:used].copy_(work[:used])
+            work = bigger
+        descs = np.array(recs, dtype=GATHER_DTYPE)
+        gather(work, work, descs, ctx=ctx, stream=stream)
+    return work, np.asarray(starts, dtype=np.int64), np.asarray(lengths, dtype=np.int64), np.asarray(clip_ids, dtype=np.int64)

@@ -1,0 +1,246 @@
+"""Batched front-end pipelines: the reference's per-file functions, run on ragged batches.
+
+Each function takes the decoded 16 kHz batch (``wav``: float32 CUDA tensor with all clips back
+to back, ``offsets``: int64 host array) and runs
+    [band-pass] -> silence trim -> pad / split / cut (host index planning) -> log-mel | fbank
+on the GPU.  The only host round trip is the (start, end) trim indices (16 bytes per clip),
+which the reference's own control flow needs (durations decide padding and skipping).
+
+Reference functions (``/root/reference``):
+    get_entire_signal_librosa      src/util.py:205-267
+    get_split_signal_librosa       src/util.py:309-364
+    get_split_signal_fbank_pad     src/util.py:794-860
+    get_split_signal_fbank         src/benchmark/baseline/extract_feature.py:213-247
+    get_individual_segments_librosa src/util.py:141-202
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import frontend as fe
+
+
+@dataclass
+class ChunkBatch:
+    """Chunks (views into ``work``) produced from a batch of recordings."""
+
+    work: torch.Tensor
+    starts: np.ndarray      # [n_chunks] element offsets into work
+    lengths: np.ndarray     # [n_chunks]
+    clip_ids: np.ndarray    # [n_chunks] source recording of each chunk
+    n_clips: int
+    valid: np.ndarray       # [n_clips] False where the reference returns None / [] ("too short")
+    trim: np.ndarray        # [n_clips, 2] trim indices (start, end), clip relative
+    used_duplicate_padding: bool = False
+    launches: int = 0
+
+    def chunks_of(self, clip: int) -> np.ndarray:
+        return np.flatnonzero(self.clip_ids == clip)
+
+
+@dataclass
+class FeatureBatch:
+    features: torch.Tensor      # [sum rows, n_mels]
+    row_offsets: np.ndarray     # [n_chunks + 1]
+    chunks: ChunkBatch
+    launches: int = 0
+
+    def chunk(self, k: int) -> torch.Tensor:
+        return self.features[int(self.row_offsets[k]) : int(self.row_offsets[k + 1])]
+
+    def of_clip(self, clip: int):
+        return [self.chunk(int(k)) for k in self.chunks.chunks_of(clip)]
+
+
+def _sos_for(butterworth_filter, lowcut, highcut, sample_rate):
+    if not butterworth_filter:
+        return None
+    return fe.butter_bandpass_sos(lowcut, highcut, sample_rate, order=int(butterworth_filter))
+
+
+def prepare_chunks(wav: torch.Tensor, offsets, chunker, *, sample_rate=16000, butterworth_filter=None, lowcut=200,
+                   highcut=1800, pad_hint: int = 0, ctx: fe.Context | None = None) -> ChunkBatch:
+    """[band-pass] -> trim -> ``chunker(n_trimmed)`` per clip -> materialised chunk views.
+
+    ``chunker`` returns a list of chunk plans (frontend.plan_*) or None to drop the clip.
+    ``pad_hint`` = expected padded-chunk length, used to size the spare capacity of the work
+    buffer so that padded copies land behind the signal without re-allocation.
+    """
+    ctx = ctx or fe.default_ctx()
+    o = fe._as_offsets(offsets)
+    n = o.size - 1
+    total = int(o[-1])
+    launches = 0
+    sos = _sos_for(butterworth_filter, lowcut, highcut, sample_rate)
+    lens = np.diff(o)
+    spare = int(pad_hint) * (int((lens < pad_hint).sum()) + 16) if pad_hint else 0
+    if sos is not None:
+        work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
+        fe.iir_sos(wav, o, sos, out=work, ctx=ctx)
+        launches += ctx.last_launches
+    else:
+        work = wav
+    se = fe.trim_indices(work, o, frame_length=int(sample_rate / 10), hop_length=int(int(sample_rate / 10) / 2), ctx=ctx)
+    launches += ctx.last_launches
+    se = se.cpu().numpy()  # the one host round trip: durations drive the reference's control flow
+    chunk_lists, valid = [], np.ones(n, dtype=bool)
+    chunker.dup_called = False  # set by chunkers whenever the reference would call _duplicate_padding
+    for i in range(n):
+        chunks = chunker(int(se[i, 1] - se[i, 0]))
+        if chunks is None:
+            valid[i] = False
+            chunks = []
+        chunk_lists.append(chunks)
+    dup = bool(getattr(chunker, "dup_called", False))
+    clip_starts = o[:-1] + se[:, 0]
+    work, starts, lengths, clip_ids = fe.materialise_chunks(work, total, clip_starts, chunk_lists, ctx=ctx)
+    if any(c[0] == "gather" for cl in chunk_lists for c in cl):
+        launches += ctx.last_launches
+    return ChunkBatch(work, starts, lengths, clip_ids, n, valid, se, dup, launches)
+
+
+def _truncate(chunk, new_len):
+    if chunk[0] == "view":
+        return fe._view(chunk[1], min(chunk[2], new_len))
+    _, length, src_start, period, a_end, a_phase, b_end, b_start = chunk
+    new_len = min(length, new_len)
+    return fe._gather(new_len, src_start, period, min(a_end, new_len), a_phase, min(b_end, new_len), b_start)
+
+
+def entire_signal_chunker(input_sec=8, sample_rate=16000, pad=False, types="repeat", max_sec=None):
+    """Control flow of get_entire_signal_librosa after the trim (src/util.py:248-259)."""
+
+    def chunker(n):
+        duration = n / sample_rate
+        chunk = fe._view(0, n)
+        if duration < input_sec:
+            if not pad:
+                return None
+            if n == 0:
+                return None  # the reference would loop forever / divide by zero on an empty clip
+            chunk = fe.plan_split_pad(n, input_sec, sample_rate, types)[0]
+            chunker.dup_called = chunker.dup_called or types != "zero"
+        if max_sec and duration > max_sec:
+            chunk = _truncate(chunk, int(max_sec * sample_rate))
+        return [chunk]
+
+    return chunker
+
+
+def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types="repeat"):
+    """get_split_signal_librosa / get_split_signal_fbank_pad after the trim (src/util.py:348-354)."""
+
+    def chunker(n):
+        if n == 0:
+            return None
+        chunks = fe.plan_split_pad(n, input_sec, sample_rate, types)
+        chunker.dup_called = chunker.dup_called or types != "zero"
+        duration = n / sample_rate
+        if trim_tail and duration > input_sec and (duration % input_sec) * 2 < input_sec:  # decide_droplast
+            chunks.pop()
+        return chunks
+
+    return chunker
+
+
+def log_mel_features(cb: ChunkBatch, f_max=8000, n_mels=64, f_min=50, nfft=1024, hop=512, sample_rate=16000,
+                     mode="normalised") -> FeatureBatch:
+    plan = fe.logmel_plan(sample_rate, n_mels, f_min, f_max, nfft, hop)
+    if len(cb.starts) == 0:
+        return FeatureBatch(torch.empty((0, n_mels), device=cb.work.device), np.zeros(1, np.int64), cb, cb.launches)
+    out, fo = fe.logmel_views(plan, cb.work, cb.starts, cb.lengths, mode=mode)
+    return FeatureBatch(out, fo, cb, cb.launches + plan.last_launches)
+
+
+def fbank_features(cb: ChunkBatch, sample_rate=16000, rows_per_chunk=0, min_samples_exclusive=400) -> FeatureBatch:
+    """kaldi fbank per chunk; chunks of <= 400 samples are skipped as in the reference
+    (``if waveform.shape[1] > 400``, src/util.py:844; extract_feature.py:231)."""
+    plan = fe.fbank_plan(sample_rate=sample_rate)
+    keep = cb.lengths > min_samples_exclusive
+    kept = ChunkBatch(cb.work, cb.starts[keep], cb.lengths[keep], cb.clip_ids[keep], cb.n_clips, cb.valid, cb.trim,
+                      cb.used_duplicate_padding, cb.launches)
+    if len(kept.starts) == 0:
+        return FeatureBatch(torch.empty((0, plan.n_mels), device=cb.work.device), np.zeros(1, np.int64), kept, cb.launches)
+    out, ro = plan.views(cb.work, kept.starts, kept.lengths, rows_per_clip=rows_per_chunk)
+    return FeatureBatch(out, ro, kept, cb.launches + plan.last_launches)
+
+
+# ----------------------------------------------------------------------------------------------
+# batch versions of the reference entry points
+# ----------------------------------------------------------------------------------------------
+
+
+def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
+                        pad=False, types="repeat", lowcut=200, highcut=1800, max_sec=None, f_max=8000):
+    """get_entire_signal_librosa over a batch.  Returns FeatureBatch (spectrogram=True) or ChunkBatch."""
+    L = int(input_sec * sample_rate)
+    cb = prepare_chunks(wav, offsets, entire_signal_chunker(input_sec, sample_rate, pad, types, max_sec),
+                        sample_rate=sample_rate, butterworth_filter=butterworth_filter, lowcut=lowcut, highcut=highcut,
+                        pad_hint=L if pad else 0)
+    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
+
+
+def split_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
+                       trim_tail=False, lowcut=200, highcut=1800, f_max=8000):
+    """get_split_signal_librosa over a batch."""
+    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail), sample_rate=sample_rate,
+                        butterworth_filter=butterworth_filter, lowcut=lowcut, highcut=highcut,
+                        pad_hint=int(input_sec * sample_rate))
+    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
+
+
+def split_signal_fbank_pad_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None,
+                                 spectrogram=False, trim_tail=False, rows_per_chunk=0):
+    """get_split_signal_fbank_pad over a batch."""
+    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail), sample_rate=sample_rate,
+                        butterworth_filter=butterworth_filter, lowcut=200, highcut=1800,
+                        pad_hint=int(input_sec * sample_rate))
+    return fbank_features(cb, sample_rate, rows_per_chunk) if spectrogram else cb
+
+
+def split_signal_fbank_batch(wav, offsets, input_sec=10, sample_rate=16000, rows_per_chunk=0):
+    """get_split_signal_fbank (extract_feature.py:213-247) over a batch."""
+
+    def chunker(n):
+        return fe.plan_split_sample(n, input_sec, sample_rate)
+
+    cb = prepare_chunks(wav, offsets, chunker, sample_rate=sample_rate)
+    return fbank_features(cb, sample_rate, rows_per_chunk)
+
+
+def individual_segments_batch(wav, offsets, input_sec=8, sample_rate=16000, hop_sec=2, butterworth_filter=None,
+                              spectrogram=False):
+    """get_individual_segments_librosa (src/util.py:141-202) over a batch (default f_max=2000 log-mel)."""
+
+    def chunker(n):
+        duration = n / sample_rate
+        if duration < 2:
+            return None
+
+        def cut(t0, t1):
+            a, b = min(int(t0 * sample_rate), n), min(int(t1 * sample_rate), n)
+            return a, b - a
+
+        chunks, start, end = [], 0, input_sec
+        while end <= duration:
+            chunks.append(fe._view(*cut(start, end)))
+            start += hop_sec
+            end += hop_sec
+        if start + 2 < duration:
+            a, ln = cut(start, end)
+            pad = fe.plan_split_pad(ln, 8, sample_rate)[0]
+            chunker.dup_called = True
+            if pad[0] == "view":
+                pad = fe._view(a + pad[1], pad[2])
+            else:  # re-base the gather on the tail segment
+                _, length, src_start, period, a_end, a_phase, b_end, b_start = pad
+                pad = fe._gather(length, a + src_start, period, a_end, a_phase, b_end, b_start)
+            chunks.append(pad)
+        return chunks
+
+    cb = prepare_chunks(wav, offsets, chunker, sample_rate=sample_rate, butterworth_filter=butterworth_filter,
+                        lowcut=200, highcut=1800, pad_hint=8 * sample_rate)
+    return log_mel_features(cb, f_max=2000, sample_rate=sample_rate) if spectrogram else cb

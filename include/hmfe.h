@@ -59,6 +59,10 @@ int64_t hmfe_logmel_num_frames(int64_t n_samples, int hop);
 int hmfe_logmel_mel_basis(const hmfe_logmel_plan* plan, float* h_out);
 int hmfe_logmel_batch(hmfe_logmel_plan* plan, const float* d_wav, const int64_t* h_offsets, int64_t n_clips,
                       float* d_out, int out_mode, void* stream);
+/* same, but clip i is the view d_wav[h_starts[i] : h_starts[i] + h_lengths[i]] (clips may overlap
+ * or leave gaps: trimmed recordings, 50 %-overlap chunks and padded copies are all views) */
+int hmfe_logmel_batch_views(hmfe_logmel_plan* plan, const float* d_wav, const int64_t* h_starts,
+                            const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream);
 /* number of kernel launches the last hmfe_logmel_batch call on this plan issued */
 int hmfe_logmel_last_launches(const hmfe_logmel_plan* plan);
 /* Measurement hook: when enabled, every hmfe_logmel_batch call records CUDA events on its
@@ -66,6 +70,119 @@ int hmfe_logmel_last_launches(const hmfe_logmel_plan* plan);
  * synchronises on them, returns the summed durations since the last query and resets. */
 int hmfe_logmel_set_profile(hmfe_logmel_plan* plan, int enable);
 int hmfe_logmel_profile_ms(hmfe_logmel_plan* plan, double* power_ms, double* finalize_ms, int* n_calls);
+
+/* ------------------------------------------------------------------------------------------
+ * Context for the plan-less stages: owns descriptor staging and device scratch.  One context
+ * per host thread / stream of work; calls on one context are ordered by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_ctx hmfe_ctx;
+int hmfe_ctx_create(hmfe_ctx** ctx);
+void hmfe_ctx_destroy(hmfe_ctx* ctx);
+/* number of kernel launches issued by the last call made on this context */
+int hmfe_ctx_last_launches(const hmfe_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Silence trim: replaces librosa.effects.trim(y, top_db=60, frame_length=sr/10, hop_length=sr/20)
+ * (src/util.py:170-172, 237-244, 338-340, 820-822; extract_feature.py:219-221).
+ * Writes int64 (start, end) per clip, clip-relative, to d_start_end[n_clips][2]; (0,0) when the
+ * whole clip is silent.  Indices are exact (integer work); the RMS reduction is float32.
+ * ------------------------------------------------------------------------------------------ */
+int64_t hmfe_trim_num_frames(int64_t n_samples, int frame_length, int hop_length);
+int hmfe_trim_batch(hmfe_ctx* ctx, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, int frame_length,
+                    int hop_length, float top_db, int64_t* d_start_end, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pad / split / tile / repeat gather: applies host-computed index tables for
+ * split_pad_sample, _duplicate_padding, _equally_slice_pad_sample/_zero_padding, the max_sec
+ * cut and split_sample (src/util.py:504-620, 257-259; extract_feature.py:250-259).
+ * Output chunk element i (0 <= i < len):
+ *   i < a_end : src[src_off + (a_phase + i) mod period]
+ *   i < b_end : src[src_off + b_start + (i - a_end)]
+ *   else      : 0
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_gather_desc {
+    int64_t src_off; /* first sample of the source clip in d_src            */
+    int64_t dst_off; /* first sample of this chunk in d_dst                 */
+    int32_t len;     /* chunk length                                        */
+    int32_t period;  /* source length used for the modular (repeat) part    */
+    int32_t a_end;
+    int32_t a_phase;
+    int32_t b_end;
+    int32_t b_start;
+} hmfe_gather_desc;
+int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* h_descs,
+                      int64_t n_chunks, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Band-pass IIR: replaces scipy.signal.lfilter(b, a, x) in _butter_bandpass_filter
+ * (src/util.py:113-126) with the equivalent second-order-section cascade, float64 arithmetic,
+ * causal, zero initial state.  h_sos is [n_sections][6] = (b0 b1 b2 a0 a1 a2) as produced by
+ * scipy.signal.butter(..., output="sos") / frontend.butter_bandpass_sos.  Either output may
+ * be NULL: d_y32 feeds the device pipeline, d_y64 reproduces lfilter's float64 result.
+ * ------------------------------------------------------------------------------------------ */
+int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
+                       const double* h_sos, int n_sections, float* d_y32, double* d_y64, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Kaldi fbank: replaces torchaudio.compliance.kaldi.fbank(w, htk_compat=True,
+ * sample_frequency=16000, use_energy=False, window_type="hanning", num_mel_bins=128, dither=0,
+ * frame_shift=10, frame_length=25) (src/util.py:845-856; extract_feature.py:232-243).
+ * Frames per clip: m = 1 + (n - win)/shift for n >= win, else 0 (snip_edges).
+ * rows_per_clip == 0: output [sum m_i, n_mels], clips packed back to back.
+ * rows_per_clip  > 0: output [n_clips, rows_per_clip, n_mels]; missing rows are zero, extra
+ *                     frames dropped (model-side pad to 1024, audioMAE/models_mae.py:1178-1181).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_fbank_plan hmfe_fbank_plan;
+int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame_length_ms, double frame_shift_ms,
+                           int n_mels, double low_freq, double high_freq, double preemph);
+void hmfe_fbank_plan_destroy(hmfe_fbank_plan* plan);
+int64_t hmfe_fbank_num_frames(const hmfe_fbank_plan* plan, int64_t n_samples);
+int hmfe_fbank_mel_basis(const hmfe_fbank_plan* plan, float* h_out);
+int hmfe_fbank_batch(hmfe_fbank_plan* plan, const float* d_wav, const int64_t* h_offsets, int64_t n_clips,
+                     float* d_out, int rows_per_clip, void* stream);
+int hmfe_fbank_batch_views(hmfe_fbank_plan* plan, const float* d_wav, const int64_t* h_starts, const int64_t* h_lengths,
+                           int64_t n_clips, float* d_out, int rows_per_clip, void* stream);
+int hmfe_fbank_last_launches(const hmfe_fbank_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Polyphase resampler (the rate conversion inside librosa.load(..., sr=16000), src/util.py:153,
+ * 222,323,391,805).  Implements the windowed-sinc algorithm of torchaudio.transforms.Resample
+ * (used by the reference at src/model/models_eval.py:964-968): method 0 = sinc_interp_hann,
+ * 1 = sinc_interp_kaiser.  librosa's own default (libsoxr HQ) is a closed third-party filter
+ * design that is not installable here; see DESIGN.md ("parity unpinned").
+ * Output clip i has ceil(n_i * new / orig) samples, clips packed back to back.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_resample_plan hmfe_resample_plan;
+int hmfe_resample_plan_create(hmfe_resample_plan** plan, int orig_freq, int new_freq, int lowpass_filter_width,
+                              double rolloff, int method, double beta);
+void hmfe_resample_plan_destroy(hmfe_resample_plan* plan);
+int64_t hmfe_resample_out_len(const hmfe_resample_plan* plan, int64_t n_in);
+int hmfe_resample_taps(const hmfe_resample_plan* plan, int* n_phases, int* n_taps, float* h_out);
+int hmfe_resample_batch(hmfe_resample_plan* plan, const float* d_in, const int64_t* h_in_offsets, int64_t n_clips,
+                        float* d_out, void* stream);
+int hmfe_resample_last_launches(const hmfe_resample_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectrogram-domain dataset ops: crop_first / random_crop / random_mask / random_multiply
+ * (src/util.py:26-51) and pad-or-crop to a fixed frame count (cola_training.py:56-80,
+ * mae_training.py:88-109, audioMAE/models_mae.py:1178-1181).  Random draws happen on the host
+ * in the reference's order; the kernels apply them.
+ * d_spec is a ragged batch of spectrograms [sum T_i, n_cols] with int64 row offsets.
+ * Output item k = rows [src_row, src_row + n_rows) of d_spec (global row index), rows whose
+ * d_row_mask byte is non-zero replaced by the mean of spectrogram spec_id, everything times
+ * gain, zero padded to out_rows:  d_out[n_items][out_rows][n_cols].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_crop_desc {
+    int64_t src_row;
+    int32_t n_rows;
+    int32_t spec_id;
+    float gain;
+    int32_t reserved;
+} hmfe_crop_desc;
+int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_row_offsets, int64_t n_specs, int n_cols,
+                         float* d_mean, void* stream);
+int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const hmfe_crop_desc* h_descs, int64_t n_items,
+                         const uint8_t* d_row_mask, const float* d_mean, float* d_out, int out_rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,266 @@
+"""Parity of the remaining CUDA stages (through the C ABI) with the oracle / live third-party
+libraries / golden fixtures: IIR band-pass, silence trim, pad-split gather, Kaldi fbank,
+resampler, spectrogram-domain ops."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from cases import PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, hash_spec, sha, sha_list
+from signals import golden_signal
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "ref_util.json")))["cases"]
+
+
+def _batch(clips):
+    off = np.zeros(len(clips) + 1, dtype=np.int64)
+    np.cumsum([len(c) for c in clips], out=off[1:])
+    return torch.from_numpy(np.concatenate(clips).astype(np.float32)).cuda(), off
+
+
+def rng_fingerprint():
+    return sha(np.array(random.getstate()[1], dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------------------------- IIR
+
+
+@pytest.mark.parametrize("order", [5, 3, 1])
+def test_iir_matches_scipy_lfilter(order):
+    """<= 1e-4 * max|y|; in practice ~1e-8 (float64 cascade vs float64 TF form)."""
+    from scipy.signal import butter, lfilter
+
+    from heart_murmur_detection_b200 import frontend as fe
+
+    lens = [1, 2, 127, 128, 129, 255, 256, 257, 4095, 4096, 4097, 128000, 90001, 12, 300000]
+    clips = [golden_signal(n, seed=3 + i) for i, n in enumerate(lens)]
+    clips[3] = np.zeros(128, np.float32)
+    clips[3][0] = 1.0  # impulse
+    clips[4] = np.ones(129, np.float32)  # step
+    wav, off = _batch(clips)
+    sos = fe.butter_bandpass_sos(200, 1800, SR, order)
+    b, a = butter(order, [200 / 8000, 1800 / 8000], btype="band")
+    y64 = fe.iir_sos(wav, off, sos, out_dtype=torch.float64).cpu().numpy()
+    y32 = fe.iir_sos(wav, off, sos, out_dtype=torch.float32).cpu().numpy()
+    for i, x in enumerate(clips):
+        ref = lfilter(b, a, x)
+        assert ref.dtype == np.float64
+        tol = 1e-4 * max(np.abs(ref).max(), 1e-12)
+        assert np.abs(y64[off[i] : off[i + 1]] - ref).max() <= min(tol, 1e-6)
+        assert np.abs(y32[off[i] : off[i + 1]] - ref).max() <= tol
+
+
+def test_iir_large_batch_uses_long_chunks_and_is_linear():
+    """> 32 Mi samples switches to 512-sample chunks; check against scipy on a few clips and
+    linearity (filter(a*x + b*y) == a*filter(x) + b*filter(y)) on the whole batch."""
+    from scipy.signal import butter, lfilter
+
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c2", 120, seed=5)
+    lens[0] = 40 * SR * 16  # one very long clip to cross 32 Mi samples in total
+    assert lens.sum() > (32 << 20)
+    wav, off = synth.make_batch(lens, base_seed=77, device="cuda")
+    sos = fe.butter_bandpass_sos(200, 1800, SR, 5)
+    y = fe.iir_sos(wav, off, sos, out_dtype=torch.float64)
+    b, a = butter(5, [200 / 8000, 1800 / 8000], btype="band")
+    for i in (0, 1, 57, 119):
+        ref = lfilter(b, a, wav[off[i] : off[i + 1]].cpu().numpy())
+        assert np.abs(y[off[i] : off[i + 1]].cpu().numpy() - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max())
+    wav2 = torch.roll(wav, 12345)
+    y2 = fe.iir_sos(wav2, off, sos, out_dtype=torch.float64)
+    y3 = fe.iir_sos((0.5 * wav + 0.25 * wav2), off, sos, out_dtype=torch.float64)
+    assert (y3 - (0.5 * y + 0.25 * y2)).abs().max().item() <= 1e-6
+
+
+def test_butter_design_matches_scipy():
+    from scipy.signal import butter
+
+    from heart_murmur_detection_b200.util import _butter_bandpass
+
+    for order, lo, hi in [(5, 200, 1800), (3, 25, 400), (2, 100, 1000)]:
+        b, a = _butter_bandpass(lo, hi, SR, order)
+        bs, as_ = butter(order, [lo / 8000, hi / 8000], btype="band")
+        np.testing.assert_allclose(b, bs, rtol=1e-9, atol=1e-15)
+        np.testing.assert_allclose(a, as_, rtol=1e-9, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------- trim
+
+
+def test_trim_indices_exact():
+    from heart_murmur_detection_b200 import frontend as fe
+    from oracle import frontend as F
+
+    clips = [golden_signal(n, seed, SR, lead, tail) for _, n, seed, lead, tail in RECORDINGS]
+    for lead, tail in [(0, 0), (799, 801), (800, 1600), (2400, 0), (0, 4000), (5, 17)]:
+        clips.append(golden_signal(48000, 11, SR, lead, tail))
+    clips.append(np.zeros(5000, np.float32))                     # all silent -> (0, 0)
+    clips.append(golden_signal(30000, 12, SR, 0, 0))             # all loud
+    clips.append(golden_signal(700, 13, SR, 0, 0))               # shorter than one hop
+    clips.append((golden_signal(20000, 14, SR, 0, 0) * 1e-4).astype(np.float32))  # quiet everywhere (relative threshold)
+    wav, off = _batch(clips)
+    se = fe.trim_indices(wav, off).cpu().numpy()
+    for i, x in enumerate(clips):
+        _, idx = F.trim_silence(x, SR)
+        assert [int(se[i, 0]), int(se[i, 1])] == [int(idx[0]), int(idx[1])], i
+    for k, (name, *_r) in enumerate(RECORDINGS):
+        assert [int(se[k, 0]), int(se[k, 1])] == META[f"trim/{name}"]
+
+
+# ------------------------------------------------------------------------------------------- pad / split
+
+
+@pytest.mark.parametrize("sec", PAD_SPLIT_SECS)
+def test_split_pad_sample_bit_exact_vs_reference(sec):
+    """Golden hashes were produced by the reference's own split_pad_sample / split_sample."""
+    from heart_murmur_detection_b200 import util as U
+    from heart_murmur_detection_b200.extract_feature import split_sample
+
+    for n in PAD_SPLIT_LENGTHS:
+        x = golden_signal(n, seed=n % 97, sr=SR, lead=0, tail=0)
+        for types_ in ("repeat", "zero"):
+            random.seed(99)
+            out = U.split_pad_sample([x, 0, 0], sec, SR, types=types_)
+            g = META[f"split_pad/{sec}/{n}/{types_}"]
+            assert len(out) == g["n_chunks"]
+            assert sha_list([o[0] for o in out]) == g["sha"], (sec, n, types_)
+            assert sorted({str(o[0].dtype) for o in out}) == g["dtypes"]
+            assert rng_fingerprint() == g["rng_after"]
+        out = split_sample(x, sec, SR)
+        g = META[f"split_sample/{sec}/{n}"]
+        assert [len(o) for o in out] == g["lens"] and sha_list(out) == g["sha"]
+        assert bool(U.decide_droplast(x, SR, sec)) == META[f"droplast/{sec}/{n}"]
+
+
+# ------------------------------------------------------------------------------------------- fbank
+
+
+def _kaldi_ref(x):
+    import torchaudio
+
+    w = torch.tensor(x - x.mean()).reshape(1, -1)
+    return torchaudio.compliance.kaldi.fbank(
+        w, channel=0, frame_length=25, htk_compat=True, sample_frequency=SR, use_energy=False, window_type="hanning",
+        num_mel_bins=128, dither=0.0, frame_shift=10,
+    ).numpy()
+
+
+def test_fbank_matches_torchaudio_kaldi():
+    """<= 2.3e-3 nat (= 1e-2 dB); floor entries (empty mel row 3) exact; frame counts exact."""
+    from heart_murmur_detection_b200.frontend import FbankPlan
+
+    plan = FbankPlan()
+    lens = [401, 560, 32000, 128000, 160000, 163840, 400, 719, 720, 721]
+    clips = [golden_signal(n, seed=21 + i, lead=0, tail=0) for i, n in enumerate(lens)]
+    clips.append((golden_signal(50000, 40, lead=0, tail=0) + 0.3).astype(np.float32))  # DC offset
+    wav, off = _batch(clips)
+    out, ro = plan(wav, off)
+    out = out.cpu().numpy()
+    floor = np.float32(np.log(np.float32(1.1920929e-7)))
+    for i, x in enumerate(clips):
+        ref = _kaldi_ref(x)
+        got = out[ro[i] : ro[i + 1]]
+        assert got.shape == ref.shape == (1 + (len(x) - 400) // 160, 128)
+        assert np.abs(got - ref).max() <= 2.3e-3
+        np.testing.assert_array_equal(got[:, 3], ref[:, 3])
+        assert (got[:, 3] == floor).all()
+    # fewer than one frame -> no rows; padded layout [n, 1024, 128] with zero rows
+    w2, o2 = _batch([clips[5], golden_signal(399, 1), clips[2]])
+    padded, ro2 = plan(w2, o2, rows_per_clip=1024)
+    padded = padded.view(3, 1024, 128).cpu().numpy()
+    assert np.abs(padded[0, :1022] - _kaldi_ref(clips[5])).max() <= 2.3e-3
+    assert not padded[0, 1022:].any() and not padded[1].any() and not padded[2, 198:].any()
+    # silence: every bin at the floor
+    z, oz = _batch([np.zeros(4000, np.float32)])
+    fz, _ = plan(z, oz)
+    assert (fz.cpu().numpy() == floor).all()
+
+
+def test_fbank_mel_basis_matches_torchaudio():
+    import torchaudio
+
+    from heart_murmur_detection_b200.frontend import FbankPlan
+
+    ours = FbankPlan().mel_basis()
+    ref, _ = torchaudio.compliance.kaldi.get_mel_banks(128, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    ref = torch.nn.functional.pad(ref, (0, 1)).numpy()
+    assert np.abs(ours - ref).max() <= 2e-6
+    assert int((ours != 0).sum()) == int((ref != 0).sum()) == 504 and not ours[3].any()
+
+
+# ------------------------------------------------------------------------------------------- resample
+
+
+@pytest.mark.parametrize("sr_in", [4000, 2000, 8000, 44100, 22050, 48000])
+def test_resample_matches_torchaudio(sr_in):
+    """Same-algorithm oracle (torchaudio.transforms.Resample, src/model/models_eval.py:964-968):
+    <= 1e-6 * max|x|; output length ceil(n * 16000 / sr) exact.  soxr parity is unpinned."""
+    import torchaudio
+
+    from heart_murmur_detection_b200.frontend import ResamplePlan
+
+    plan = ResamplePlan(sr_in, 16000)
+    lens = [1, 17, 1000, 12345, 3 * sr_in + 7]
+    clips = [golden_signal(n, seed=5 + i, sr=sr_in, lead=0, tail=0) for i, n in enumerate(lens)]
+    wav, off = _batch(clips)
+    out, no = plan(wav, off)
+    out = out.cpu().numpy()
+    tr = torchaudio.transforms.Resample(sr_in, 16000)
+    for i, x in enumerate(clips):
+        ref = tr(torch.from_numpy(x)).numpy()
+        got = out[no[i] : no[i + 1]]
+        assert len(got) == len(ref) == int(np.ceil(len(x) * 16000 / sr_in))
+        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(x).max())
+        ref_f = torchaudio.functional.resample(torch.from_numpy(x), sr_in, 16000).numpy()  # float32-built taps
+        assert np.abs(got - ref_f).max() <= 5e-6
+
+
+# ------------------------------------------------------------------------------------------- spectrogram ops
+
+
+@pytest.mark.parametrize("T,Fq,crop", [(251, 64, 251), (400, 64, 251), (1022, 128, 512), (63, 64, 32), (3750, 64, 251)])
+def test_cola_batcher_matches_reference_draws(T, Fq, crop):
+    """Crop starts, gains and masked rows are bit-exact with the reference's RNG stream
+    (golden hashes from the reference's random_mask/random_crop/random_multiply); masked rows
+    hold the float32 mean within 1 ulp-level tolerance (numpy pairwise vs float64 accumulate)."""
+    from heart_murmur_detection_b200 import datasets as D
+    from oracle import frontend as F
+
+    g = META[f"specops/{T}x{Fq}/{crop}"]
+    spec = hash_spec(T, Fq, seed=T)
+    store = D.SpecStore([spec])
+    random.seed(1000 + T)
+    x1, x2 = D.cola_batch(store, [0], max_len=crop, augment=True)
+    assert rng_fingerprint() == g["rng_after"]
+    random.seed(1000 + T)
+    m = F.random_mask(spec)
+    c1 = F.random_crop(m, crop_size=crop)
+    c2 = F.random_crop(m, crop_size=crop)
+    r1, r2 = F.random_multiply(c1), F.random_multiply(c2)
+    assert [sha(r1), sha(r2)] == g["mul_sha"]  # the oracle replay reproduces the reference outputs
+    for got, ref in ((x1, r1), (x2, r2)):
+        got = got[0].cpu().numpy()
+        unmasked = ~np.all(ref == ref[:, :1], axis=1)
+        np.testing.assert_array_equal(got[unmasked], ref[unmasked])  # bit exact
+        assert np.abs(got - ref).max() <= 2e-7
+    first = D.pad_or_crop_batch(store, [0], max_len=crop)[0].cpu().numpy()
+    assert sha(first[: min(T, crop)]) == g["first_sha"]
+
+
+def test_pad_to_model_size():
+    from heart_murmur_detection_b200 import datasets as D
+    from oracle import frontend as F
+
+    specs = [hash_spec(998, 128, 1), hash_spec(1022, 128, 2), hash_spec(1300, 128, 3), hash_spec(5, 128, 4)]
+    store = D.SpecStore(specs)
+    out = D.pad_or_crop_batch(store, [0, 1, 2, 3], max_len=1024).cpu().numpy()
+    for i, s in enumerate(specs):
+        np.testing.assert_array_equal(out[i], F.pad_to_model(s, 1024, 128))
