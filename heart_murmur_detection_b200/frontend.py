@@ -610,9 +610,9 @@ def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, 
 
     ``work[:used]`` holds the signal; gather chunks are written behind it (the buffer is
     re-allocated with the signal copied if its spare capacity is too small).
-    Returns (work, starts, lengths, clip_ids).
+    Returns (work, starts, lengths, clip_ids, is_view).
     """
-    starts, lengths, clip_ids, recs = [], [], [], []
+    starts, lengths, clip_ids, recs, is_view = [], [], [], [], []
     tail = used
     for cid, (c0, chunks) in enumerate(zip(clip_starts, chunk_lists)):
         for ch in chunks or ():
@@ -626,6 +626,7 @@ def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, 
                 lengths.append(length)
                 tail += length
             clip_ids.append(cid)
+            is_view.append(ch[0] == "view")
     if recs:
         if tail > work.numel():
             bigger = torch.empty(tail, dtype=torch.float32, device=work.device)
@@ -633,4 +634,5 @@ def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, 
             work = bigger
         descs = np.array(recs, dtype=GATHER_DTYPE)
         gather(work, work, descs, ctx=ctx, stream=stream)
-    return work, np.asarray(starts, dtype=np.int64), np.asarray(lengths, dtype=np.int64), np.asarray(clip_ids, dtype=np.int64)
+    return (work, np.asarray(starts, dtype=np.int64), np.asarray(lengths, dtype=np.int64),
+            np.asarray(clip_ids, dtype=np.int64), np.asarray(is_view, dtype=bool))

@@ -36,6 +36,13 @@ class ChunkBatch:
     trim: np.ndarray        # [n_clips, 2] trim indices (start, end), clip relative
     used_duplicate_padding: bool = False
     launches: int = 0
+    is_view: np.ndarray | None = None   # [n_chunks] True for straight views (no padding applied)
+    filtered: bool = False              # band-pass applied (the reference's data is float64 then)
+
+    def ref_dtype(self, k: int):
+        """dtype the reference produces for chunk k: float64 for untouched views of band-passed
+        audio (lfilter output), float32 for padded copies (np.zeros(..., float32)) and unfiltered audio."""
+        return np.float64 if self.filtered and (self.is_view is None or bool(self.is_view[k])) else np.float32
 
     def chunks_of(self, clip: int) -> np.ndarray:
         return np.flatnonzero(self.clip_ids == clip)
@@ -96,10 +103,10 @@ def prepare_chunks(wav: torch.Tensor, offsets, chunker, *, sample_rate=16000, bu
         chunk_lists.append(chunks)
     dup = bool(getattr(chunker, "dup_called", False))
     clip_starts = o[:-1] + se[:, 0]
-    work, starts, lengths, clip_ids = fe.materialise_chunks(work, total, clip_starts, chunk_lists, ctx=ctx)
-    if any(c[0] == "gather" for cl in chunk_lists for c in cl):
+    work, starts, lengths, clip_ids, is_view = fe.materialise_chunks(work, total, clip_starts, chunk_lists, ctx=ctx)
+    if not is_view.all():
         launches += ctx.last_launches
-    return ChunkBatch(work, starts, lengths, clip_ids, n, valid, se, dup, launches)
+    return ChunkBatch(work, starts, lengths, clip_ids, n, valid, se, dup, launches, is_view, sos is not None)
 
 
 def _truncate(chunk, new_len):
@@ -161,7 +168,8 @@ def fbank_features(cb: ChunkBatch, sample_rate=16000, rows_per_chunk=0, min_samp
     plan = fe.fbank_plan(sample_rate=sample_rate)
     keep = cb.lengths > min_samples_exclusive
     kept = ChunkBatch(cb.work, cb.starts[keep], cb.lengths[keep], cb.clip_ids[keep], cb.n_clips, cb.valid, cb.trim,
-                      cb.used_duplicate_padding, cb.launches)
+                      cb.used_duplicate_padding, cb.launches, None if cb.is_view is None else cb.is_view[keep],
+                      cb.filtered)
     if len(kept.starts) == 0:
         return FeatureBatch(torch.empty((0, plan.n_mels), device=cb.work.device), np.zeros(1, np.int64), kept, cb.launches)
     out, ro = plan.views(cb.work, kept.starts, kept.lengths, rows_per_clip=rows_per_chunk)

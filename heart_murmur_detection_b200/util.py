@@ -131,7 +131,7 @@ def split_pad_sample(sample, desired_length, sample_rate, types="repeat"):
     clip = np.asarray(sample[0])
     chunks = fe.plan_split_pad(len(clip), desired_length, sample_rate, types)
     work, off = _one(clip)
-    work, starts, lengths, _ = fe.materialise_chunks(work, len(clip), [0], [chunks])
+    work, starts, lengths, _, _ = fe.materialise_chunks(work, len(clip), [0], [chunks])
     if types != "zero":
         fe.reseed_like_reference()
     return [(work[int(s) : int(s) + int(n)].cpu().numpy(), sample[1], sample[2]) for s, n in zip(starts, lengths)]
@@ -176,9 +176,9 @@ def get_entire_signal_librosa(
             print("Warning: audio too short, skipped")
             return None
         work, _ = _one(np.asarray(yt))
-        work, starts, lengths, _ = fe.materialise_chunks(work, n, [0], [chunks])
+        work, starts, lengths, _, is_view = fe.materialise_chunks(work, n, [0], [chunks])
         cb = pl.ChunkBatch(work, starts, lengths, np.zeros(1, np.int64), 1, np.ones(1, bool), np.array([[0, n]]),
-                           chunker.dup_called)
+                           chunker.dup_called, 0, is_view, np.asarray(yt).dtype == np.float64)
         res = pl.log_mel_features(cb, f_max=8000, sample_rate=sample_rate) if spectrogram else cb
     else:
         data, _ = _load(data_folder, filename, sample_rate)
@@ -194,14 +194,11 @@ def get_entire_signal_librosa(
     duration = (cb.trim[0, 1] - cb.trim[0, 0]) / sample_rate
     if max_sec and duration > max_sec:
         print(f"Trimmed audio to {max_sec} seconds")
-    out_dtype = np.float64 if butterworth_filter and not from_cycle else np.float32
+    # padded chunks are float32 in the reference (np.zeros(..., float32)); untouched views of
+    # band-passed audio keep lfilter's float64
     if spectrogram:
-        return res.chunk(0).cpu().numpy().astype(out_dtype, copy=False)
-    # audio out: padded chunks are float32 in the reference (np.zeros(..., float32)); untouched
-    # views keep the filter's float64
-    arr = _chunks_to_numpy(cb)[0]
-    padded = int(cb.lengths[0]) != int(cb.trim[0, 1] - cb.trim[0, 0]) and duration < input_sec
-    return arr if padded else arr.astype(out_dtype, copy=False)
+        return res.chunk(0).cpu().numpy().astype(cb.ref_dtype(0), copy=False)
+    return _chunks_to_numpy(cb)[0].astype(cb.ref_dtype(0), copy=False)
 
 
 def _split_common(data_folder, filename, input_sec, sample_rate, butterworth_filter, trim_tail, lowcut, highcut):
@@ -228,9 +225,8 @@ def get_split_signal_librosa(
     if cb.used_duplicate_padding:
         fe.reseed_like_reference()
     if not spectrogram:
-        return _chunks_to_numpy(cb)
-    out_dtype = np.float64 if butterworth_filter else np.float32
-    return [res.chunk(k).cpu().numpy().astype(out_dtype, copy=False) for k in range(len(cb.starts))]
+        return [a.astype(cb.ref_dtype(k), copy=False) for k, a in enumerate(_chunks_to_numpy(cb))]
+    return [res.chunk(k).cpu().numpy().astype(cb.ref_dtype(k), copy=False) for k in range(len(cb.starts))]
 
 
 def get_split_signal_fbank_pad(
@@ -272,6 +268,5 @@ def get_individual_segments_librosa(
         print("Warning: audio too short, skipped")
         return []
     if not spectrogram:
-        return _chunks_to_numpy(cb)
-    out_dtype = np.float64 if butterworth_filter else np.float32
-    return [res.chunk(k).cpu().numpy().astype(out_dtype, copy=False) for k in range(len(cb.starts))]
+        return [a.astype(cb.ref_dtype(k), copy=False) for k, a in enumerate(_chunks_to_numpy(cb))]
+    return [res.chunk(k).cpu().numpy().astype(cb.ref_dtype(k), copy=False) for k in range(len(cb.starts))]
