@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""bench.py - throughput of the B200 audio front-end hot path (contract: see DESIGN.md section 7).
+"""bench.py - throughput of the B200 audio front-end hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic PCG-like clips.
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through
-the public host-buffer API (pinned host -> device -> features -> host, copies timed),
-`roofline` is the dominant kernel's algorithmic bytes / its CUDA-event time, `cpu_baseline`
-is the oracle port on the host cores over a bounded sample of the same workload.
+One "step" = one pass of the hot path over one batch of synthetic PCG-like clips (per GPU).
+Workloads (BASELINE.json configs):
+  c2 (default)  OPERA-CT linear-probe front-end: order-5 band-pass 200-1800 Hz + silence trim +
+                zero/tile pad to >= 8 s + cut at 32 s + 64-mel log-spectrogram, 5 272 ragged clips
+                of 2-80 s (model_util.py:161-163 with the band-pass enabled).
+  c1            CirCor-shaped log-mel only: 1000 clips x 8 s -> [251, 64] (src/util.py:481-501).
+  c3            Audio-MAE front-end: kaldi fbank 128 mel, 1000 clips x 10.24 s -> [1024, 128].
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` goes through the host-buffer API (pinned host in, features out, copies timed);
+`roofline` is the dominant kernel's algorithmic bytes / its mean CUDA-event duration inside
+the timed region; `cpu_baseline` is the oracle port on all host cores over a bounded sample.
 """
 from __future__ import annotations
 
@@ -27,20 +33,25 @@ sys.path.insert(0, ROOT)
 SR = 16000
 
 WORKLOADS = {
-    # name -> (BASELINE.json config, description)
-    "c1": "CirCor-shaped synthetic PCG: 1000 clips x 8 s @16 kHz -> librosa-style 64-mel log-spectrogram [251,64] "
+    "c1": "CirCor-shaped synthetic PCG: 1000 clips x 8 s @16 kHz -> 64-mel log-spectrogram [251,64] "
           "(src/util.py:481-501)",
+    "c2": "OPERA-CT linear-probe front-end: order-5 Butterworth band-pass 200-1800 Hz + silence trim + zero/tile pad "
+          "to >=8 s + cut at 32 s + 64-mel log-spectrogram over 5272 ragged clips, log-uniform 2-80 s "
+          "(model_util.py:161-163, src/util.py:205-267 with butterworth_filter=5)",
+    "c3": "Audio-MAE front-end: kaldi fbank 128 mel, 25 ms / 10 ms, 1000 clips x 10.24 s padded to [1024,128] "
+          "(src/util.py:845-856, audioMAE/models_mae.py:1178-1181)",
 }
-
+DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000}
+CPU_SAMPLE = {"c1": 256, "c2": 96, "c3": 256}
+C2_KW = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
 
 # ----------------------------------------------------------------------------- CPU reference arm
-
 
 _BLAS_LIMIT = None
 
 
 def _cpu_worker_init():
-    """One BLAS thread per worker process: the pool already uses every core."""
+    """One BLAS / torch thread per worker process: the pool already uses every core."""
     global _BLAS_LIMIT
     try:
         from threadpoolctl import threadpool_limits
@@ -53,15 +64,22 @@ def _cpu_worker_init():
     torch.set_num_threads(1)
 
 
-def _cpu_logmel_one(x):
+def _cpu_one(args):
+    workload, x = args
     from oracle import frontend as F
 
-    return F.log_mel(x, f_max=8000).shape[0]
+    if workload == "c1":
+        return F.log_mel(x, f_max=8000).shape[0]
+    if workload == "c2":
+        out = F.entire_signal(x, spectrogram=True, **C2_KW)
+        return 0 if out is None else out.shape[0]
+    fb = F.kaldi_fbank_chunk(x)
+    return 0 if fb is None else int(F.pad_to_model(fb.numpy()).shape[0])
 
 
-def cpu_reference_c1(n_clips: int, repeats: int = 1):
-    """Oracle port (numpy restatement of the reference's librosa path), one clip per task over
-    all host cores - mirrors the reference's one-file-at-a-time loop (model_util.py:138)."""
+def cpu_reference(workload: str, n_clips: int, repeats: int = 1):
+    """Oracle port (numpy restatement of the librosa path + live scipy / torchaudio), one clip per
+    task over all host cores - mirrors the reference's one-file-at-a-time loop (model_util.py:138)."""
     import multiprocessing as mp
 
     import torch
@@ -69,19 +87,22 @@ def cpu_reference_c1(n_clips: int, repeats: int = 1):
     from heart_murmur_detection_b200 import synth
 
     cores = os.cpu_count() or 1
-    clips = [synth.make_clip(8 * SR, 1000 + i).numpy() for i in range(n_clips)]
+    cfg = {"c1": "c1", "c2": "c2", "c3": "c3"}[workload]
+    lens = synth.clip_lengths(cfg, n_clips, seed=4321)
+    clips = [(workload, synth.make_clip(int(n), 1000 + i).numpy()) for i, n in enumerate(lens)]
     ctx = mp.get_context("fork")
     torch.set_num_threads(1)
     best = None
     with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
-        pool.map(_cpu_logmel_one, clips[: 2 * cores])  # warm-up (imports, page-in)
+        pool.map(_cpu_one, clips[: min(len(clips), 2 * cores)])  # warm-up (imports, page-in)
         for _ in range(repeats):
             t0 = time.perf_counter()
-            frames = sum(pool.map(_cpu_logmel_one, clips, chunksize=1))
+            frames = sum(pool.map(_cpu_one, clips, chunksize=1))
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return {"clips_per_s": n_clips / best, "frames_per_s": frames / best, "cores": cores, "seconds": best,
-            "sample": f"{n_clips} clips x 8 s, one clip per task, multiprocessing.Pool({cores})"}
+            "sample": f"{n_clips} clips of workload {workload} ({float(lens.sum()) / SR:.0f} s of audio), one clip per "
+                      f"task, multiprocessing.Pool({cores}), 1 BLAS thread per worker"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -98,7 +119,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -107,31 +128,35 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, ln in self.lines:
+            if t_begin is not None and not (t_begin <= ts <= t_end):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 smax = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "window": "timed region + end-to-end loop (the timed region alone is shorter than nvidia-smi's period)"}
 
 
 # ----------------------------------------------------------------------------- main
@@ -141,20 +166,20 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy kernel)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = 256
-    r = cpu_reference_c1(n, repeats=max(1, args.steps))
+    n = CPU_SAMPLE[args.workload]
+    r = cpu_reference(args.workload, n, repeats=max(1, min(args.steps, 3)))
     line = {
-        "impl": "reference", "metric": "log-mel clips/s", "value": r["clips_per_s"], "unit": "clips/s",
+        "impl": "reference", "metric": "front-end clips/s", "value": r["clips_per_s"], "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT / f32 mel (numpy)",
-        "data": "synthetic", "config": {"workload": WORKLOADS["c1"], "sample_clips": n},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT + f64 IIR / f32 mel (numpy, scipy)",
+        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload], "sample_clips": n},
         "frames_per_s": r["frames_per_s"],
         "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
@@ -167,17 +192,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="auto", choices=["auto", "scalar", "packed"])
-    ap.add_argument("--clips", type=int, default=1000, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (0 = the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     args.warmup = max(args.warmup, 3)
+    wl = args.workload
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -186,33 +213,68 @@ def main():
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork safety)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_c1(256, repeats=2)
+        r = cpu_reference(wl, CPU_SAMPLE[wl], repeats=2)
         cpu = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "frames_per_s": r["frames_per_s"]}
 
     import torch
     import torch.distributed as dist
 
-    from heart_murmur_detection_b200 import frontend, synth
+    from heart_murmur_detection_b200 import frontend, pipeline, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_clips = args.clips
-    lens = synth.clip_lengths("c1", n_clips)
-    wav, off = synth.make_batch(lens, base_seed=10_000 * rank, device=dev)
-    plan = frontend.LogMelPlan(f_max=8000, variant=args.variant)
-    fo = plan.frame_offsets(off)
-    n_frames = int(fo[-1])
-    out = torch.empty((n_frames, 64), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * n_frames, 64), dtype=torch.float32, device=dev) if world > 1 else None
+    n_clips = args.clips or DEFAULT_CLIPS[wl]
+    lens = synth.clip_lengths(wl, n_clips, seed=1234 + rank)
+    wav, off = synth.make_batch(lens, base_seed=10_000_000 * rank, device=dev)
+    total_samples = int(off[-1])
+    ctx = frontend.default_ctx()
+    lm_plan = frontend.logmel_plan(16000, 64, 50, 8000, 1024, 512, args.variant)
+    fb_plan = frontend.fbank_plan(sample_rate=16000)
+    state = {}
 
-    def step():
-        plan(wav, off, out=out)
-        if world > 1:  # the path's single collective: all-gather of the feature tensors
-            dist.all_gather_into_tensor(gathered, out)
+    if wl == "c1":
+        fo = lm_plan.frame_offsets(off)
+        out = torch.empty((int(fo[-1]), 64), dtype=torch.float32, device=dev)
+
+        def step():
+            lm_plan(wav, off, out=out)
+            state.update(features=out, rows=int(fo[-1]), launches=lm_plan.last_launches)
+    elif wl == "c2":
+        def step():
+            # frontend.logmel_plan caches by parameters: route the variant through the plan cache
+            res = pipeline.entire_signal_batch(wav, off, spectrogram=True, **C2_KW)
+            state.update(features=res.features, rows=int(res.row_offsets[-1]), launches=res.launches, res=res)
+    else:
+        out = torch.empty((n_clips * 1024, 128), dtype=torch.float32, device=dev)
+
+        def step():
+            fb_plan(wav, off, rows_per_clip=1024, out=out)
+            state.update(features=out, rows=n_clips * 1024, launches=fb_plan.last_launches)
+
+    if wl == "c2" and args.variant != "auto":  # make the pipeline pick the requested log-mel variant
+        frontend._plans[("logmel", torch.cuda.current_device(), 16000, 64, 50.0, 8000.0, 1024, 512, "auto")] = lm_plan
+
+    step()
+    torch.cuda.synchronize()
+    rows = state["rows"]
+    n_cols = state["features"].shape[1]
+    max_rows = rows
+    if world > 1:
+        t = torch.tensor([rows], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_rows = int(t.item())
+        send = torch.zeros((max_rows, n_cols), dtype=torch.float32, device=dev)
+        gathered = torch.empty((world * max_rows, n_cols), dtype=torch.float32, device=dev)
+
+    def full_step():
+        step()
+        if world > 1:  # the path's single collective: all-gather of the (row-padded) feature blocks
+            send[:rows].copy_(state["features"][:rows])
+            dist.all_gather_into_tensor(gathered, send)
 
     def barrier():
         if world > 1:
@@ -220,70 +282,122 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step()
+        full_step()
     barrier()
-    plan.set_profile(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_begin = time.perf_counter()
+    ctx.set_profile(True)
+    lm_plan.set_profile(True)
+    fb_plan.set_profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        full_step()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    power_ms, fin_ms, n_calls = plan.profile_ms()
-    plan.set_profile(False)
+    kern = {k: v for k, v in ctx.profile_ms().items() if v[1]}
+    p_ms, f_ms, p_n = lm_plan.profile_ms()
+    if p_n:
+        kern["logmel_power"] = (p_ms, p_n)
+        kern["logmel_finalize"] = (f_ms, p_n)
+    k_ms, k_n = fb_plan.profile_ms()
+    if k_n:
+        kern["fbank"] = (k_ms, k_n)
+    ctx.set_profile(False)
+    lm_plan.set_profile(False)
+    fb_plan.set_profile(False)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = float(t.item()) / args.steps
     clips_per_s = world * n_clips / (ms_step * 1e-3)
+    n_frames_valid = rows if wl != "c3" else int(fb_plan.num_frames(np.diff(off)).sum())
 
     # ---- end to end through the host-buffer API (pinned host in, pinned host out, copies timed)
-    h_wav = torch.empty(wav.numel(), dtype=torch.float32, pin_memory=True)
-    h_wav.copy_(wav)
-    h_out = torch.empty((n_frames, 64), dtype=torch.float32, pin_memory=True)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        frontend.logmel_from_host(plan, h_wav, off, h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        frontend.logmel_from_host(plan, h_wav, off, h_out)
+    e2e = None
+    if not args.no_e2e:
+        h_wav = torch.empty(total_samples, dtype=torch.float32, pin_memory=True)
+        h_wav.copy_(wav)
+        h_out = torch.empty((rows, n_cols), dtype=torch.float32, pin_memory=True)
+        d_wav2 = torch.empty_like(wav) if wl == "c3" else None
+
+        def e2e_step():
+            if wl == "c1":
+                frontend.logmel_from_host(lm_plan, h_wav, off, h_out)
+            elif wl == "c2":
+                pipeline.entire_signal_from_host(h_wav, off, h_out, **C2_KW)
+            else:
+                d_wav2.copy_(h_wav, non_blocking=True)
+                fb_plan(d_wav2, off, rows_per_clip=1024, out=out)
+                h_out.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, send)
+
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": world * n_clips / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": total_samples * 4,
+               "d2h_bytes_per_step": rows * n_cols * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "api": {"c1": "frontend.logmel_from_host", "c2": "pipeline.entire_signal_from_host",
+                       "c3": "FbankPlan on a pinned-host batch"}[wl]}
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        bytes_per_clip = 128000 * 4 + 251 * 64 * 4  # algorithmic: f32 samples in + f32 [251,64] out
-        kern_s = power_ms * 1e-3 / max(1, n_calls)
-        achieved = n_clips * bytes_per_clip / kern_s / 1e9
+        # algorithmic bytes per launch of each kernel
+        out_bytes = rows * n_cols * 4
+        if wl == "c2":
+            chunk_samples = int(state["res"].chunks.lengths.sum())
+        else:
+            chunk_samples = total_samples
+        alg = {
+            "logmel_power": 4 * chunk_samples + out_bytes,
+            "logmel_finalize": 2 * out_bytes,
+            "fbank": 4 * total_samples + out_bytes,
+            "iir_zero_state": 4 * total_samples,
+            "iir_final": 8 * total_samples,
+            "trim_power": 4 * total_samples,
+        }
+        per_launch = {k: v[0] / v[1] for k, v in kern.items()}
+        dom = max(per_launch, key=lambda k: per_launch[k])
+        dom_s = per_launch[dom] * 1e-3
+        achieved = alg.get(dom, 0) / dom_s / 1e9
+        step_kernel_ms = sum(v[0] for v in kern.values()) / args.steps
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": dom, "kernel_ms": per_launch[dom],
+                "algorithmic_bytes_per_launch": alg.get(dom),
+                "kernels_ms_per_launch": {k: round(v, 4) for k, v in sorted(per_launch.items())},
+                "kernels_gbs": {k: round(alg[k] / (per_launch[k] * 1e-3) / 1e9, 1) for k in per_launch if k in alg},
+                "sum_kernel_ms_per_step": step_kernel_ms,
+                "note": "FFT kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5): fp32 pipe fraction "
+                        "is reported in profiles/"}
         line = {
-            "metric": "log-mel clips/s", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "metric": "front-end clips/s", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "clips_per_gpu_per_step": n_clips,
-                       "variant": args.variant, "l2_policy": "inputs larger than L2 (512 MB of samples per step)",
-                       "collective": "all_gather_into_tensor(features)" if world > 1 else "none"},
-            "frames_per_s": clips_per_s * 251,
-            "e2e": {"value": world * n_clips / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": int(wav.numel() * 4),
-                    "d2h_bytes_per_step": int(n_frames * 64 * 4), "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": plan.last_launches * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "logmel_power_kernel (framing+window+rFFT-1024+power+mel)",
-                         "kernel_ms": kern_s * 1e3, "finalize_ms": fin_ms / max(1, n_calls),
-                         "fp32_tflops_algorithmic": n_clips * 251 * 28.8e3 / kern_s / 1e12},
+            "vs_baseline": None, "dtype": "f32 (FFT, mel) + f64 (IIR)", "data": "synthetic",
+            "config": {"workload": WORKLOADS[wl], "workload_id": wl, "clips_per_gpu_per_step": n_clips,
+                       "audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
+                       "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
+                       "collective": "all_gather_into_tensor(row-padded features)" if world > 1 else "none"},
+            "frames_per_s": world * n_frames_valid / (ms_step * 1e-3),
+            "audio_seconds_per_s": world * total_samples / SR / (ms_step * 1e-3),
+            "e2e": e2e,
+            "gpu_launches": int(state["launches"]) * args.steps,
+            "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

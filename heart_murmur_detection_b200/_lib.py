@@ -62,6 +62,9 @@ hmfe_logmel_profile_ms = _sig(
 hmfe_ctx_create = _sig("hmfe_ctx_create", C.c_int, C.POINTER(c_voidp))
 hmfe_ctx_destroy = _sig("hmfe_ctx_destroy", None, c_voidp)
 hmfe_ctx_last_launches = _sig("hmfe_ctx_last_launches", C.c_int, c_voidp)
+hmfe_ctx_set_profile = _sig("hmfe_ctx_set_profile", C.c_int, c_voidp, C.c_int)
+hmfe_ctx_profile_ms = _sig("hmfe_ctx_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_int))
+KERNEL_NAMES = ["iir_zero_state", "iir_carry", "iir_final", "trim_power", "trim_index", "gather", "spec_mean", "spec_crop"]
 
 hmfe_trim_num_frames = _sig("hmfe_trim_num_frames", C.c_int64, C.c_int64, C.c_int, C.c_int)
 hmfe_trim_batch = _sig(
@@ -102,6 +105,8 @@ hmfe_fbank_batch_views = _sig(
     "hmfe_fbank_batch_views", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
 )
 hmfe_fbank_last_launches = _sig("hmfe_fbank_last_launches", C.c_int, c_voidp)
+hmfe_fbank_set_profile = _sig("hmfe_fbank_set_profile", C.c_int, c_voidp, C.c_int)
+hmfe_fbank_profile_ms = _sig("hmfe_fbank_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_int))
 
 hmfe_resample_plan_create = _sig(
     "hmfe_resample_plan_create", C.c_int, C.POINTER(c_voidp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double

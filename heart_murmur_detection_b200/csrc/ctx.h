@@ -4,7 +4,21 @@
 #include <limits.h>
 #include <string.h>
 
+#include <vector>
+
 #include "api_common.h"
+
+enum HmfeKernelId {
+    HMFE_K_IIR_ZERO_STATE = 0,
+    HMFE_K_IIR_CARRY = 1,
+    HMFE_K_IIR_FINAL = 2,
+    HMFE_K_TRIM_POWER = 3,
+    HMFE_K_TRIM_INDEX = 4,
+    HMFE_K_GATHER = 5,
+    HMFE_K_SPEC_MEAN = 6,
+    HMFE_K_SPEC_CROP = 7,
+    HMFE_K_COUNT = 8
+};
 
 struct hmfe_ctx {
     hmfe::DescRing ring;
@@ -12,6 +26,28 @@ struct hmfe_ctx {
     size_t scratch_cap = 0;
     int sm_count = 148;
     int last_launches = 0;
+    // measurement hook (bench.py roofline): events around every kernel, on the launch stream
+    bool profile = false;
+    struct ProfRec {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof;
+
+    int prof_begin(int id, cudaStream_t st) {
+        if (!profile) return HMFE_OK;
+        ProfRec r{id, nullptr, nullptr};
+        HMFE_CHECK_CUDA(cudaEventCreate(&r.a));
+        HMFE_CHECK_CUDA(cudaEventCreate(&r.b));
+        HMFE_CHECK_CUDA(cudaEventRecord(r.a, st));
+        prof.push_back(r);
+        return HMFE_OK;
+    }
+    int prof_end(cudaStream_t st) {
+        if (!profile || prof.empty()) return HMFE_OK;
+        HMFE_CHECK_CUDA(cudaEventRecord(prof.back().b, st));
+        return HMFE_OK;
+    }
 
     // grows the device scratch; growing frees the old block (cudaFree synchronises the device,
     // so kernels still using it have finished)

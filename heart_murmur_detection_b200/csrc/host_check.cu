@@ -28,7 +28,11 @@ static void run_logmel(const std::vector<float>& x, int hop, int n_mels, double 
     const int nsamp = (int)x.size();
     const int T = 1 + nsamp / hop;
     const std::vector<float> dense = mel_filterbank_slaney(16000, kNfft, n_mels, fmin, fmax);
-    const BandedMel bm = build_banded(dense, n_mels, kNfft / 2 + 1);
+    const BandedMel bm = build_banded(dense, n_mels, kNfft / 2 + 1, lanes_of<V>::value == 2 ? 8 : 16, kBinsPad);
+    if (!verify_banded(bm, dense, kBinsPad)) {
+        fprintf(stderr, "banded mel verification failed\n");
+        exit(3);
+    }
     const std::vector<float> win = half_hann_periodic(kNfft);
     const std::vector<float> twv = twiddle_plane(kNfft, 32);
     const float2* tw = reinterpret_cast<const float2*>(twv.data());
@@ -85,7 +89,11 @@ static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float
     const float preemph = 0.97f;
     const int m = nsamp >= win ? 1 + (nsamp - win) / shift : 0;
     const std::vector<float> dense = mel_banks_kaldi(n_mels, 512, 16000.0, 20.0, 0.0);
-    const BandedMel bm = build_banded(dense, n_mels, 257);
+    const BandedMel bm = build_banded(dense, n_mels, 257, 16, 320);
+    if (!verify_banded(bm, dense, 320)) {
+        fprintf(stderr, "banded mel verification failed\n");
+        exit(3);
+    }
     const std::vector<float> w = half_hann_symmetric(win);
     const std::vector<float> twv = twiddle_plane(512, 16);
     const float2* tw = reinterpret_cast<const float2*>(twv.data());
@@ -157,15 +165,21 @@ static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float
         for (int lane = 0; lane < 32; ++lane)
             for (int s = 0; s < bm.n_slots; ++s) {
                 const int start = bm.start[s * 32 + lane], row = bm.row[s * 32 + lane];
-                float a[4] = {0, 0, 0, 0};
-                for (int i = 0; i < bm.trip[s]; ++i) {
-                    const float wt = bm.w[((size_t)bm.wbase[s] + i) * 32 + lane];
+                float a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+                for (int i = 0; i < bm.trip[s]; i += 2) {
+                    const float w0 = bm.w[((size_t)bm.wbase[s] + i) * 32 + lane], w1 = bm.w[((size_t)bm.wbase[s] + i + 1) * 32 + lane];
                     const xelem<float> ea = tile[start + i], eb = tile[PS + start + i];
-                    a[0] = fmaf(ea.a, wt, a[0]);
-                    a[1] = fmaf(ea.b, wt, a[1]);
-                    a[2] = fmaf(eb.a, wt, a[2]);
-                    a[3] = fmaf(eb.b, wt, a[3]);
+                    const xelem<float> fa = tile[start + i + 1], fb = tile[PS + start + i + 1];
+                    a[0] = fmaf(ea.a, w0, a[0]);
+                    a[1] = fmaf(ea.b, w0, a[1]);
+                    a[2] = fmaf(eb.a, w0, a[2]);
+                    a[3] = fmaf(eb.b, w0, a[3]);
+                    c[0] = fmaf(fa.a, w1, c[0]);
+                    c[1] = fmaf(fa.b, w1, c[1]);
+                    c[2] = fmaf(fb.a, w1, c[2]);
+                    c[3] = fmaf(fb.b, w1, c[3]);
                 }
+                for (int t = 0; t < 4; ++t) a[t] += c[t];
                 if (row < 0) continue;
                 for (int t = 0; t < 4; ++t)
                     if (f0 + t < m) out[(size_t)(f0 + t) * n_mels + row] = logf(fmaxf(a[t], 1.1920929e-7f));

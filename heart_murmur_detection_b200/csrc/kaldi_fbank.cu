@@ -208,16 +208,26 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
             const float* wl = s_melw + mm.wbase[s] * 32 + lane;
             const xelem<float>* pa = tile + start;
             const xelem<float>* pb = tile + kFbPStride + start;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < trip; ++i) {
-                const float w = wl[i * 32];
-                const xelem<float> ea = pa[i], eb = pb[i];
-                a0 = fmaf(ea.a, w, a0);
-                a1 = fmaf(ea.b, w, a1);
-                a2 = fmaf(eb.a, w, a2);
-                a3 = fmaf(eb.b, w, a3);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            for (int i = 0; i < trip; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float w0 = wl[(i + j) * 32], w1 = wl[(i + j + 1) * 32];
+                    const xelem<float> ea = pa[i + j], eb = pb[i + j], fa = pa[i + j + 1], fb = pb[i + j + 1];
+                    a0 = fmaf(ea.a, w0, a0);
+                    a1 = fmaf(ea.b, w0, a1);
+                    a2 = fmaf(eb.a, w0, a2);
+                    a3 = fmaf(eb.b, w0, a3);
+                    c0 = fmaf(fa.a, w1, c0);
+                    c1 = fmaf(fa.b, w1, c1);
+                    c2 = fmaf(fb.a, w1, c2);
+                    c3 = fmaf(fb.b, w1, c3);
+                }
             }
+            a0 += c0;
+            a1 += c1;
+            a2 += c2;
+            a3 += c3;
             const int row = s_row[s * 32 + lane];
             if (row >= 0) {
                 const float acc[4] = {a0, a1, a2, a3};
@@ -244,6 +254,8 @@ struct hmfe_fbank_plan {
     size_t table_smem = 0;
     DescRing ring;
     int last_launches = 0, sm_count = 148;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs around fbank_kernel
 };
 
 template <typename T>
@@ -262,6 +274,7 @@ void hmfe_fbank_plan_destroy(hmfe_fbank_plan* p) {
     cudaFree(p->d_melw);
     cudaFree(p->d_start);
     cudaFree(p->d_row);
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     delete p;
 }
 
@@ -286,7 +299,12 @@ int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame
     p->n_mels = n_mels;
     p->sm_count = device_sm_count();
     p->mel_dense = mel_banks_kaldi(n_mels, kFbPad, sample_rate, low_freq, high_freq);
-    const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1);
+    const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1, 16, kFbPStride);
+    if (!verify_banded(bm, p->mel_dense, kFbPStride)) {
+        set_error("internal error: banded mel tables do not reproduce the mel basis");
+        delete p;
+        return HMFE_ERR_INVALID;
+    }
     p->meta.n_slots = bm.n_slots;
     p->meta.total_trip = bm.total_trip;
     p->meta.n_mels = n_mels;
@@ -324,6 +342,29 @@ int hmfe_fbank_mel_basis(const hmfe_fbank_plan* p, float* h_out) {
 }
 
 int hmfe_fbank_last_launches(const hmfe_fbank_plan* p) { return p ? p->last_launches : 0; }
+
+int hmfe_fbank_set_profile(hmfe_fbank_plan* p, int enable) {
+    HMFE_REQUIRE(p, "NULL plan");
+    p->profile = enable != 0;
+    return HMFE_OK;
+}
+
+int hmfe_fbank_profile_ms(hmfe_fbank_plan* p, double* kernel_ms, int* n_calls) {
+    HMFE_REQUIRE(p, "NULL plan");
+    double a = 0;
+    const int n = (int)(p->prof_events.size() / 2);
+    for (int i = 0; i < n; ++i) {
+        float t = 0;
+        HMFE_CHECK_CUDA(cudaEventSynchronize(p->prof_events[2 * i + 1]));
+        HMFE_CHECK_CUDA(cudaEventElapsedTime(&t, p->prof_events[2 * i], p->prof_events[2 * i + 1]));
+        a += t;
+    }
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    p->prof_events.clear();
+    if (kernel_ms) *kernel_ms = a;
+    if (n_calls) *n_calls = n;
+    return HMFE_OK;
+}
 
 // rows_per_clip == 0: clips' frames are packed back to back ([sum m_i, n_mels]);
 // rows_per_clip  > 0: clip i owns rows [i*rows_per_clip, (i+1)*rows_per_clip), frames beyond
@@ -399,8 +440,17 @@ int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t
         const int64_t want = (b.n_items + kFbWarps - 1) / kFbWarps;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));
         FbTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        if (p->profile) {
+            for (int i = 0; i < 2; ++i) {
+                HMFE_CHECK_CUDA(cudaEventCreate(&ev[i]));
+                p->prof_events.push_back(ev[i]);
+            }
+            HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
+        }
         fbank_kernel<<<grid, kFbWarps * 32, smem, st>>>(b, tb, mm);
         HMFE_CHECK_CUDA(cudaGetLastError());
+        if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
         p->last_launches = 1;
     }
     return p->ring.release(slot, st);

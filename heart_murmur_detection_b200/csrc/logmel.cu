@@ -48,7 +48,97 @@ HMFE_D f32x2 shfl(f32x2 v, int src) {
     return f32x2{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
 }
 
-template <typename V, int WARPS, int MINB>
+// Work item descriptor: 2*NV consecutive frames of one clip.
+struct ItemCtx {
+    const float* x;  // clip samples
+    float* o;        // clip output rows
+    int64_t clip;
+    int nsamp, T, f0;
+    bool valid;
+};
+
+template <int FR>
+HMFE_D ItemCtx locate_item(const LogmelBatch& b, int n_mels, int64_t item, int64_t it_end, int64_t& clip) {
+    ItemCtx c;
+    c.valid = item < it_end;
+    if (!c.valid) {
+        c.x = b.wav;
+        c.o = b.out;
+        c.clip = 0;
+        c.nsamp = c.T = c.f0 = 0;
+        return c;
+    }
+    int64_t q;
+    if (b.uniform_items > 0) {
+        clip = item / b.uniform_items;
+        q = item - clip * b.uniform_items;
+        c.nsamp = b.uniform_n;
+        c.T = b.uniform_T;
+        c.x = b.wav + clip * (int64_t)c.nsamp;
+        c.o = b.out + clip * (int64_t)c.T * n_mels;
+    } else {
+        if (clip < 0) {  // first item of this warp: binary search, largest c with prefix[c] <= item
+            int64_t lo = 0, hi = b.n_clips;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (b.item_prefix[mid] <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            clip = lo;
+        }
+        while (item >= b.item_prefix[clip + 1]) ++clip;
+        q = item - b.item_prefix[clip];
+        c.nsamp = (int)b.clip_len[clip];
+        const int64_t f0g = b.frame_off[clip];
+        c.T = (int)(b.frame_off[clip + 1] - f0g);
+        c.x = b.wav + b.clip_start[clip];
+        c.o = b.out + f0g * n_mels;
+    }
+    c.clip = clip;
+    c.f0 = (int)q * FR;
+    return c;
+}
+
+// raw[t][h][n2] = sample (lane + 32*n2) of frame f0 + 2t + h (zero outside the clip / beyond T)
+template <int NV>
+HMFE_D void load_raw(const ItemCtx& c, int hop, int lane, float (&raw)[NV][2][32]) {
+    int base[NV][2];
+    bool interior = c.valid;
+#pragma unroll
+    for (int t = 0; t < NV; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int f = c.f0 + 2 * t + h;
+            base[t][h] = f * hop - kNfft / 2;
+            interior = interior && f < c.T && base[t][h] >= 0 && base[t][h] + kNfft <= c.nsamp;
+            if (f >= c.T) base[t][h] = c.nsamp;  // every sample out of range -> zeros
+        }
+    if (interior) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float* p = c.x + base[t][h] + lane;
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) raw[t][h][n2] = __ldg(p + 32 * n2);
+            }
+    } else {
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) {
+                    const int i = base[t][h] + lane + 32 * n2;
+                    raw[t][h][n2] = (c.valid && i >= 0 && i < c.nsamp) ? __ldg(c.x + i) : 0.0f;
+                }
+    }
+}
+
+// NSLOTS > 0: number of mel slots known at compile time (2 for 64 mels, 4 for 128); 0: runtime.
+template <typename V, int WARPS, int MINB, int NSLOTS>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm) {
     constexpr int NV = lanes_of<V>::value;
@@ -59,7 +149,8 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     float* s_melw = s_win + 1024;
     int* s_start = reinterpret_cast<int*>(s_melw + mm.total_trip * 32);
     int* s_row = s_start + mm.n_slots * 32;
-    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + mm.total_trip * 128 + mm.n_slots * 256);
+    int* s_meta = s_row + mm.n_slots * 32;  // trip[kMaxSlots], wbase[kMaxSlots]
+    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + mm.total_trip * 128 + mm.n_slots * 256 + 2 * kMaxSlots * 4);
     tbytes = (tbytes + 15) & ~(size_t)15;
     xelem<V>* tile = reinterpret_cast<xelem<V>*>(smem + tbytes) + (threadIdx.x >> 5) * kTileElems;
 
@@ -72,73 +163,39 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
         s_start[i] = tb.start[i];
         s_row[i] = tb.row[i];
     }
+    if (threadIdx.x < kMaxSlots) {
+        s_meta[threadIdx.x] = mm.trip[threadIdx.x];
+        s_meta[kMaxSlots + threadIdx.x] = mm.wbase[threadIdx.x];
+    }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mels = mm.n_mels;
+    const int n_slots = NSLOTS > 0 ? NSLOTS : mm.n_slots;
     const int64_t per_cta = (b.n_items + gridDim.x - 1) / gridDim.x;
     const int64_t it_begin = (int64_t)blockIdx.x * per_cta;
     const int64_t it_end = min(b.n_items, it_begin + per_cta);
-    int64_t clip = -1;
+    int64_t clip_cursor = -1;
+
+    // software pipeline: the samples of item i+WARPS are fetched into registers while the mel
+    // projection of item i runs (the FFT registers are dead by then)
+    float raw[NV][2][32];
+    ItemCtx cur = locate_item<FR>(b, n_mels, it_begin + warp, it_end, clip_cursor);
+    load_raw<NV>(cur, b.hop, lane, raw);
 
     for (int64_t item = it_begin + warp; item < it_end; item += WARPS) {
-        int64_t q;
-        int nsamp, T;
-        const float* x;
-        float* o;
-        if (b.uniform_items > 0) {
-            clip = item / b.uniform_items;
-            q = item - clip * b.uniform_items;
-            nsamp = b.uniform_n;
-            T = b.uniform_T;
-            x = b.wav + clip * (int64_t)nsamp;
-            o = b.out + clip * (int64_t)T * mm.n_mels;
-        } else {
-            if (clip < 0) {  // first item of this warp: binary search, largest c with prefix[c] <= item
-                int64_t lo = 0, hi = b.n_clips;
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (b.item_prefix[mid] <= item)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                clip = lo;
-            }
-            while (item >= b.item_prefix[clip + 1]) ++clip;
-            q = item - b.item_prefix[clip];
-            const int64_t c0 = b.clip_start[clip];
-            nsamp = (int)b.clip_len[clip];
-            const int64_t f0g = b.frame_off[clip];
-            T = (int)(b.frame_off[clip + 1] - f0g);
-            x = b.wav + c0;
-            o = b.out + f0g * mm.n_mels;
-        }
-        const int f0 = (int)q * FR;
-
         V re[32], im[32];
-        {
-            // frame f covers clip samples [f*hop - 512, f*hop + 512); outside the clip -> 0
-            int base[NV][2];
-            bool interior = true;
 #pragma unroll
-            for (int t = 0; t < NV; ++t)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const float w = s_win[lane + 32 * n2];
+            V xa, xb;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int f = f0 + 2 * t + h;
-                    base[t][h] = f * b.hop - kNfft / 2;
-                    interior = interior && f < T && base[t][h] >= 0 && base[t][h] + kNfft <= nsamp;
-                    if (f >= T) base[t][h] = nsamp;  // every sample out of range -> zeros
-                }
-            if (interior) {
-                auto fetch = [&](int t, bool second, int n) -> float { return __ldg(x + base[t][second ? 1 : 0] + n); };
-                load_window<V>(lane, s_win, fetch, re, im);
-            } else {
-                auto fetch = [&](int t, bool second, int n) -> float {
-                    const int i = base[t][second ? 1 : 0] + n;
-                    return (i >= 0 && i < nsamp) ? __ldg(x + i) : 0.0f;
-                };
-                load_window<V>(lane, s_win, fetch, re, im);
+            for (int t = 0; t < NV; ++t) {
+                vput(xa, t, raw[t][0][n2]);
+                vput(xb, t, raw[t][1][n2]);
             }
+            re[brev(n2, 5)] = vmuls(xa, w);
+            im[brev(n2, 5)] = vmuls(xb, w);
         }
         fft_dit<32, V>(re, im);
         apply_twiddle<V>(lane, s_tw, re, im);
@@ -161,24 +218,29 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
         }
         __syncwarp();
 
+        const ItemCtx nxt = locate_item<FR>(b, n_mels, item + WARPS, it_end, clip_cursor);
+        load_raw<NV>(nxt, b.hop, lane, raw);
+
         float vmax = 0.0f, vmin = INFINITY;
-        for (int s = 0; s < mm.n_slots; ++s) {
+#pragma unroll
+        for (int s = 0; s < (NSLOTS > 0 ? NSLOTS : kMaxSlots); ++s) {
+            if (NSLOTS == 0 && s >= n_slots) break;
             V aa, ab;
-            mel_slot<V>(lane, tile, s_melw + mm.wbase[s] * 32, s_start[s * 32 + lane], mm.trip[s], aa, ab);
+            mel_slot<V>(lane, tile, s_melw + s_meta[kMaxSlots + s] * 32, s_start[s * 32 + lane], s_meta[s], aa, ab);
             const int row = s_row[s * 32 + lane];
             if (row >= 0) {
 #pragma unroll
                 for (int t = 0; t < NV; ++t) {
-                    const int fa = f0 + 2 * t;
-                    if (fa < T) {
+                    const int fa = cur.f0 + 2 * t;
+                    if (fa < cur.T) {
                         const float v = vget(aa, t);
-                        o[(int64_t)fa * mm.n_mels + row] = v;
+                        cur.o[(int64_t)fa * n_mels + row] = v;
                         vmax = fmaxf(vmax, v);
                         vmin = fminf(vmin, v);
                     }
-                    if (fa + 1 < T) {
+                    if (fa + 1 < cur.T) {
                         const float v = vget(ab, t);
-                        o[(int64_t)(fa + 1) * mm.n_mels + row] = v;
+                        cur.o[(int64_t)(fa + 1) * n_mels + row] = v;
                         vmax = fmaxf(vmax, v);
                         vmin = fminf(vmin, v);
                     }
@@ -191,10 +253,11 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
             vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
         }
         if (lane == 0) {
-            atomicMax(b.stats + 2 * clip, __float_as_uint(vmax));
-            atomicMin(b.stats + 2 * clip + 1, __float_as_uint(vmin));
+            atomicMax(b.stats + 2 * cur.clip, __float_as_uint(vmax));
+            atomicMin(b.stats + 2 * cur.clip + 1, __float_as_uint(vmin));
         }
         __syncwarp();
+        cur = nxt;
     }
 }
 
@@ -273,10 +336,10 @@ static int upload_vec(const std::vector<T>& v, T** dptr) {
     return HMFE_OK;
 }
 
-template <typename V, int WARPS, int MINB>
-static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+template <typename V, int WARPS, int MINB, int NSLOTS>
+static int launch_power_n(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
     const size_t smem = p->table_smem + (size_t)WARPS * kTileElems * sizeof(xelem<V>);
-    auto kern = logmel_power_kernel<V, WARPS, MINB>;
+    auto kern = logmel_power_kernel<V, WARPS, MINB, NSLOTS>;
     HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (b.n_items + WARPS - 1) / WARPS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * MINB));
@@ -284,6 +347,15 @@ static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t 
     kern<<<grid, WARPS * 32, smem, st>>>(b, tb, p->meta);
     HMFE_CHECK_CUDA(cudaGetLastError());
     return HMFE_OK;
+}
+
+template <typename V, int WARPS, int MINB>
+static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    switch (p->meta.n_slots) {
+        case 2: return launch_power_n<V, WARPS, MINB, 2>(p, b, st);
+        case 4: return launch_power_n<V, WARPS, MINB, 4>(p, b, st);
+        default: return launch_power_n<V, WARPS, MINB, 0>(p, b, st);
+    }
 }
 
 extern "C" {
@@ -314,13 +386,19 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
     p->variant = variant == HMFE_VARIANT_AUTO ? HMFE_VARIANT_PACKED : variant;
     p->sm_count = device_sm_count();
     p->mel_dense = mel_filterbank_slaney(sample_rate, n_fft, n_mels, f_min, f_max);
-    const BandedMel bm = build_banded(p->mel_dense, n_mels, p->n_bins);
+    const int group = p->variant == HMFE_VARIANT_PACKED ? 8 : 16;  // lanes per shared-memory phase (16 B / 8 B elements)
+    const BandedMel bm = build_banded(p->mel_dense, n_mels, p->n_bins, group, kBinsPad);
+    if (!verify_banded(bm, p->mel_dense, kBinsPad)) {
+        set_error("internal error: banded mel tables do not reproduce the mel basis");
+        delete p;
+        return HMFE_ERR_INVALID;
+    }
     p->meta.n_slots = bm.n_slots;
     p->meta.total_trip = bm.total_trip;
     p->meta.n_mels = n_mels;
-    for (int s = 0; s < bm.n_slots; ++s) {
-        p->meta.trip[s] = bm.trip[s];
-        p->meta.wbase[s] = bm.wbase[s];
+    for (int s = 0; s < kMaxSlots; ++s) {
+        p->meta.trip[s] = s < bm.n_slots ? bm.trip[s] : 0;
+        p->meta.wbase[s] = s < bm.n_slots ? bm.wbase[s] : 0;
     }
     const std::vector<float> win = half_hann_periodic(n_fft);
     const std::vector<float> tw = twiddle_plane(n_fft, 32);
@@ -333,7 +411,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
         hmfe_logmel_plan_destroy(p);
         return rc;
     }
-    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + bm.total_trip * 128 + bm.n_slots * 256);
+    size_t tbytes = (size_t)(1024 * 8 + 1024 * 4 + bm.total_trip * 128 + bm.n_slots * 256 + 2 * kMaxSlots * 4);
     p->table_smem = (tbytes + 15) & ~(size_t)15;
     *plan = p;
     return HMFE_OK;

@@ -93,21 +93,27 @@ HMFE_HD xelem<V> frame_powers(V zr, V zi, V pr, V pi) {
     return o;
 }
 
-// ---- mel: accumulate one slot for this lane from the power tile
+// ---- mel: accumulate one slot for this lane from the power tile.  `trip` is a multiple of 8;
+// two independent accumulators per output halve the dependent-FMA chain.
 template <typename V>
 HMFE_HD void mel_slot(int lane, const xelem<V>* __restrict__ ptile, const float* __restrict__ w, int start, int trip,
                       V& acc_a, V& acc_b) {
-    acc_a = V{};
-    acc_b = V{};
+    V a0 = V{}, a1 = V{}, b0 = V{}, b1 = V{};
     const xelem<V>* p = ptile + start;
     const float* wl = w + lane;
-#pragma unroll 8
-    for (int i = 0; i < trip; ++i) {
-        const float wi = wl[i * 32];
-        const xelem<V> e = p[i];
-        acc_a = vfmas(e.a, wi, acc_a);
-        acc_b = vfmas(e.b, wi, acc_b);
+    for (int i = 0; i < trip; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const float w0 = wl[(i + j) * 32], w1 = wl[(i + j + 1) * 32];
+            const xelem<V> e0 = p[i + j], e1 = p[i + j + 1];
+            a0 = vfmas(e0.a, w0, a0);
+            b0 = vfmas(e0.b, w0, b0);
+            a1 = vfmas(e1.a, w1, a1);
+            b1 = vfmas(e1.b, w1, b1);
+        }
     }
+    acc_a = vadd(a0, a1);
+    acc_b = vadd(b0, b1);
 }
 
 }  // namespace hmfe

@@ -173,10 +173,39 @@ int hmfe_ctx_create(hmfe_ctx** ctx) {
 void hmfe_ctx_destroy(hmfe_ctx* ctx) {
     if (!ctx) return;
     if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
     delete ctx;
 }
 
 int hmfe_ctx_last_launches(const hmfe_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int hmfe_ctx_set_profile(hmfe_ctx* ctx, int enable) {
+    HMFE_REQUIRE(ctx, "NULL ctx");
+    ctx->profile = enable != 0;
+    return HMFE_OK;
+}
+
+int hmfe_ctx_profile_ms(hmfe_ctx* ctx, double* ms_by_kernel, int* launches_by_kernel) {
+    HMFE_REQUIRE(ctx && ms_by_kernel && launches_by_kernel, "NULL argument");
+    for (int i = 0; i < HMFE_K_COUNT; ++i) {
+        ms_by_kernel[i] = 0.0;
+        launches_by_kernel[i] = 0;
+    }
+    for (auto& r : ctx->prof) {
+        float ms = 0.0f;
+        HMFE_CHECK_CUDA(cudaEventSynchronize(r.b));
+        HMFE_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_by_kernel[r.id] += ms;
+        launches_by_kernel[r.id] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    return HMFE_OK;
+}
 
 int64_t hmfe_trim_num_frames(int64_t n_samples, int frame_length, int hop_length) {
     if (n_samples < 0 || frame_length < 1 || hop_length < 1) return -1;
@@ -224,12 +253,16 @@ int hmfe_trim_batch(hmfe_ctx* ctx, const float* d_wav, const int64_t* h_offsets,
     if (b.n_frames_total > 0) {
         const int64_t warps_wanted = b.n_frames_total;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_wanted + 7) / 8, (int64_t)ctx->sm_count * 8));
+        ctx->prof_begin(HMFE_K_TRIM_POWER, st);
         trim_frame_power_kernel<<<grid, 256, 0, st>>>(b);
         HMFE_CHECK_CUDA(cudaGetLastError());
+        ctx->prof_end(st);
         ctx->last_launches++;
     }
+    ctx->prof_begin(HMFE_K_TRIM_INDEX, st);
     trim_index_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(b);
     HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
     ctx->last_launches++;
     return ctx->ring.release(slot, st);
 }
@@ -260,8 +293,10 @@ int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmf
     if (rc != HMFE_OK) return rc;
     const int tiles = (max_len + kGatherTile - 1) / kGatherTile;
     HMFE_REQUIRE(n_chunks * tiles < (int64_t)INT32_MAX, "gather grid too large");
+    ctx->prof_begin(HMFE_K_GATHER, st);
     gather_kernel<<<(unsigned)(n_chunks * tiles), 256, 0, st>>>(d_src, d_dst, static_cast<hmfe_gather_desc*>(dbuf), tiles);
     HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
     ctx->last_launches = 1;
     return ctx->ring.release(slot, st);
 }

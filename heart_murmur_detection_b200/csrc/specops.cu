@@ -77,8 +77,10 @@ int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_ro
     memcpy(hbuf, h_row_offsets, bytes);
     int rc = ctx->ring.upload(slot, bytes, st);
     if (rc != HMFE_OK) return rc;
+    ctx->prof_begin(HMFE_K_SPEC_MEAN, st);
     spec_mean_kernel<<<(unsigned)n_specs, 256, 0, st>>>(d_spec, static_cast<int64_t*>(dbuf), n_cols, d_mean);
     HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
     ctx->last_launches = 1;
     return ctx->ring.release(slot, st);
 }
@@ -104,9 +106,11 @@ int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const h
     if (rc != HMFE_OK) return rc;
     const int tiles = (out_rows + kCropRowsPerCta - 1) / kCropRowsPerCta;
     HMFE_REQUIRE(n_items * tiles < (int64_t)INT32_MAX, "crop grid too large");
+    ctx->prof_begin(HMFE_K_SPEC_CROP, st);
     spec_crop_kernel<<<(unsigned)(n_items * tiles), 256, 0, st>>>(d_spec, d_out, static_cast<hmfe_crop_desc*>(dbuf),
                                                                     d_row_mask, d_mean, n_cols, out_rows, tiles);
     HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
     ctx->last_launches = 1;
     return ctx->ring.release(slot, st);
 }

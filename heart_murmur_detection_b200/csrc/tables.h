@@ -113,7 +113,12 @@ struct BandedMel {
     int total_trip = 0;
 };
 
-inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n_bins) {
+// `group`: lanes whose shared-memory reads are served in one phase (8 for 16-byte tile elements,
+// 16 for 8-byte ones).  Lane l gets a window start congruent to l modulo `group`, which makes the
+// per-iteration tile reads bank-conflict free; rows are placed on the lane that needs the
+// smallest downward shift of their window.  Trip counts are rounded up to a multiple of 8 (no
+// remainder loop) and every window must end at or before `cap` tile rows.
+inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n_bins, int group = 8, int cap = 576) {
     BandedMel b;
     b.n_mels = n_mels;
     b.n_bins = n_bins;
@@ -131,35 +136,90 @@ inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n
     }
     std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return len[a] > len[c]; });
     b.n_slots = (n_mels + 31) / 32;
-    b.trip.assign(b.n_slots, 1);
+    b.trip.assign(b.n_slots, 8);
     b.wbase.assign(b.n_slots, 0);
     b.start.assign((size_t)b.n_slots * 32, 0);
     b.row.assign((size_t)b.n_slots * 32, -1);
+    std::vector<int> shift((size_t)b.n_slots * 32, 0);
     for (int s = 0; s < b.n_slots; ++s) {
-        int t = 1;
-        for (int l = 0; l < 32; ++l) {
-            const int idx = s * 32 + l;
-            if (idx < n_mels) t = std::max(t, len[order[idx]]);
+        bool used[32] = {false};
+        int need = 1;
+        for (int j = 0; j < 32; ++j) {
+            const int idx = s * 32 + j;
+            if (idx >= n_mels) break;
+            const int m = order[idx];
+            int best = -1, best_shift = 1 << 30;
+            for (int l = 0; l < 32; ++l) {
+                if (used[l]) continue;
+                const int sh = ((first[m] - l) % group + group) % group;  // start = first - sh == l (mod group)
+                if (first[m] - sh < 0) continue;
+                if (sh < best_shift) {
+                    best_shift = sh;
+                    best = l;
+                }
+            }
+            if (best < 0) {  // only possible for rows starting below `group`: take any free lane unshifted
+                for (int l = 0; l < 32 && best < 0; ++l)
+                    if (!used[l]) best = l;
+                best_shift = 0;
+            }
+            used[best] = true;
+            b.row[(size_t)s * 32 + best] = m;
+            b.start[(size_t)s * 32 + best] = first[m] - best_shift;
+            need = std::max(need, len[m] + best_shift);
         }
-        b.trip[s] = t;
+        b.trip[s] = (need + 7) / 8 * 8;
         b.wbase[s] = b.total_trip;
-        b.total_trip += t;
+        b.total_trip += b.trip[s];
     }
     b.w.assign((size_t)b.total_trip * 32, 0.0f);
     for (int s = 0; s < b.n_slots; ++s)
         for (int l = 0; l < 32; ++l) {
             const int idx = s * 32 + l;
-            if (idx >= n_mels) continue;
-            const int m = order[idx];
-            const int st = std::max(0, std::min(first[m], n_bins - b.trip[s]));
+            const int m = b.row[idx];
+            if (m < 0) {
+                b.start[idx] = l % group;  // idle lane: harmless conflict-free reads, zero weights
+                continue;
+            }
+            int st = b.start[idx];
+            while (st + b.trip[s] > cap && st >= group) st -= group;  // keep the window inside the tile
             b.start[idx] = st;
-            b.row[idx] = m;
             for (int i = 0; i < b.trip[s]; ++i) {
                 const int k = st + i;
                 if (k < n_bins) b.w[((size_t)b.wbase[s] + i) * 32 + l] = dense[(size_t)m * n_bins + k];
             }
         }
     return b;
+}
+
+// true iff expanding the banded tables reproduces the dense matrix exactly (plan creation
+// refuses to continue otherwise: a wrong table would silently change the features)
+inline bool verify_banded(const BandedMel& b, const std::vector<float>& dense, int cap) {
+    std::vector<float> re((size_t)b.n_mels * b.n_bins, 0.0f);
+    std::vector<char> seen(b.n_mels, 0);
+    for (int s = 0; s < b.n_slots; ++s) {
+        if (b.trip[s] % 8) return false;
+        for (int l = 0; l < 32; ++l) {
+            const int idx = s * 32 + l, m = b.row[idx], st = b.start[idx];
+            if (st < 0 || st + b.trip[s] > cap) return false;
+            for (int i = 0; i < b.trip[s]; ++i) {
+                const float w = b.w[((size_t)b.wbase[s] + i) * 32 + l];
+                if (m < 0) {
+                    if (w != 0.0f) return false;
+                    continue;
+                }
+                const int k = st + i;
+                if (k < b.n_bins)
+                    re[(size_t)m * b.n_bins + k] = w;
+                else if (w != 0.0f)
+                    return false;
+            }
+            if (m >= 0) seen[m] = 1;
+        }
+    }
+    for (int m = 0; m < b.n_mels; ++m)
+        if (!seen[m]) return false;
+    return re == dense;
 }
 
 // ------------------------------------------------------------------ inter-pass twiddles

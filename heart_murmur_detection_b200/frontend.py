@@ -188,6 +188,16 @@ class Context:
     def last_launches(self) -> int:
         return int(_lib.hmfe_ctx_last_launches(self._h))
 
+    def set_profile(self, enable: bool):
+        check(_lib.hmfe_ctx_set_profile(self._h, int(bool(enable))))
+
+    def profile_ms(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last query (synchronises)."""
+        n = len(_lib.KERNEL_NAMES)
+        ms, cnt = (C.c_double * n)(), (C.c_int * n)()
+        check(_lib.hmfe_ctx_profile_ms(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_NAMES)}
+
 
 _ctxs: dict = {}
 
@@ -361,6 +371,14 @@ class FbankPlan:
     @property
     def last_launches(self) -> int:
         return int(_lib.hmfe_fbank_last_launches(self._h))
+
+    def set_profile(self, enable: bool):
+        check(_lib.hmfe_fbank_set_profile(self._h, int(bool(enable))))
+
+    def profile_ms(self):
+        a, n = C.c_double(), C.c_int()
+        check(_lib.hmfe_fbank_profile_ms(self._h, C.byref(a), C.byref(n)))
+        return a.value, n.value
 
     def views(self, wav: torch.Tensor, starts, lengths, rows_per_clip=0, out: torch.Tensor | None = None, stream=None):
         """fbank of the clips wav[starts[i] : starts[i]+lengths[i]].  Returns (out, row_offsets)."""

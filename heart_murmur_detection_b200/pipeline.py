@@ -181,13 +181,88 @@ def fbank_features(cb: ChunkBatch, sample_rate=16000, rows_per_chunk=0, min_samp
 # ----------------------------------------------------------------------------------------------
 
 
+def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut, max_sec,
+                        ctx=None) -> ChunkBatch:
+    """Vectorised planning for get_entire_signal_librosa (one output chunk per recording): the
+    same integer formulas as frontend.plan_* evaluated with numpy over the whole batch."""
+    ctx = ctx or fe.default_ctx()
+    o = fe._as_offsets(offsets)
+    n_clips, total = o.size - 1, int(o[-1])
+    L = int(input_sec * sample_rate)
+    launches = 0
+    sos = _sos_for(butterworth_filter, lowcut, highcut, sample_rate)
+    lens = np.diff(o)
+    spare = L * (int((lens < L).sum()) + 16) if pad else 0
+    if sos is not None:
+        work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
+        fe.iir_sos(wav, o, sos, out=work, ctx=ctx)
+        launches += ctx.last_launches
+    else:
+        work = wav
+    se = fe.trim_indices(work, o, frame_length=int(sample_rate / 10), hop_length=int(int(sample_rate / 10) / 2), ctx=ctx)
+    launches += ctx.last_launches
+    se = se.cpu().numpy()
+    n = se[:, 1] - se[:, 0]
+    dur = n / sample_rate
+    short = dur < input_sec
+    valid = ~short | (bool(pad) & (n > 0))
+    starts = o[:-1] + se[:, 0]
+    lengths = n.copy()
+    if max_sec:
+        cut = dur > max_sec
+        lengths[cut] = np.minimum(lengths[cut], int(max_sec * sample_rate))
+    is_view = np.ones(n_clips, dtype=bool)
+    padded = np.flatnonzero(short & valid)
+    dup = False
+    if padded.size:
+        npad = n[padded]
+        d = np.zeros(padded.size, dtype=fe.GATHER_DTYPE)
+        d["src_off"] = starts[padded]
+        d["dst_off"] = total + L * np.arange(padded.size, dtype=np.int64)
+        d["len"] = L
+        d["period"] = npad
+        if types == "zero":  # _equally_slice_pad_sample -> one slice -> _zero_padding
+            tile = npad / L < 0.5
+            copies = (L - 1) // npad
+            d["a_end"] = np.where(tile, copies * npad, 0)
+            d["b_end"] = np.where(tile, copies * npad, npad)
+        else:  # _duplicate_padding: source at the end, tail of the doubled clip in front
+            left = L - npad
+            k = np.ceil(np.log2(np.maximum(1.0, left / npad))).astype(np.int64)
+            len_aug = npad << k
+            len_aug = np.where(len_aug < left, len_aug * 2, len_aug)  # guard log2 round-off
+            half = len_aug // 2
+            len_aug = np.where((len_aug > npad) & (half >= left), half, len_aug)
+            d["a_end"] = left
+            d["a_phase"] = (len_aug - left) % npad
+            d["b_end"] = L
+            dup = True
+        need = total + L * padded.size
+        if need > work.numel():
+            bigger = torch.empty(need, dtype=torch.float32, device=work.device)
+            bigger[:total].copy_(work[:total])
+            work = bigger
+        fe.gather(work, work, d, ctx=ctx)
+        launches += ctx.last_launches
+        starts[padded] = d["dst_off"]
+        lengths[padded] = L
+        is_view[padded] = False
+    keep = np.flatnonzero(valid)
+    return ChunkBatch(work, starts[keep], lengths[keep], keep.astype(np.int64), n_clips, valid, se, dup, launches,
+                      is_view[keep], sos is not None)
+
+
 def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
                         pad=False, types="repeat", lowcut=200, highcut=1800, max_sec=None, f_max=8000):
     """get_entire_signal_librosa over a batch.  Returns FeatureBatch (spectrogram=True) or ChunkBatch."""
-    L = int(input_sec * sample_rate)
-    cb = prepare_chunks(wav, offsets, entire_signal_chunker(input_sec, sample_rate, pad, types, max_sec),
-                        sample_rate=sample_rate, butterworth_filter=butterworth_filter, lowcut=lowcut, highcut=highcut,
-                        pad_hint=L if pad else 0)
+    if not max_sec or max_sec >= input_sec:
+        cb = _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut,
+                                 max_sec)
+    else:  # padded-then-cut corner: generic per-clip planner
+        L = int(input_sec * sample_rate)
+        cb = prepare_chunks(wav, offsets, entire_signal_chunker(input_sec, sample_rate, pad, types, max_sec),
+                            sample_rate=sample_rate, butterworth_filter=butterworth_filter, lowcut=lowcut,
+                            highcut=highcut, pad_hint=L if pad else 0)
     return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
 
 
@@ -252,3 +327,70 @@ def individual_segments_batch(wav, offsets, input_sec=8, sample_rate=16000, hop_
     cb = prepare_chunks(wav, offsets, chunker, sample_rate=sample_rate, butterworth_filter=butterworth_filter,
                         lowcut=200, highcut=1800, pad_hint=8 * sample_rate)
     return log_mel_features(cb, f_max=2000, sample_rate=sample_rate) if spectrogram else cb
+
+
+# ----------------------------------------------------------------------------------------------
+# host-buffer entry (what an extractor loop holding decoded audio in host memory calls)
+# ----------------------------------------------------------------------------------------------
+
+
+def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, *, chunk_bytes=256 << 20,
+                            device=None, **kw):
+    """get_entire_signal_librosa(spectrogram=True) over a batch held in (pinned) HOST memory.
+
+    Sub-batches of about ``chunk_bytes`` flow through three streams - copy-in, compute,
+    copy-out - so the PCIe transfers of neighbouring sub-batches overlap the kernels.
+    Returns (h_out [sum T, 64] host tensor, row_offsets [n_chunks+1], clip_ids, valid).
+    """
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    o = fe._as_offsets(offsets)
+    n = o.size - 1
+    bounds = [0]
+    while bounds[-1] < n:
+        c0 = bounds[-1]
+        c1 = int(np.searchsorted(o, o[c0] + chunk_bytes // 4, side="right")) - 1
+        bounds.append(min(n, max(c0 + 1, c1)))
+    subs = list(zip(bounds[:-1], bounds[1:]))
+    max_samples = max(int(o[b] - o[a]) for a, b in subs)
+    s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+    d_in = [torch.empty(max_samples, dtype=torch.float32, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    hop = 512
+    input_sec, sr = kw.get("input_sec", 8), kw.get("sample_rate", 16000)
+    L = int(input_sec * sr)
+    if h_out is None:
+        ub = int(sum(1 + max(int(x), L) // hop for x in np.diff(o)))
+        h_out = torch.empty((ub, 64), dtype=torch.float32, pin_memory=True)
+
+    def copy_in(i):
+        a, b = subs[i]
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[i % 2]) if i >= 2 else None
+            d_in[i % 2][: int(o[b] - o[a])].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+            ev_in[i % 2].record(s_in)
+
+    row_offsets, clip_ids, valid = [0], [], np.zeros(n, dtype=bool)
+    keep_alive = []
+    copy_in(0)
+    for i, (a, b) in enumerate(subs):
+        if i + 1 < len(subs):
+            copy_in(i + 1)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[i % 2])
+            res = entire_signal_batch(d_in[i % 2][: int(o[b] - o[a])], o[a : b + 1] - o[a], spectrogram=True, **kw)
+            ev_free[i % 2].record(s_cmp)
+            done = torch.cuda.Event()
+            done.record(s_cmp)
+        rows = int(res.row_offsets[-1])
+        base = row_offsets[-1]
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            h_out[base : base + rows].copy_(res.features[:rows], non_blocking=True)
+        keep_alive.append(res)  # features must outlive the async copy-out
+        row_offsets.extend((base + res.row_offsets[1:]).tolist())
+        clip_ids.extend((a + res.chunks.clip_ids).tolist())
+        valid[a:b] = res.chunks.valid
+    s_out.synchronize()
+    s_cmp.synchronize()
+    return h_out, np.asarray(row_offsets, dtype=np.int64), np.asarray(clip_ids, dtype=np.int64), valid

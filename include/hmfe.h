@@ -80,6 +80,14 @@ int hmfe_ctx_create(hmfe_ctx** ctx);
 void hmfe_ctx_destroy(hmfe_ctx* ctx);
 /* number of kernel launches issued by the last call made on this context */
 int hmfe_ctx_last_launches(const hmfe_ctx* ctx);
+/* Measurement hook: with profiling enabled every kernel a ctx stage launches is bracketed by
+ * CUDA events on its launch stream.  hmfe_ctx_profile_ms synchronises on them, writes the
+ * summed milliseconds and launch counts per kernel id (arrays of HMFE_KERNEL_COUNT) and resets.
+ * ids: 0 iir zero-state pass, 1 iir carry scan, 2 iir final pass, 3 trim frame power,
+ *      4 trim first/last index, 5 pad-split gather, 6 spectrogram mean, 7 spectrogram crop */
+#define HMFE_KERNEL_COUNT 8
+int hmfe_ctx_set_profile(hmfe_ctx* ctx, int enable);
+int hmfe_ctx_profile_ms(hmfe_ctx* ctx, double* ms_by_kernel, int* launches_by_kernel);
 
 /* ------------------------------------------------------------------------------------------
  * Silence trim: replaces librosa.effects.trim(y, top_db=60, frame_length=sr/10, hop_length=sr/20)
@@ -143,6 +151,9 @@ int hmfe_fbank_batch(hmfe_fbank_plan* plan, const float* d_wav, const int64_t* h
 int hmfe_fbank_batch_views(hmfe_fbank_plan* plan, const float* d_wav, const int64_t* h_starts, const int64_t* h_lengths,
                            int64_t n_clips, float* d_out, int rows_per_clip, void* stream);
 int hmfe_fbank_last_launches(const hmfe_fbank_plan* plan);
+/* measurement hook, as hmfe_logmel_set_profile / hmfe_logmel_profile_ms */
+int hmfe_fbank_set_profile(hmfe_fbank_plan* plan, int enable);
+int hmfe_fbank_profile_ms(hmfe_fbank_plan* plan, double* kernel_ms, int* n_calls);
 
 /* ------------------------------------------------------------------------------------------
  * Polyphase resampler (the rate conversion inside librosa.load(..., sr=16000), src/util.py:153,

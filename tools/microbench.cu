@@ -64,6 +64,21 @@ __global__ void k_shfl(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+template <int ILP>
+__global__ void k_dfma(double* out, int iters, double s) {
+    double acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x * 0.001 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], s, 0.5);
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) r += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 template <typename F>
 static float time_ms(F launch) {
     cudaEvent_t a, b;
@@ -95,6 +110,11 @@ int main() {
     printf(", \"ffma2_tflops\": %.2f, \"ffma2_warp_instr_per_ns\": %.2f", 4 * n_thread_ops / ms * 1e-9, n_thread_ops / 32 / ms * 1e-6);
     ms = time_ms([&] { k_shfl<ILP><<<blocks, threads>>>(out, iters / 4); });
     printf(", \"shfl_warp_instr_per_ns\": %.2f", n_thread_ops / 4 / 32 / ms * 1e-6);
+    double* dout;
+    cudaMalloc(&dout, sizeof(double) * blocks * threads);
+    ms = time_ms([&] { k_dfma<ILP><<<blocks, threads>>>(dout, iters / 8, 0.999); });
+    printf(", \"dfma_tflops\": %.2f, \"dfma_per_clk_per_sm_at_1965\": %.1f", 2 * n_thread_ops / 8 / ms * 1e-9,
+           n_thread_ops / 8 / (ms * 1e-3) / sms / 1.965e9);
     printf("}\n");
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
