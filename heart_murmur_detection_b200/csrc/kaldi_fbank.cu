@@ -79,6 +79,9 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
         s_start[i] = tb.start[i];
         s_row[i] = tb.row[i];
     }
+    // clear the tile's padding column once (read under zero mel weights, never written by the
+    // exchange): stale NaN bit patterns in shared memory must not poison 0 * x
+    tile[(threadIdx.x & 31) * kXStride + 32] = xelem<float>{};
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -167,6 +167,10 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
         s_meta[threadIdx.x] = mm.trip[threadIdx.x];
         s_meta[kMaxSlots + threadIdx.x] = mm.wbase[threadIdx.x];
     }
+    // The exchange never writes the padding column (index 33*a + 32) of the tile, but the mel
+    // windows may read it under a zero weight: clear it once so stale shared memory (NaN bit
+    // patterns left by other kernels) cannot turn 0 * x into NaN.
+    tile[(threadIdx.x & 31) * kXStride + 32] = xelem<V>{};
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,13 +201,19 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
             re[brev(n2, 5)] = vmuls(xa, w);
             im[brev(n2, 5)] = vmuls(xb, w);
         }
-        fft_dit<32, V>(re, im);
-        apply_twiddle<V>(lane, s_tw, re, im);
-        exchange_store<V>(lane, tile, re, im);
-        __syncwarp();
-        exchange_load<V>(lane, tile, re, im);
-        __syncwarp();
-        fft_dit<32, V>(re, im);
+        // both 32-point passes run the same unrolled butterfly code (one copy in the instruction
+        // cache); the first pass is followed by the twiddle and the lane exchange
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            fft_dit<32, V>(re, im);
+            if (pass == 0) {
+                apply_twiddle<V>(lane, s_tw, re, im);
+                exchange_store<V>(lane, tile, re, im);
+                __syncwarp();
+                exchange_load<V>(lane, tile, re, im);
+                __syncwarp();
+            }
+        }
 
         {
             const int src = (32 - lane) & 31;
@@ -212,7 +222,8 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
                 const V give_r = lane == 0 ? re[(32 - k1) & 31] : re[31 - k1];
                 const V give_i = lane == 0 ? im[(32 - k1) & 31] : im[31 - k1];
                 const V pr = shfl(give_r, src), pi = shfl(give_i, src);
-                tile[lane + 32 * k1] = frame_powers<V>(re[k1], im[k1], pr, pi);
+                const xelem<V> pw = frame_powers<V>(re[k1], im[k1], pr, pi);
+                store_halves(&tile[lane + 32 * k1], pw.a, pw.b);
             }
             if (lane == 0) tile[512] = frame_powers<V>(re[16], im[16], re[16], im[16]);
         }

@@ -32,6 +32,29 @@ struct __align__(16) xelem<f32x2> {
     f32x2 a, b;
 };
 
+// Store the two halves of a tile element with separate instructions.  The halves live in
+// unrelated registers; one wide store would need register moves to line them up first
+// (4 MOV per STS.128 in the packed kernel), two half-width stores need none and cost the same
+// number of shared-memory wavefronts.
+#if defined(__CUDA_ARCH__)
+HMFE_D void store_halves(xelem<float>* p, float a, float b) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+    asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(addr), "f"(b) : "memory");
+}
+HMFE_D void store_halves(xelem<f32x2>* p, f32x2 a, f32x2 b) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a.x), "f"(a.y) : "memory");
+    asm volatile("st.shared.v2.f32 [%0+8], {%1, %2};" ::"r"(addr), "f"(b.x), "f"(b.y) : "memory");
+}
+#else
+template <typename V>
+inline void store_halves(xelem<V>* p, V a, V b) {
+    p->a = a;
+    p->b = b;
+}
+#endif
+
 // ---- phase 1: windowed samples -> bit-reversed registers.  `fetch(t, n)` returns sample n
 // (0..1023) of transform t's frame a (im=false) / frame b (im=true), already bounds-handled.
 template <typename V, typename Fetch>
@@ -68,7 +91,7 @@ HMFE_HD void apply_twiddle(int lane, const float2* __restrict__ plane, V (&re)[3
 template <typename V>
 HMFE_HD void exchange_store(int lane, xelem<V>* tile, const V (&re)[32], const V (&im)[32]) {
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) tile[k2 * kXStride + lane] = xelem<V>{re[k2], im[k2]};
+    for (int k2 = 0; k2 < 32; ++k2) store_halves(&tile[k2 * kXStride + lane], re[k2], im[k2]);
 }
 // loads into bit-reversed positions, ready for the second DIT pass
 template <typename V>
