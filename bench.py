@@ -370,6 +370,7 @@ def main():
             "fbank": 4 * total_samples + out_bytes,
             "iir_zero_state": 4 * total_samples,
             "iir_final": 8 * total_samples,
+            "iir_overlap": 8 * total_samples,
             "trim_power": 4 * total_samples,
         }
         per_launch = {k: v[0] / v[1] for k, v in kern.items()}

@@ -64,7 +64,8 @@ hmfe_ctx_destroy = _sig("hmfe_ctx_destroy", None, c_voidp)
 hmfe_ctx_last_launches = _sig("hmfe_ctx_last_launches", C.c_int, c_voidp)
 hmfe_ctx_set_profile = _sig("hmfe_ctx_set_profile", C.c_int, c_voidp, C.c_int)
 hmfe_ctx_profile_ms = _sig("hmfe_ctx_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_int))
-KERNEL_NAMES = ["iir_zero_state", "iir_carry", "iir_final", "trim_power", "trim_index", "gather", "spec_mean", "spec_crop"]
+KERNEL_NAMES = ["iir_zero_state", "iir_carry", "iir_final", "trim_power", "trim_index", "gather", "spec_mean", "spec_crop",
+                "iir_overlap"]
 
 hmfe_trim_num_frames = _sig("hmfe_trim_num_frames", C.c_int64, C.c_int64, C.c_int, C.c_int)
 hmfe_trim_batch = _sig(
@@ -91,6 +92,16 @@ class CropDesc(C.Structure):
 hmfe_gather_batch = _sig("hmfe_gather_batch", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp)
 hmfe_iir_sos_batch = _sig(
     "hmfe_iir_sos_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, c_voidp
+)
+
+hmfe_iir_sos_trim_batch = _sig(
+    "hmfe_iir_sos_trim_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, C.c_int,
+    C.c_int, C.c_float, c_voidp, c_voidp,
+)
+IIR_ALGOS = {"auto": 0, "scan": 1, "overlap": 2}
+hmfe_ctx_set_iir_algo = _sig("hmfe_ctx_set_iir_algo", C.c_int, c_voidp, C.c_int)
+hmfe_ctx_last_iir_plan = _sig(
+    "hmfe_ctx_last_iir_plan", C.c_int, c_voidp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)
 )
 
 hmfe_fbank_plan_create = _sig(

@@ -17,7 +17,8 @@ enum HmfeKernelId {
     HMFE_K_GATHER = 5,
     HMFE_K_SPEC_MEAN = 6,
     HMFE_K_SPEC_CROP = 7,
-    HMFE_K_COUNT = 8
+    HMFE_K_IIR_OVERLAP = 8,
+    HMFE_K_COUNT = 9
 };
 
 struct hmfe_ctx {
@@ -26,6 +27,12 @@ struct hmfe_ctx {
     size_t scratch_cap = 0;
     int sm_count = 148;
     int last_launches = 0;
+    // IIR algorithm choice (hmfe_ctx_set_iir_algo) and what the last call used
+    int iir_algo = HMFE_IIR_ALGO_AUTO;
+    int iir_last_algo = 0, iir_last_C = 0, iir_last_W = 0;
+    // decay length of the last filter seen (depends on the coefficients only)
+    int iir_cache_S = 0, iir_cache_W = 0;
+    double iir_cache_sos[6 * 8] = {};
     // measurement hook (bench.py roofline): events around every kernel, on the launch stream
     bool profile = false;
     struct ProfRec {

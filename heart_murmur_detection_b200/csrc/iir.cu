@@ -12,6 +12,15 @@
 // One lane owns one chunk (sequential recurrence); a warp owns 32 consecutive chunks and
 // moves samples through a padded shared-memory tile so that global loads/stores stay
 // coalesced 128-byte rows.
+//
+// Overlap ("warm-up") variant, used when the filter forgets fast enough: the zero-input
+// response of a stable cascade decays geometrically, so a chunk that starts W samples early
+// from a ZERO state reaches its true state to within ||A^W|| (W is chosen on the host so that
+// ||A^W||_inf <= 1e-13, below the rounding noise of the float64 recurrence itself).  That makes
+// ONE pass of (1 + W/C) x the work instead of two passes plus the carry scan, and it lets the
+// pass also produce the per-hop energy sums the silence trim needs (hmfe_iir_sos_trim_batch),
+// so the filtered signal is not read a second time.  Filters with slowly decaying poles fall
+// back to the exact three-kernel scan above.
 #include <math.h>
 
 #include <algorithm>
@@ -184,6 +193,221 @@ __global__ void __launch_bounds__(128) iir_carry_kernel(const IirBatch b) {
     }
 }
 
+
+// ------------------------------------------------------------------------------ overlap variant
+struct IirOverlapBatch {
+    const float* x;
+    float* y32;
+    double* y64;
+    const int64_t* clip_off;      // [n_clips+1]
+    const int64_t* chunk_prefix;  // [n_clips+1]
+    const int64_t* hop_off;       // [n_clips+1] first hop-energy slot of each clip (POWER only)
+    float* hop_energy;            // [sum ceil(n/hop)] sum of y^2 (float32 squares) per hop block
+    int64_t n_clips, n_chunks;
+    int C, W;                     // multiples of 32; POWER: C is a multiple of hop
+    int hop_steps;                // hop / 32 (POWER only)
+};
+
+struct __align__(16) IirRow {
+    long long off;  // element offset of stream position t = 0 (may be negative: never dereferenced there)
+    int lo, span;   // stream positions [lo, lo + span) hold clip samples
+};
+
+// T = tile element: float (y32 only) or double (y64 requested)
+template <int S, bool BP, typename T, bool POWER>
+__global__ void __launch_bounds__(kIirWarps * 32, 4) iir_overlap_kernel(const IirOverlapBatch b, const IirCoef<S> cf) {
+    __shared__ T s_tile[kIirWarps][32][33];
+    __shared__ IirRow s_rowd[kIirWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * kIirWarps + warp) * 32 + lane;
+    double s1[S], s2[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) s1[k] = s2[k] = 0.0;
+    IirRow me{0, 0, 0};
+    int valid = 0;
+    int64_t hop_base = 0;
+    if (g < b.n_chunks) {
+        int64_t lo = 0, hi = b.n_clips;  // largest clip with chunk_prefix[clip] <= g
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (b.chunk_prefix[mid] <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int64_t j = g - b.chunk_prefix[lo];
+        const int64_t c0 = b.clip_off[lo], n = b.clip_off[lo + 1] - c0;
+        const int64_t out0 = j * b.C;  // clip-relative first output sample of this chunk
+        valid = (int)min((int64_t)b.C, n - out0);
+        me.off = c0 + out0 - b.W;
+        me.lo = (int)max((int64_t)0, (int64_t)b.W - out0);  // nothing before the clip start: exact zero state
+        me.span = b.W + valid - me.lo;
+        if (POWER) hop_base = b.hop_off[lo] + j * (b.C / (b.hop_steps * 32));
+    }
+    s_rowd[warp][lane] = me;
+    __syncwarp();
+    const int hi_self = b.W + valid;
+    T(*tile)[33] = s_tile[warp];
+    const IirRow* rows = s_rowd[warp];
+    const int t_end = b.W + b.C;
+    // the whole warp skips the steps in which no lane has clip samples yet (first chunks of a clip)
+    int t_first = me.span > 0 ? (me.lo & ~31) : t_end;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, d));
+
+    float nxt[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const IirRow rd = rows[r];
+        const int i = t_first + lane;
+        nxt[r] = (unsigned)(i - rd.lo) < (unsigned)rd.span ? __ldg(b.x + rd.off + i) : 0.0f;
+    }
+    float hop_acc = 0.0f;
+    int hop_step = 0, hop_idx = 0;
+    for (int t0 = t_first; t0 < t_end; t0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[r][lane] = (T)nxt[r];
+        __syncwarp();
+        if (t0 + 32 < t_end) {
+            const int i = t0 + 32 + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const IirRow rd = rows[r];
+                nxt[r] = (unsigned)(i - rd.lo) < (unsigned)rd.span ? __ldg(b.x + rd.off + i) : 0.0f;
+            }
+        }
+        const bool emit = t0 >= b.W;  // warp uniform (W is a multiple of 32)
+        if (t0 < hi_self) {
+            if (!emit) {
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) cascade<S, BP>(cf, (double)tile[lane][k], s1, s2);
+            } else if (t0 + 32 <= hi_self) {
+                float e = 0.0f;
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) {
+                    const double y = cascade<S, BP>(cf, (double)tile[lane][k], s1, s2);
+                    tile[lane][k] = (T)y;
+                    if (POWER) {
+                        const float f = (float)y;
+                        e = fmaf(f, f, e);
+                    }
+                }
+                hop_acc += e;
+            } else {  // the step that holds the end of the clip
+                float e = 0.0f;
+                const int kmax = hi_self - t0;
+#pragma unroll 1
+                for (int k = 0; k < kmax; ++k) {
+                    const double y = cascade<S, BP>(cf, (double)tile[lane][k], s1, s2);
+                    tile[lane][k] = (T)y;
+                    if (POWER) {
+                        const float f = (float)y;
+                        e = fmaf(f, f, e);
+                    }
+                }
+                hop_acc += e;
+            }
+        }
+        __syncwarp();
+        if (emit) {
+            const int i = t0 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const IirRow rd = rows[r];
+                if (i < rd.lo + rd.span) {
+                    const T y = tile[r][lane];
+                    if (sizeof(T) == 4) {
+                        b.y32[rd.off + i] = (float)y;
+                    } else {
+                        if (b.y32) b.y32[rd.off + i] = (float)y;
+                        b.y64[rd.off + i] = (double)y;
+                    }
+                }
+            }
+            __syncwarp();
+            if (POWER && ++hop_step == b.hop_steps) {  // a hop block is complete (warp uniform)
+                if (hop_idx * b.hop_steps * 32 < valid) b.hop_energy[hop_base + hop_idx] = hop_acc;
+                hop_acc = 0.0f;
+                hop_step = 0;
+                ++hop_idx;
+            }
+        }
+    }
+}
+
+// Silence-trim indices from per-hop energy sums (frame_length == 2 * hop, centred frames):
+// frame t covers hop blocks t-1 and t.  Same float32 arithmetic as trim_frame_power_kernel +
+// trim_index_kernel (ragged_ops.cu); one CTA per clip.
+struct TrimHopBatch {
+    const float* hop_energy;
+    const int64_t* clip_off;
+    const int64_t* hop_off;
+    int64_t* start_end;
+    int64_t n_clips;
+    int hop;
+    float top_db;
+};
+
+__global__ void __launch_bounds__(256) trim_index_hop_kernel(const TrimHopBatch b) {
+    __shared__ float s_f[8];
+    __shared__ int s_i[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float frame_length = (float)(2 * b.hop);
+    for (int64_t clip = blockIdx.x; clip < b.n_clips; clip += gridDim.x) {
+        const int n = (int)(b.clip_off[clip + 1] - b.clip_off[clip]);
+        const int T = 1 + n / b.hop;
+        const int H = (int)(b.hop_off[clip + 1] - b.hop_off[clip]);
+        const float* e = b.hop_energy + b.hop_off[clip];
+        auto power = [&](int t) {
+            const float acc = (t >= 1 ? e[t - 1] : 0.0f) + (t < H ? e[t] : 0.0f);
+            const float rms = sqrtf(acc / frame_length);
+            return rms * rms;
+        };
+        float m = 0.0f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) m = fmaxf(m, power(t));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) s_f[warp] = m;
+        __syncthreads();
+        m = s_f[0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_f[w]);
+        const float amin2 = 1e-10f;
+        const float ref_db = (float)(10.0 * log10(fmax(1e-10, (double)m)));
+        int first = INT_MAX, last = -1;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const float db = 10.0f * log10f(fmaxf(amin2, power(t))) - ref_db;
+            if (db > -b.top_db) {
+                first = min(first, t);
+                last = max(last, t);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+        }
+        if (lane == 0) {
+            s_i[warp] = first;
+            s_i[8 + warp] = last;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                first = min(first, s_i[w]);
+                last = max(last, s_i[8 + w]);
+            }
+            int64_t st = 0, en = 0;
+            if (last >= 0) {
+                st = (int64_t)first * b.hop;
+                en = min((int64_t)n, (int64_t)(last + 1) * b.hop);
+            }
+            b.start_end[2 * clip] = st;
+            b.start_end[2 * clip + 1] = en;
+        }
+        __syncthreads();
+    }
+}
+
 // zero-input transition of the cascade over C samples: column k = state after C steps from e_k
 static void transition_matrix(const double* sos, int S, int C, std::vector<double>& M) {
     const int D = 2 * S;
@@ -241,16 +465,88 @@ static int run_iir(hmfe_ctx* ctx, IirBatch b, const double* sos, bool bp, double
         iir_chunk_kernel<S, true, false><<<grid, kIirWarps * 32, 0, st>>>(b, cf);
     HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->prof_end(st);
-    ctx->last_launches = 3;
+    ctx->last_launches += 3;
     return HMFE_OK;
 }
 
-}  // namespace hmfe
 
-using namespace hmfe;
+// smallest multiple of 32 after which the zero-input response of the cascade has decayed below
+// tol (infinity norm of the state transition), or -1 if that takes more than max_w samples
+static int decay_length(const double* sos, int S, double tol, int max_w) {
+    const int D = 2 * S;
+    std::vector<double> st((size_t)D * D, 0.0);  // column c = state reached from unit vector e_c
+    for (int c = 0; c < D; ++c) st[(size_t)c * D + c] = 1.0;
+    for (int t = 1; t <= max_w; ++t) {
+        for (int c = 0; c < D; ++c) {
+            double* s = st.data() + (size_t)c * D;  // (s1[0], s2[0], s1[1], ...)
+            double v = 0.0;
+            for (int k = 0; k < S; ++k) {
+                const double* q = sos + 6 * k;
+                const double y = fma(q[0], v, s[2 * k]);
+                s[2 * k] = fma(q[1], v, fma(-q[4], y, s[2 * k + 1]));
+                s[2 * k + 1] = fma(q[2], v, -q[5] * y);
+                v = y;
+            }
+        }
+        if (t % 32 == 0) {
+            double norm = 0.0;
+            for (int r = 0; r < D; ++r) {
+                double row = 0.0;
+                for (int c = 0; c < D; ++c) row += fabs(st[(size_t)c * D + r]);
+                norm = std::max(norm, row);
+            }
+            if (!(norm < 1e300)) return -1;  // unstable
+            if (norm <= tol) return t;
+        }
+    }
+    return -1;
+}
 
-extern "C" int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
-                                  const double* h_sos, int n_sections, float* d_y32, double* d_y64, void* stream) {
+template <int S, typename T, bool POWER>
+static int launch_overlap(const IirOverlapBatch& b, const IirCoef<S>& cf, bool bp, cudaStream_t st) {
+    const unsigned grid = (unsigned)((b.n_chunks + kIirWarps * 32 - 1) / (kIirWarps * 32));
+    if (bp)
+        iir_overlap_kernel<S, true, T, POWER><<<grid, kIirWarps * 32, 0, st>>>(b, cf);
+    else
+        iir_overlap_kernel<S, false, T, POWER><<<grid, kIirWarps * 32, 0, st>>>(b, cf);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
+template <int S>
+static int run_iir_overlap(hmfe_ctx* ctx, const IirOverlapBatch& b, const double* sos, bool bp, double gain, bool power,
+                           cudaStream_t st) {
+    IirCoef<S> cf;
+    for (int k = 0; k < S; ++k) {
+        cf.b0[k] = sos[6 * k + 0];
+        cf.b1[k] = sos[6 * k + 1];
+        cf.b2[k] = sos[6 * k + 2];
+        cf.a1[k] = sos[6 * k + 4];
+        cf.a2[k] = sos[6 * k + 5];
+    }
+    cf.bandpass_form = bp ? 1 : 0;
+    cf.gain = gain;
+    ctx->prof_begin(HMFE_K_IIR_OVERLAP, st);
+    int rc;
+    if (b.y64)
+        rc = power ? launch_overlap<S, double, true>(b, cf, bp, st) : launch_overlap<S, double, false>(b, cf, bp, st);
+    else
+        rc = power ? launch_overlap<S, float, true>(b, cf, bp, st) : launch_overlap<S, float, false>(b, cf, bp, st);
+    if (rc != HMFE_OK) return rc;
+    ctx->prof_end(st);
+    ctx->last_launches += 1;
+    return HMFE_OK;
+}
+
+struct TrimArgs {
+    int frame_length, hop_length;
+    float top_db;
+    int64_t* d_start_end;
+};
+
+// Shared implementation of hmfe_iir_sos_batch (trim == nullptr) and hmfe_iir_sos_trim_batch.
+static int iir_impl(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips, const double* h_sos,
+                    int n_sections, float* d_y32, double* d_y64, const TrimArgs* trim, void* stream) {
     HMFE_REQUIRE(ctx && h_offsets && h_sos, "NULL argument");
     HMFE_REQUIRE(n_sections >= 1 && n_sections <= kIirMaxSections, "n_sections=%d not in [1, %d]", n_sections,
                  kIirMaxSections);
@@ -258,6 +554,10 @@ extern "C" int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t
     ctx->last_launches = 0;
     if (n_clips == 0) return HMFE_OK;
     HMFE_REQUIRE(d_x && (d_y32 || d_y64), "NULL device pointer");
+    if (trim) {
+        HMFE_REQUIRE(d_y32 && trim->d_start_end, "the fused trim needs the float32 output and d_start_end");
+        HMFE_REQUIRE(trim->frame_length >= 2 && trim->hop_length >= 1, "bad trim arguments");
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int S = n_sections, D = 2 * S;
     std::vector<double> sos((size_t)6 * S);
@@ -282,54 +582,190 @@ extern "C" int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t
         }
     else
         gain = 1.0;
-    const int64_t total = h_offsets[n_clips] - h_offsets[0];
-    const int C = total >= ((int64_t)32 << 20) ? 512 : 128;
-    std::vector<double> M;
-    transition_matrix(sos.data(), S, C, M);
+    int64_t total = 0, max_len = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30, "clip %lld has invalid length %lld", (long long)i, (long long)n);
+        total += n;
+        max_len = std::max(max_len, n);
+    }
 
-    const size_t idx_bytes = 2 * (size_t)(n_clips + 1) * sizeof(int64_t);
-    const size_t m_bytes = (size_t)D * D * sizeof(double);
+    // ---- choose the algorithm: overlap (one pass, W warm-up samples per chunk) or exact scan
+    const int C_exact = total >= ((int64_t)32 << 20) ? 512 : 128;
+    if (ctx->iir_cache_S != S || memcmp(ctx->iir_cache_sos, sos.data(), sizeof(double) * 6 * S) != 0) {
+        ctx->iir_cache_W = decay_length(sos.data(), S, 1e-13, 8192);
+        ctx->iir_cache_S = S;
+        memcpy(ctx->iir_cache_sos, sos.data(), sizeof(double) * 6 * S);
+    }
+    const int W = ctx->iir_cache_W;
+    const bool fuse_trim = trim && trim->frame_length == 2 * trim->hop_length && trim->hop_length % 32 == 0;
+    const int unit = fuse_trim ? trim->hop_length : 800;
+    int C_overlap = 0;
+    if (W > 0 && ctx->iir_algo != HMFE_IIR_ALGO_SCAN) {
+        const double slots_o = (double)ctx->sm_count * 4 * kIirWarps * 32;  // launch bounds: 4 CTAs per SM
+        const double slots_e = (double)ctx->sm_count * 6 * kIirWarps * 32;
+        auto chunks_at = [&](int C) {
+            int64_t c = 0;
+            for (int64_t i = 0; i < n_clips; ++i) c += (h_offsets[i + 1] - h_offsets[i] + C - 1) / C;
+            return c;
+        };
+        const double cost_exact = 2.2 * C_exact * ceil((double)chunks_at(C_exact) / slots_e) * slots_e;
+        double best = 0.0;
+        static const int mult[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40};
+        for (int m : mult) {
+            const int C = unit * m;
+            if (C < 512 || C > 32768) continue;
+            const double cost = (double)(W + C) * ceil((double)chunks_at(C) / slots_o) * slots_o;
+            if (C_overlap == 0 || cost < best) {
+                best = cost;
+                C_overlap = C;
+            }
+        }
+        if (ctx->iir_algo == HMFE_IIR_ALGO_AUTO && !(best < cost_exact)) C_overlap = 0;
+    }
+    HMFE_REQUIRE(C_overlap > 0 || ctx->iir_algo != HMFE_IIR_ALGO_OVERLAP,
+                 "overlap IIR requested but the filter does not decay within 8192 samples");
+    const bool overlap = C_overlap > 0;
+    const int C = overlap ? C_overlap : C_exact;
+    const bool power = overlap && fuse_trim;
+    ctx->iir_last_algo = overlap ? HMFE_IIR_ALGO_OVERLAP : HMFE_IIR_ALGO_SCAN;
+    ctx->iir_last_C = C;
+    ctx->iir_last_W = overlap ? W : 0;
+
+    std::vector<double> M;
+    if (!overlap) transition_matrix(sos.data(), S, C, M);
+    const size_t idx_bytes = 3 * (size_t)(n_clips + 1) * sizeof(int64_t);
+    const size_t m_bytes = overlap ? 0 : (size_t)D * D * sizeof(double);
     void *hbuf = nullptr, *dbuf = nullptr;
     const int slot = ctx->ring.acquire(idx_bytes + m_bytes, &hbuf, &dbuf);
     if (slot < 0) return slot;
     int64_t* hc = static_cast<int64_t*>(hbuf);
     int64_t* hp = hc + (n_clips + 1);
-    hp[0] = 0;
+    int64_t* hh = hp + (n_clips + 1);
+    hp[0] = hh[0] = 0;
+    const int hop = trim ? trim->hop_length : 1;
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t n = h_offsets[i + 1] - h_offsets[i];
-        HMFE_REQUIRE(n >= 0, "clip %lld has negative length", (long long)i);
         hc[i] = h_offsets[i];
         hp[i + 1] = hp[i] + (n + C - 1) / C;
+        hh[i + 1] = hh[i] + (power ? (n + hop - 1) / hop : 0);
     }
     hc[n_clips] = h_offsets[n_clips];
-    memcpy(static_cast<unsigned char*>(hbuf) + idx_bytes, M.data(), m_bytes);
+    if (m_bytes) memcpy(static_cast<unsigned char*>(hbuf) + idx_bytes, M.data(), m_bytes);
     int rc = ctx->ring.upload(slot, idx_bytes + m_bytes, st);
     if (rc != HMFE_OK) return rc;
-    IirBatch b{};
-    b.x = d_x;
-    b.y32 = d_y32;
-    b.y64 = d_y64;
-    b.clip_off = static_cast<int64_t*>(dbuf);
-    b.chunk_prefix = b.clip_off + (n_clips + 1);
-    b.M = reinterpret_cast<double*>(static_cast<unsigned char*>(dbuf) + idx_bytes);
-    b.n_clips = n_clips;
-    b.n_chunks = hp[n_clips];
-    b.C = C;
-    if (b.n_chunks == 0) return ctx->ring.release(slot, st);
-    rc = ctx->reserve_scratch(2 * (size_t)b.n_chunks * D * sizeof(double));
-    if (rc != HMFE_OK) return rc;
-    b.zstate = static_cast<double*>(ctx->scratch);
-    b.init = b.zstate + b.n_chunks * D;
-    switch (S) {
-        case 1: rc = run_iir<1>(ctx, b, sos.data(), bp, gain, st); break;
-        case 2: rc = run_iir<2>(ctx, b, sos.data(), bp, gain, st); break;
-        case 3: rc = run_iir<3>(ctx, b, sos.data(), bp, gain, st); break;
-        case 4: rc = run_iir<4>(ctx, b, sos.data(), bp, gain, st); break;
-        case 5: rc = run_iir<5>(ctx, b, sos.data(), bp, gain, st); break;
-        case 6: rc = run_iir<6>(ctx, b, sos.data(), bp, gain, st); break;
-        case 7: rc = run_iir<7>(ctx, b, sos.data(), bp, gain, st); break;
-        default: rc = run_iir<8>(ctx, b, sos.data(), bp, gain, st); break;
+    const int64_t* d_clip_off = static_cast<int64_t*>(dbuf);
+    const int64_t* d_chunk_prefix = d_clip_off + (n_clips + 1);
+    const int64_t* d_hop_off = d_chunk_prefix + (n_clips + 1);
+    const int64_t n_chunks = hp[n_clips];
+
+    if (overlap) {
+        IirOverlapBatch b{};
+        b.x = d_x;
+        b.y32 = d_y32;
+        b.y64 = d_y64;
+        b.clip_off = d_clip_off;
+        b.chunk_prefix = d_chunk_prefix;
+        b.hop_off = d_hop_off;
+        b.n_clips = n_clips;
+        b.n_chunks = n_chunks;
+        b.C = C;
+        b.W = W;
+        b.hop_steps = power ? hop / 32 : 1;
+        if (power) {
+            rc = ctx->reserve_scratch((size_t)std::max<int64_t>(1, hh[n_clips]) * sizeof(float));
+            if (rc != HMFE_OK) return rc;
+            b.hop_energy = static_cast<float*>(ctx->scratch);
+        }
+        if (n_chunks > 0) {
+            switch (S) {
+                case 1: rc = run_iir_overlap<1>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 2: rc = run_iir_overlap<2>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 3: rc = run_iir_overlap<3>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 4: rc = run_iir_overlap<4>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 5: rc = run_iir_overlap<5>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 6: rc = run_iir_overlap<6>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 7: rc = run_iir_overlap<7>(ctx, b, sos.data(), bp, gain, power, st); break;
+                default: rc = run_iir_overlap<8>(ctx, b, sos.data(), bp, gain, power, st); break;
+            }
+            if (rc != HMFE_OK) return rc;
+        }
+        if (power) {
+            TrimHopBatch tb{b.hop_energy, d_clip_off, d_hop_off, trim->d_start_end, n_clips, hop, trim->top_db};
+            ctx->prof_begin(HMFE_K_TRIM_INDEX, st);
+            trim_index_hop_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(tb);
+            HMFE_CHECK_CUDA(cudaGetLastError());
+            ctx->prof_end(st);
+            ctx->last_launches += 1;
+        }
+    } else {
+        IirBatch b{};
+        b.x = d_x;
+        b.y32 = d_y32;
+        b.y64 = d_y64;
+        b.clip_off = d_clip_off;
+        b.chunk_prefix = d_chunk_prefix;
+        b.M = reinterpret_cast<const double*>(static_cast<const unsigned char*>(dbuf) + idx_bytes);
+        b.n_clips = n_clips;
+        b.n_chunks = n_chunks;
+        b.C = C;
+        if (n_chunks > 0) {
+            rc = ctx->reserve_scratch(2 * (size_t)n_chunks * D * sizeof(double));
+            if (rc != HMFE_OK) return rc;
+            b.zstate = static_cast<double*>(ctx->scratch);
+            b.init = b.zstate + n_chunks * D;
+            switch (S) {
+                case 1: rc = run_iir<1>(ctx, b, sos.data(), bp, gain, st); break;
+                case 2: rc = run_iir<2>(ctx, b, sos.data(), bp, gain, st); break;
+                case 3: rc = run_iir<3>(ctx, b, sos.data(), bp, gain, st); break;
+                case 4: rc = run_iir<4>(ctx, b, sos.data(), bp, gain, st); break;
+                case 5: rc = run_iir<5>(ctx, b, sos.data(), bp, gain, st); break;
+                case 6: rc = run_iir<6>(ctx, b, sos.data(), bp, gain, st); break;
+                case 7: rc = run_iir<7>(ctx, b, sos.data(), bp, gain, st); break;
+                default: rc = run_iir<8>(ctx, b, sos.data(), bp, gain, st); break;
+            }
+            if (rc != HMFE_OK) return rc;
+        }
     }
+    rc = ctx->ring.release(slot, st);
     if (rc != HMFE_OK) return rc;
-    return ctx->ring.release(slot, st);
+    if (trim && !power) {  // exact scan (or a hop the fused kernel does not cover): separate trim kernels
+        const int launches = ctx->last_launches;
+        rc = hmfe_trim_batch(ctx, d_y32, h_offsets, n_clips, trim->frame_length, trim->hop_length, trim->top_db,
+                             trim->d_start_end, stream);
+        ctx->last_launches += launches;
+    }
+    return rc;
+}
+
+}  // namespace hmfe
+
+using namespace hmfe;
+
+extern "C" int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
+                                  const double* h_sos, int n_sections, float* d_y32, double* d_y64, void* stream) {
+    return iir_impl(ctx, d_x, h_offsets, n_clips, h_sos, n_sections, d_y32, d_y64, nullptr, stream);
+}
+
+extern "C" int hmfe_iir_sos_trim_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
+                                       const double* h_sos, int n_sections, float* d_y32, double* d_y64,
+                                       int frame_length, int hop_length, float top_db, int64_t* d_start_end,
+                                       void* stream) {
+    const TrimArgs t{frame_length, hop_length, top_db, d_start_end};
+    return iir_impl(ctx, d_x, h_offsets, n_clips, h_sos, n_sections, d_y32, d_y64, &t, stream);
+}
+
+extern "C" int hmfe_ctx_set_iir_algo(hmfe_ctx* ctx, int algo) {
+    HMFE_REQUIRE(ctx, "NULL ctx");
+    HMFE_REQUIRE(algo >= HMFE_IIR_ALGO_AUTO && algo <= HMFE_IIR_ALGO_OVERLAP, "bad IIR algorithm id %d", algo);
+    ctx->iir_algo = algo;
+    return HMFE_OK;
+}
+
+extern "C" int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup) {
+    HMFE_REQUIRE(ctx, "NULL ctx");
+    if (algo) *algo = ctx->iir_last_algo;
+    if (chunk) *chunk = ctx->iir_last_C;
+    if (warmup) *warmup = ctx->iir_last_W;
+    return HMFE_OK;
 }

@@ -191,6 +191,16 @@ class Context:
     def set_profile(self, enable: bool):
         check(_lib.hmfe_ctx_set_profile(self._h, int(bool(enable))))
 
+    def set_iir_algo(self, algo: str = "auto"):
+        """"auto" | "scan" (exact chunked scan) | "overlap" (one pass with warm-up) - include/hmfe.h."""
+        check(_lib.hmfe_ctx_set_iir_algo(self._h, _lib.IIR_ALGOS[algo]), "hmfe_ctx_set_iir_algo")
+
+    def last_iir_plan(self) -> dict:
+        a, c, w = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.hmfe_ctx_last_iir_plan(self._h, C.byref(a), C.byref(c), C.byref(w)))
+        return {"algo": {v: k for k, v in _lib.IIR_ALGOS.items()}.get(a.value, "none"), "chunk": c.value,
+                "warmup": w.value}
+
     def profile_ms(self) -> dict:
         """{kernel name: (total ms, launches)} since the last query (synchronises)."""
         n = len(_lib.KERNEL_NAMES)
@@ -292,6 +302,32 @@ def iir_sos(wav: torch.Tensor, offsets, sos: np.ndarray, out: torch.Tensor | Non
             "hmfe_iir_sos_batch",
         )
     return out
+
+
+def iir_sos_trim(wav: torch.Tensor, offsets, sos: np.ndarray, out: torch.Tensor | None = None, frame_length=1600,
+                 hop_length=800, top_db=60.0, out64: torch.Tensor | None = None, ctx: Context | None = None, stream=None):
+    """Band-pass + silence-trim indices of the filtered signal in one call (src/util.py:226-244).
+
+    Returns (filtered float32 signal, int64 CUDA tensor [n_clips, 2] of clip-relative (start, end))."""
+    _require_cuda_f32(wav, "wav")
+    o = _as_offsets(offsets)
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    ctx = ctx or default_ctx()
+    if out is None:
+        out = torch.empty(wav.numel(), dtype=torch.float32, device=wav.device)
+    if out.dtype != torch.float32:
+        raise TypeError("out must be float32 (pass out64 for the float64 copy)")
+    y64 = C.c_void_p(out64.data_ptr()) if out64 is not None else C.c_void_p()
+    se = torch.empty((o.size - 1, 2), dtype=torch.int64, device=wav.device)
+    with torch.cuda.device(wav.device):
+        check(
+            _lib.hmfe_iir_sos_trim_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
+                                         sos.ctypes.data_as(C.c_void_p), sos.shape[0], C.c_void_p(out.data_ptr()), y64,
+                                         int(frame_length), int(hop_length), float(top_db), C.c_void_p(se.data_ptr()),
+                                         _stream_ptr(stream)),
+            "hmfe_iir_sos_trim_batch",
+        )
+    return out, se
 
 
 def trim_indices(wav: torch.Tensor, offsets, frame_length=1600, hop_length=800, top_db=60.0, ctx: Context | None = None,

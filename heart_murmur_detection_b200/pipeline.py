@@ -84,13 +84,13 @@ def prepare_chunks(wav: torch.Tensor, offsets, chunker, *, sample_rate=16000, bu
     sos = _sos_for(butterworth_filter, lowcut, highcut, sample_rate)
     lens = np.diff(o)
     spare = int(pad_hint) * (int((lens < pad_hint).sum()) + 16) if pad_hint else 0
-    if sos is not None:
+    frame_len = int(sample_rate / 10)
+    if sos is not None:  # band-pass and the trim of the filtered signal in one call
         work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
-        fe.iir_sos(wav, o, sos, out=work, ctx=ctx)
-        launches += ctx.last_launches
+        _, se = fe.iir_sos_trim(wav, o, sos, out=work, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     else:
         work = wav
-    se = fe.trim_indices(work, o, frame_length=int(sample_rate / 10), hop_length=int(int(sample_rate / 10) / 2), ctx=ctx)
+        se = fe.trim_indices(work, o, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     launches += ctx.last_launches
     se = se.cpu().numpy()  # the one host round trip: durations drive the reference's control flow
     chunk_lists, valid = [], np.ones(n, dtype=bool)
@@ -193,13 +193,13 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
     sos = _sos_for(butterworth_filter, lowcut, highcut, sample_rate)
     lens = np.diff(o)
     spare = L * (int((lens < L).sum()) + 16) if pad else 0
-    if sos is not None:
+    frame_len = int(sample_rate / 10)
+    if sos is not None:  # band-pass and the trim of the filtered signal in one call
         work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
-        fe.iir_sos(wav, o, sos, out=work, ctx=ctx)
-        launches += ctx.last_launches
+        _, se = fe.iir_sos_trim(wav, o, sos, out=work, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     else:
         work = wav
-    se = fe.trim_indices(work, o, frame_length=int(sample_rate / 10), hop_length=int(int(sample_rate / 10) / 2), ctx=ctx)
+        se = fe.trim_indices(work, o, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     launches += ctx.last_launches
     se = se.cpu().numpy()
     n = se[:, 1] - se[:, 0]

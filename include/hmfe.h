@@ -84,8 +84,9 @@ int hmfe_ctx_last_launches(const hmfe_ctx* ctx);
  * CUDA events on its launch stream.  hmfe_ctx_profile_ms synchronises on them, writes the
  * summed milliseconds and launch counts per kernel id (arrays of HMFE_KERNEL_COUNT) and resets.
  * ids: 0 iir zero-state pass, 1 iir carry scan, 2 iir final pass, 3 trim frame power,
- *      4 trim first/last index, 5 pad-split gather, 6 spectrogram mean, 7 spectrogram crop */
-#define HMFE_KERNEL_COUNT 8
+ *      4 trim first/last index, 5 pad-split gather, 6 spectrogram mean, 7 spectrogram crop,
+ *      8 iir one-pass overlap kernel */
+#define HMFE_KERNEL_COUNT 9
 int hmfe_ctx_set_profile(hmfe_ctx* ctx, int enable);
 int hmfe_ctx_profile_ms(hmfe_ctx* ctx, double* ms_by_kernel, int* launches_by_kernel);
 
@@ -130,6 +131,26 @@ int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmf
  * ------------------------------------------------------------------------------------------ */
 int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
                        const double* h_sos, int n_sections, float* d_y32, double* d_y64, void* stream);
+/* Band-pass followed by the silence trim of the FILTERED signal, i.e. lines 226-244 of
+ * get_entire_signal_librosa (src/util.py; same pair at :157-172, :327-340, :809-822) in one call:
+ * y = lfilter(b, a, x) as above, and d_start_end[n_clips][2] = librosa.effects.trim indices of y
+ * as hmfe_trim_batch would return them.  When the one-pass overlap kernel runs and
+ * frame_length == 2 * hop_length, the frame energies are accumulated while y is produced and y
+ * is not read back.  d_y32 is required. */
+int hmfe_iir_sos_trim_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
+                            const double* h_sos, int n_sections, float* d_y32, double* d_y64, int frame_length,
+                            int hop_length, float top_db, int64_t* d_start_end, void* stream);
+/* Two realisations of the same filter.  SCAN: exact chunked scan (zero-state pass, carry scan with
+ * the chunk transition matrix, final pass), any stable or unstable cascade.  OVERLAP: one pass in
+ * which every chunk starts W samples early from a zero state, W chosen so that the cascade's
+ * zero-input response has decayed below 1e-13 (infinity norm); refused for filters that need
+ * W > 8192.  AUTO (default) picks the cheaper one for the batch at hand. */
+#define HMFE_IIR_ALGO_AUTO 0
+#define HMFE_IIR_ALGO_SCAN 1
+#define HMFE_IIR_ALGO_OVERLAP 2
+int hmfe_ctx_set_iir_algo(hmfe_ctx* ctx, int algo);
+/* algorithm, chunk length and warm-up length the last IIR call on this context used */
+int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup);
 
 /* ------------------------------------------------------------------------------------------
  * Kaldi fbank: replaces torchaudio.compliance.kaldi.fbank(w, htk_compat=True,

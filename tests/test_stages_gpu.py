@@ -84,6 +84,134 @@ def test_iir_large_batch_uses_long_chunks_and_is_linear():
     assert (y3 - (0.5 * y + 0.25 * y2)).abs().max().item() <= 1e-6
 
 
+@pytest.mark.parametrize("order", [5, 2])
+def test_iir_overlap_matches_scan_and_scipy(order):
+    """The one-pass overlap kernel (chunks warmed up over W samples) against scipy.lfilter and
+    against the exact scan, on lengths around the chunk / warm-up / hop boundaries."""
+    from scipy.signal import butter, lfilter
+
+    from heart_murmur_detection_b200 import frontend as fe
+
+    sos = fe.butter_bandpass_sos(200, 1800, SR, order)
+    b, a = butter(order, [200 / 8000, 1800 / 8000], btype="band")
+    ctx_o, ctx_s = fe.Context(), fe.Context()
+    ctx_o.set_iir_algo("overlap")
+    ctx_s.set_iir_algo("scan")
+    probe, poff = _batch([golden_signal(64000, 1)])
+    fe.iir_sos(probe, poff, sos, ctx=ctx_o)
+    plan = ctx_o.last_iir_plan()
+    assert plan["algo"] == "overlap" and plan["warmup"] % 32 == 0 and plan["chunk"] % 32 == 0
+    for _ in range(3):  # the chunk length depends on the batch: iterate until the lengths straddle it
+        Cc, W = plan["chunk"], plan["warmup"]
+        lens = [1, 2, 31, 32, 33, 799, 800, 801, 1599, 1601, W - 1, W, W + 1, Cc - 1, Cc, Cc + 1, 2 * Cc + 5, 3 * Cc,
+                128000, 90001, 300000, 5 * Cc + W + 17]
+        clips = [golden_signal(n, seed=3 + i) for i, n in enumerate(lens)]
+        clips[4] = np.zeros(33, np.float32)
+        clips[4][0] = 1.0  # impulse
+        clips[5] = np.ones(799, np.float32)  # step
+        wav, off = _batch(clips)
+        y64 = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx_o).cpu().numpy()
+        assert ctx_o.last_launches == 1
+        plan = ctx_o.last_iir_plan()
+        assert plan["algo"] == "overlap"
+        if plan["chunk"] == Cc:
+            break
+    y32 = fe.iir_sos(wav, off, sos, out_dtype=torch.float32, ctx=ctx_o).cpu().numpy()
+    ys = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx_s).cpu().numpy()
+    assert ctx_s.last_iir_plan()["algo"] == "scan"
+    # scipy's own pairing -> the general (non band-pass-form) cascade code
+    y64g = fe.iir_sos(wav, off, butter(order, [200 / 8000, 1800 / 8000], btype="band", output="sos"),
+                      out_dtype=torch.float64, ctx=ctx_o).cpu().numpy()
+    for i, x in enumerate(clips):
+        ref = lfilter(b, a, x)
+        scale = max(np.abs(ref).max(), 1e-12)
+        seg = slice(off[i], off[i + 1])
+        assert np.abs(y64[seg] - ref).max() <= min(1e-4 * scale, 1e-6), (i, lens[i])
+        assert np.abs(y64g[seg] - ref).max() <= min(1e-4 * scale, 1e-6), (i, lens[i])
+        assert np.abs(y32[seg] - ref).max() <= 1e-4 * scale, (i, lens[i])
+        assert np.abs(y64[seg] - ys[seg]).max() <= 1e-10 * max(scale, 1e-3), (i, lens[i])
+
+
+def test_iir_overlap_refused_for_slow_filters():
+    """A pole at radius 0.99995 needs far more than 8192 warm-up samples: forced overlap is an
+    error, auto falls back to the exact scan and still matches scipy."""
+    from scipy.signal import lfilter
+
+    from heart_murmur_detection_b200 import _lib
+    from heart_murmur_detection_b200 import frontend as fe
+
+    r, th = 0.99995, 0.3
+    sos = np.array([[1.0, 0.0, 0.0, 1.0, -2 * r * np.cos(th), r * r]])
+    x = golden_signal(50000, 5)
+    wav, off = _batch([x])
+    ctx = fe.Context()
+    y = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx).cpu().numpy()
+    assert ctx.last_iir_plan()["algo"] == "scan"
+    ref = lfilter(sos[0, :3], sos[0, 3:], x)
+    assert np.abs(y - ref).max() <= 1e-9 * np.abs(ref).max()
+    ctx.set_iir_algo("overlap")
+    with pytest.raises(_lib.HmfeError):
+        fe.iir_sos(wav, off, sos, ctx=ctx)
+
+
+@pytest.mark.parametrize("algo", ["overlap", "scan", "auto"])
+def test_iir_trim_fused_indices_exact(algo):
+    """hmfe_iir_sos_trim_batch: indices equal librosa.effects.trim of scipy's lfilter output."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from oracle import frontend as F
+
+    clips = [golden_signal(n, seed, SR, lead, tail) for _, n, seed, lead, tail in RECORDINGS]
+    for lead, tail in [(0, 0), (799, 801), (800, 1600), (2400, 0), (0, 4000), (5, 17)]:
+        clips.append(golden_signal(48000, 11, SR, lead, tail))
+    clips.append(np.zeros(5000, np.float32))
+    clips.append(golden_signal(30000, 12, SR, 0, 0))
+    clips.append(golden_signal(700, 13, SR, 0, 0))
+    clips.append(golden_signal(800, 14, SR, 0, 0))
+    clips.append(golden_signal(25600 + 799, 15, SR, 3000, 0))
+    clips.append(golden_signal(300000, 16, SR, 20000, 33000))
+    # in-band tone bursts between very quiet edges: after the band-pass the edges fall > 60 dB below the
+    # burst, so the trim indices are non-trivial (the heart tones of golden_signal are out of band)
+    for k, (lead, body, tail) in enumerate([(4000, 30000, 9000), (801, 16000, 1599), (0, 52000, 20000), (12345, 3200, 0)]):
+        t = np.arange(lead + body + tail)
+        x = 1e-6 * ((t * 7919 + k) % 13 - 6.0)
+        x[lead : lead + body] += 0.4 * np.sin(2 * np.pi * (450 + 100 * k) * t[lead : lead + body] / SR)
+        clips.append(x.astype(np.float32))
+    wav, off = _batch(clips)
+    ctx = fe.Context()
+    ctx.set_iir_algo(algo)
+    sos = fe.butter_bandpass_sos(200, 1800, SR, 5)
+    y, se = fe.iir_sos_trim(wav, off, sos, ctx=ctx)
+    if algo == "overlap":
+        assert ctx.last_launches == 2  # one filter pass + the index kernel: the signal is not re-read
+    y, se = y.cpu().numpy(), se.cpu().numpy()
+    for i, x in enumerate(clips):
+        ref = F.butter_bandpass_filter(x, 200, 1800, SR, 5)
+        _, idx = F.trim_silence(ref, SR)
+        assert [int(se[i, 0]), int(se[i, 1])] == [int(idx[0]), int(idx[1])], (i, len(x))
+        assert np.abs(y[off[i] : off[i + 1]] - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-12)
+
+
+def test_iir_auto_picks_overlap_on_large_batches():
+    from scipy.signal import butter, lfilter
+
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c2", 600, seed=9)
+    wav, off = synth.make_batch(lens, base_seed=31, device="cuda")
+    sos = fe.butter_bandpass_sos(200, 1800, SR, 5)
+    ctx = fe.Context()
+    y = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx)
+    assert ctx.last_iir_plan()["algo"] == "overlap", ctx.last_iir_plan()
+    b, a = butter(5, [200 / 8000, 1800 / 8000], btype="band")
+    for i in (0, 1, 299, 599):
+        ref = lfilter(b, a, wav[off[i] : off[i + 1]].cpu().numpy())
+        assert np.abs(y[off[i] : off[i + 1]].cpu().numpy() - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max())
+    ctx.set_iir_algo("scan")
+    ys = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx)
+    assert (y - ys).abs().max().item() <= 1e-10
+
+
 def test_butter_design_matches_scipy():
     from scipy.signal import butter
 
