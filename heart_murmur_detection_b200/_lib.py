@@ -100,8 +100,11 @@ hmfe_iir_sos_trim_batch = _sig(
 )
 IIR_ALGOS = {"auto": 0, "scan": 1, "overlap": 2}
 hmfe_ctx_set_iir_algo = _sig("hmfe_ctx_set_iir_algo", C.c_int, c_voidp, C.c_int)
+IIR_ROWS = {"auto": 0, "scalar": 1, "vector": 2}
+hmfe_ctx_set_iir_rows = _sig("hmfe_ctx_set_iir_rows", C.c_int, c_voidp, C.c_int)
 hmfe_ctx_last_iir_plan = _sig(
-    "hmfe_ctx_last_iir_plan", C.c_int, c_voidp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)
+    "hmfe_ctx_last_iir_plan", C.c_int, c_voidp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+    C.POINTER(C.c_int),
 )
 
 hmfe_fbank_plan_create = _sig(

@@ -29,7 +29,8 @@ struct hmfe_ctx {
     int last_launches = 0;
     // IIR algorithm choice (hmfe_ctx_set_iir_algo) and what the last call used
     int iir_algo = HMFE_IIR_ALGO_AUTO;
-    int iir_last_algo = 0, iir_last_C = 0, iir_last_W = 0;
+    int iir_rows = HMFE_IIR_ROWS_AUTO;
+    int iir_last_algo = 0, iir_last_C = 0, iir_last_W = 0, iir_last_rows = 0;
     // decay length of the last filter seen (depends on the coefficients only)
     int iir_cache_S = 0, iir_cache_W = 0;
     double iir_cache_sos[6 * 8] = {};

@@ -22,6 +22,7 @@
 // so the filtered signal is not read a second time.  Filters with slowly decaying poles fall
 // back to the exact three-kernel scan above.
 #include <math.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <vector>
@@ -335,6 +336,236 @@ __global__ void __launch_bounds__(kIirWarps * 32, 4) iir_overlap_kernel(const Ii
     }
 }
 
+// ------------------------------------------------------------------------------ overlap, 128-bit rows
+// Same algorithm with 16-byte global accesses.  Every clip is addressed from the 16-byte aligned
+// element at or before its first sample (aligned origin = c0 - s, s in 0..3): chunk boundaries,
+// the warm-up length and the 128-sample steps are multiples of 4 in that coordinate, so a lane's
+// float4 never straddles two chunks and rows move as LDG.128 / STG.128.  Samples in front of the
+// clip (the s alignment slots, and the warm-up of its first chunks) are loaded as zeros, which
+// leaves the zero state untouched.  Steps in which some row has a clip edge inside a float4 take
+// a scalar (per element predicated) variant of the load / store phase.
+//
+// Hop energies are accumulated in the aligned coordinate as well: group g holds the samples at
+// aligned positions [g*hop, (g+1)*hop) as {sum over all but the first four, the four first
+// squares}; trim_index_hop4_kernel re-assembles the clip-relative hop block h from groups h and
+// h+1 (additions only).
+struct IirOverlap4Batch {
+    const float* x;
+    float* y32;
+    const int64_t* clip_off;      // [n_clips+1]
+    const int64_t* chunk_prefix;  // [n_clips+1]  chunks of ceil((s + n) / C)
+    const int64_t* group_off;     // [n_clips+1]  groups of ceil((s + n) / hop)    (POWER only)
+    float* group_energy;          // [n_groups][8]                                  (POWER only)
+    int64_t n_clips, n_chunks;
+    int C, W;                     // multiples of 128; POWER: C is a multiple of hop
+    int hop;                      // multiple of 32 (POWER only)
+    int align;                    // (address of x / 4) mod 4
+};
+
+constexpr int kRow4 = 132;  // tile row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row
+
+struct __align__(16) IirRow4 {
+    long long base;  // element index of stream position 0 (16-byte aligned address; may be negative)
+    int lo, hi;      // stream positions [lo, hi) hold clip samples
+};
+
+template <int S, bool BP>
+HMFE_D void iir_block32(const IirCoef<S>& cf, float* row, double (&s1)[S], double (&s2)[S], bool emit, float& body,
+                        float (&head)[4]) {
+    // 32 consecutive samples of this lane's row: read as 8 float4, filter, write back in place
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float4 v = *reinterpret_cast<const float4*>(row + 4 * u);
+        float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float f = (float)cascade<S, BP>(cf, (double)e[c], s1, s2);
+            e[c] = f;
+            if (u == 0)
+                head[c] = f * f;
+            else
+                body = fmaf(f, f, body);
+        }
+        if (emit) *reinterpret_cast<float4*>(row + 4 * u) = v;
+    }
+}
+
+template <int S, bool BP, bool POWER>
+__global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const IirOverlap4Batch b, const IirCoef<S> cf) {
+    extern __shared__ __align__(16) unsigned char iir_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float(*tile)[kRow4] = reinterpret_cast<float(*)[kRow4]>(iir_smem) + warp * 32;
+    IirRow4* rows = reinterpret_cast<IirRow4*>(iir_smem + (size_t)kIirWarps * 32 * kRow4 * sizeof(float)) + warp * 32;
+    const int64_t g = ((int64_t)blockIdx.x * kIirWarps + warp) * 32 + lane;
+    double s1[S], s2[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) s1[k] = s2[k] = 0.0;
+    IirRow4 me{0, 0, 0};
+    int64_t group_base = 0;
+    if (g < b.n_chunks) {
+        int64_t lo = 0, hi = b.n_clips;  // largest clip with chunk_prefix[clip] <= g
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (b.chunk_prefix[mid] <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int64_t j = g - b.chunk_prefix[lo];
+        const int64_t c0 = b.clip_off[lo], n = b.clip_off[lo + 1] - c0;
+        const int s = (int)((c0 + b.align) & 3);
+        const int64_t p0 = j * b.C;  // aligned-coordinate start of this chunk
+        me.base = c0 - s + p0 - b.W;
+        me.lo = (int)max((int64_t)0, (int64_t)s + b.W - p0);
+        me.hi = b.W + (int)min((int64_t)b.C, (int64_t)s + n - p0);
+        if (POWER) group_base = b.group_off[lo] + j * (b.C / b.hop);
+    }
+    rows[lane] = me;
+    __syncwarp();
+    const int hi_self = me.hi;
+    const int valid_len = me.hi - b.W;  // chunk positions [0, valid_len) exist (<= 0 for idle lanes)
+    const int t_end = b.W + b.C;
+    int t_first = me.hi > me.lo ? (me.lo & ~127) : t_end;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, d));
+    // steps in which one of this warp's rows has an edge that is not a multiple of 4
+    const int edge_lo = (me.hi > me.lo && (me.lo & 3)) ? (me.lo >> 7) : -1;
+    const int edge_hi = (me.hi > me.lo && (me.hi & 3)) ? (me.hi >> 7) : -1;
+
+    float body = 0.0f, head[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q[4] = {0.0f, 0.0f, 0.0f, 0.0f}, grp = 0.0f;
+    int gidx = 0, pos_in_group = 0;
+    const int tl = 4 * lane;
+    for (int t0 = t_first; t0 < t_end; t0 += 128) {
+        const int step = t0 >> 7;
+        const bool edge = __any_sync(0xffffffffu, edge_lo == step || edge_hi == step);
+        const int t = t0 + tl;
+        // ---- load phase: row r, positions t .. t+3 -> tile[r][4*lane ..]
+        if (!edge) {
+#pragma unroll
+            for (int rb = 0; rb < 32; rb += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const IirRow4 rd = rows[rb + u];
+                    v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if ((unsigned)(t - rd.lo) < (unsigned)(rd.hi - rd.lo)) {
+#ifdef HMFE_DEBUG_ALIGN
+                        if (reinterpret_cast<uintptr_t>(b.x + rd.base + t) & 15)
+                            printf("LD misaligned: row %d base %lld t %d lo %d hi %d align %d\n", rb + u, rd.base, t, rd.lo,
+                                   rd.hi, b.align);
+                        else
+#endif
+                        v[u] = __ldg(reinterpret_cast<const float4*>(b.x + rd.base + t));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(&tile[rb + u][tl]) = v[u];
+            }
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const IirRow4 rd = rows[r];
+                float4 v;
+                float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    e[c] = (unsigned)(t + c - rd.lo) < (unsigned)(rd.hi - rd.lo) ? __ldg(b.x + rd.base + t + c) : 0.0f;
+                *reinterpret_cast<float4*>(&tile[r][tl]) = v;
+            }
+        }
+        __syncwarp();
+        // ---- filter phase: this lane's row, 4 blocks of 32 samples
+        const bool emit = t0 >= b.W;  // warp uniform (W is a multiple of 128)
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            const int tb = t0 + 32 * sub;
+            bool group_start = false;
+            if (POWER && emit) {
+                if (pos_in_group == b.hop) {  // a group is complete (warp uniform)
+                    if (gidx * b.hop < valid_len) {
+                        float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
+                        dst[0] = make_float4(grp, q[0], q[1], q[2]);
+                        dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
+                    }
+                    ++gidx;
+                    pos_in_group = 0;
+                    grp = 0.0f;
+                }
+                group_start = pos_in_group == 0;
+                pos_in_group += 32;
+            }
+            const int rem = hi_self - tb;
+            if (rem >= 32) {
+                body = 0.0f;
+                iir_block32<S, BP>(cf, &tile[lane][32 * sub], s1, s2, emit, body, head);
+                if (POWER && emit) {
+                    if (group_start) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q[c] = head[c];
+                    } else {
+                        body += (head[0] + head[1]) + (head[2] + head[3]);
+                    }
+                    grp += body;
+                }
+            } else if (rem > 0) {  // the block that holds the end of the clip
+                float acc = 0.0f;
+                if (POWER && emit && group_start) q[0] = q[1] = q[2] = q[3] = 0.0f;
+#pragma unroll 1
+                for (int k = 0; k < rem; ++k) {
+                    const float f = (float)cascade<S, BP>(cf, (double)tile[lane][32 * sub + k], s1, s2);
+                    tile[lane][32 * sub + k] = f;
+                    if (POWER && emit) {
+                        if (group_start && k < 4)
+                            q[k] = f * f;
+                        else
+                            acc = fmaf(f, f, acc);
+                    }
+                }
+                grp += acc;
+            } else if (POWER && emit && group_start) {
+                q[0] = q[1] = q[2] = q[3] = 0.0f;
+            }
+        }
+        __syncwarp();
+        // ---- store phase
+        if (emit) {
+            if (!edge) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const IirRow4 rd = rows[r];
+                    const int olo = max(rd.lo, b.W);
+                    if (t >= olo && t < rd.hi) {
+#ifdef HMFE_DEBUG_ALIGN
+                        if (reinterpret_cast<uintptr_t>(b.y32 + rd.base + t) & 15)
+                            printf("ST misaligned: row %d base %lld t %d lo %d hi %d align %d\n", r, rd.base, t, rd.lo, rd.hi,
+                                   b.align);
+                        else
+#endif
+                        *reinterpret_cast<float4*>(b.y32 + rd.base + t) = *reinterpret_cast<const float4*>(&tile[r][tl]);
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const IirRow4 rd = rows[r];
+                    const int olo = max(rd.lo, b.W);
+                    const float4 v = *reinterpret_cast<const float4*>(&tile[r][tl]);
+                    const float* e = reinterpret_cast<const float*>(&v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (t + c >= olo && t + c < rd.hi) b.y32[rd.base + t + c] = e[c];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (POWER && gidx * b.hop < valid_len) {  // the last group of the chunk
+        float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
+        dst[0] = make_float4(grp, q[0], q[1], q[2]);
+        dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
+    }
+}
+
 // Silence-trim indices from per-hop energy sums (frame_length == 2 * hop, centred frames):
 // frame t covers hop blocks t-1 and t.  Same float32 arithmetic as trim_frame_power_kernel +
 // trim_index_kernel (ragged_ops.cu); one CTA per clip.
@@ -360,6 +591,92 @@ __global__ void __launch_bounds__(256) trim_index_hop_kernel(const TrimHopBatch 
         const float* e = b.hop_energy + b.hop_off[clip];
         auto power = [&](int t) {
             const float acc = (t >= 1 ? e[t - 1] : 0.0f) + (t < H ? e[t] : 0.0f);
+            const float rms = sqrtf(acc / frame_length);
+            return rms * rms;
+        };
+        float m = 0.0f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) m = fmaxf(m, power(t));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) s_f[warp] = m;
+        __syncthreads();
+        m = s_f[0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_f[w]);
+        const float amin2 = 1e-10f;
+        const float ref_db = (float)(10.0 * log10(fmax(1e-10, (double)m)));
+        int first = INT_MAX, last = -1;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            const float db = 10.0f * log10f(fmaxf(amin2, power(t))) - ref_db;
+            if (db > -b.top_db) {
+                first = min(first, t);
+                last = max(last, t);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+        }
+        if (lane == 0) {
+            s_i[warp] = first;
+            s_i[8 + warp] = last;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                first = min(first, s_i[w]);
+                last = max(last, s_i[8 + w]);
+            }
+            int64_t st = 0, en = 0;
+            if (last >= 0) {
+                st = (int64_t)first * b.hop;
+                en = min((int64_t)n, (int64_t)(last + 1) * b.hop);
+            }
+            b.start_end[2 * clip] = st;
+            b.start_end[2 * clip + 1] = en;
+        }
+        __syncthreads();
+    }
+}
+
+// Same for the aligned-coordinate groups of iir_overlap4_kernel: hop block h of a clip whose first
+// sample sits at alignment slot s is {first squares e >= s of group h} + {rest of group h} +
+// {first squares e < s of group h+1}.
+struct TrimHop4Batch {
+    const float* group_energy;  // [n_groups][8] = {rest, q0, q1, q2, q3, -, -, -}
+    const int64_t* clip_off;
+    const int64_t* group_off;
+    int64_t* start_end;
+    int64_t n_clips;
+    int hop, align;
+    float top_db;
+};
+
+__global__ void __launch_bounds__(256) trim_index_hop4_kernel(const TrimHop4Batch b) {
+    __shared__ float s_f[8];
+    __shared__ int s_i[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float frame_length = (float)(2 * b.hop);
+    for (int64_t clip = blockIdx.x; clip < b.n_clips; clip += gridDim.x) {
+        const int64_t c0 = b.clip_off[clip];
+        const int n = (int)(b.clip_off[clip + 1] - c0);
+        const int s = (int)((c0 + b.align) & 3);
+        const int T = 1 + n / b.hop;
+        const int H = (n + b.hop - 1) / b.hop;
+        const int G = (int)(b.group_off[clip + 1] - b.group_off[clip]);
+        const float* ge = b.group_energy + b.group_off[clip] * 8;
+        auto block_energy = [&](int h) {
+            if (h < 0 || h >= H) return 0.0f;
+            const float* a = ge + (size_t)h * 8;
+            float e = 0.0f;
+            for (int c = s; c < 4; ++c) e += a[1 + c];
+            e += a[0];
+            if (h + 1 < G)
+                for (int c = 0; c < s; ++c) e += a[8 + 1 + c];
+            return e;
+        };
+        auto power = [&](int t) {
+            const float acc = block_energy(t - 1) + block_energy(t);
             const float rms = sqrtf(acc / frame_length);
             return rms * rms;
         };
@@ -538,6 +855,43 @@ static int run_iir_overlap(hmfe_ctx* ctx, const IirOverlapBatch& b, const double
     return HMFE_OK;
 }
 
+constexpr size_t kOverlap4Smem = (size_t)kIirWarps * 32 * kRow4 * sizeof(float) + (size_t)kIirWarps * 32 * sizeof(IirRow4);
+
+template <int S, bool BP, bool POWER>
+static int launch_overlap4_k(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
+    auto kern = iir_overlap4_kernel<S, BP, POWER>;
+    HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOverlap4Smem));
+    const unsigned grid = (unsigned)((b.n_chunks + kIirWarps * 32 - 1) / (kIirWarps * 32));
+    kern<<<grid, kIirWarps * 32, kOverlap4Smem, st>>>(b, cf);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
+template <int S>
+static int run_iir_overlap4(hmfe_ctx* ctx, const IirOverlap4Batch& b, const double* sos, bool bp, double gain, bool power,
+                            cudaStream_t st) {
+    IirCoef<S> cf;
+    for (int k = 0; k < S; ++k) {
+        cf.b0[k] = sos[6 * k + 0];
+        cf.b1[k] = sos[6 * k + 1];
+        cf.b2[k] = sos[6 * k + 2];
+        cf.a1[k] = sos[6 * k + 4];
+        cf.a2[k] = sos[6 * k + 5];
+    }
+    cf.bandpass_form = bp ? 1 : 0;
+    cf.gain = gain;
+    ctx->prof_begin(HMFE_K_IIR_OVERLAP, st);
+    int rc;
+    if (bp)
+        rc = power ? launch_overlap4_k<S, true, true>(b, cf, st) : launch_overlap4_k<S, true, false>(b, cf, st);
+    else
+        rc = power ? launch_overlap4_k<S, false, true>(b, cf, st) : launch_overlap4_k<S, false, false>(b, cf, st);
+    if (rc != HMFE_OK) return rc;
+    ctx->prof_end(st);
+    ctx->last_launches += 1;
+    return HMFE_OK;
+}
+
 struct TrimArgs {
     int frame_length, hop_length;
     float top_db;
@@ -597,25 +951,50 @@ static int iir_impl(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, i
         ctx->iir_cache_S = S;
         memcpy(ctx->iir_cache_sos, sos.data(), sizeof(double) * 6 * S);
     }
-    const int W = ctx->iir_cache_W;
+    int W = ctx->iir_cache_W;
     const bool fuse_trim = trim && trim->frame_length == 2 * trim->hop_length && trim->hop_length % 32 == 0;
-    const int unit = fuse_trim ? trim->hop_length : 800;
+    const int hop = trim ? trim->hop_length : 1;
+    // 128-bit rows need x and y32 on the same 16-byte phase and no float64 output
+    const int align = (int)((reinterpret_cast<uintptr_t>(d_x) >> 2) & 3);
+    const bool vec = d_y64 == nullptr && (reinterpret_cast<uintptr_t>(d_x) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(d_y32) & 3) == 0 &&
+                     (int)((reinterpret_cast<uintptr_t>(d_y32) >> 2) & 3) == align && ctx->iir_rows != HMFE_IIR_ROWS_SCALAR;
+    auto shift_of = [&](int64_t i) { return vec ? (int)((h_offsets[i] + align) & 3) : 0; };
+    int unit = 800;
+    if (vec) {
+        W = W > 0 ? (W + 127) / 128 * 128 : W;
+        unit = 128;
+        if (fuse_trim) {
+            int a = 128, bb = hop;  // lcm(128, hop)
+            while (bb) {
+                const int r = a % bb;
+                a = bb;
+                bb = r;
+            }
+            unit = 128 / a * hop;
+        } else {
+            unit = 3200;
+        }
+    } else if (fuse_trim) {
+        unit = hop;
+    }
     int C_overlap = 0;
     if (W > 0 && ctx->iir_algo != HMFE_IIR_ALGO_SCAN) {
-        const double slots_o = (double)ctx->sm_count * 4 * kIirWarps * 32;  // launch bounds: 4 CTAs per SM
+        const double slots_o = (double)ctx->sm_count * (vec ? 3 : 4) * kIirWarps * 32;  // CTAs per SM by launch bounds
         const double slots_e = (double)ctx->sm_count * 6 * kIirWarps * 32;
-        auto chunks_at = [&](int C) {
+        auto chunks_at = [&](int C, bool shifted) {
             int64_t c = 0;
-            for (int64_t i = 0; i < n_clips; ++i) c += (h_offsets[i + 1] - h_offsets[i] + C - 1) / C;
+            for (int64_t i = 0; i < n_clips; ++i)
+                c += (h_offsets[i + 1] - h_offsets[i] + (shifted ? shift_of(i) : 0) + C - 1) / C;
             return c;
         };
-        const double cost_exact = 2.2 * C_exact * ceil((double)chunks_at(C_exact) / slots_e) * slots_e;
+        const double cost_exact = 2.2 * C_exact * ceil((double)chunks_at(C_exact, false) / slots_e) * slots_e;
         double best = 0.0;
-        static const int mult[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40};
-        for (int m : mult) {
+        for (int m = 1; m <= 64; ++m) {
             const int C = unit * m;
-            if (C < 512 || C > 32768) continue;
-            const double cost = (double)(W + C) * ceil((double)chunks_at(C) / slots_o) * slots_o;
+            if (C < 512) continue;
+            if (C > 32768) break;
+            const double cost = (double)(W + C) * ceil((double)chunks_at(C, true) / slots_o) * slots_o;
             if (C_overlap == 0 || cost < best) {
                 best = cost;
                 C_overlap = C;
@@ -631,6 +1010,7 @@ static int iir_impl(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, i
     ctx->iir_last_algo = overlap ? HMFE_IIR_ALGO_OVERLAP : HMFE_IIR_ALGO_SCAN;
     ctx->iir_last_C = C;
     ctx->iir_last_W = overlap ? W : 0;
+    ctx->iir_last_rows = overlap && vec ? HMFE_IIR_ROWS_VECTOR : HMFE_IIR_ROWS_SCALAR;
 
     std::vector<double> M;
     if (!overlap) transition_matrix(sos.data(), S, C, M);
@@ -643,9 +1023,8 @@ static int iir_impl(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, i
     int64_t* hp = hc + (n_clips + 1);
     int64_t* hh = hp + (n_clips + 1);
     hp[0] = hh[0] = 0;
-    const int hop = trim ? trim->hop_length : 1;
     for (int64_t i = 0; i < n_clips; ++i) {
-        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        const int64_t n = h_offsets[i + 1] - h_offsets[i] + (overlap ? shift_of(i) : 0);
         hc[i] = h_offsets[i];
         hp[i + 1] = hp[i] + (n + C - 1) / C;
         hh[i + 1] = hh[i] + (power ? (n + hop - 1) / hop : 0);
@@ -659,7 +1038,46 @@ static int iir_impl(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, i
     const int64_t* d_hop_off = d_chunk_prefix + (n_clips + 1);
     const int64_t n_chunks = hp[n_clips];
 
-    if (overlap) {
+    if (overlap && vec) {
+        IirOverlap4Batch b{};
+        b.x = d_x;
+        b.y32 = d_y32;
+        b.clip_off = d_clip_off;
+        b.chunk_prefix = d_chunk_prefix;
+        b.group_off = d_hop_off;
+        b.n_clips = n_clips;
+        b.n_chunks = n_chunks;
+        b.C = C;
+        b.W = W;
+        b.hop = power ? hop : C;
+        b.align = align;
+        if (power) {
+            rc = ctx->reserve_scratch((size_t)std::max<int64_t>(1, hh[n_clips]) * 8 * sizeof(float));
+            if (rc != HMFE_OK) return rc;
+            b.group_energy = static_cast<float*>(ctx->scratch);
+        }
+        if (n_chunks > 0) {
+            switch (S) {
+                case 1: rc = run_iir_overlap4<1>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 2: rc = run_iir_overlap4<2>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 3: rc = run_iir_overlap4<3>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 4: rc = run_iir_overlap4<4>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 5: rc = run_iir_overlap4<5>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 6: rc = run_iir_overlap4<6>(ctx, b, sos.data(), bp, gain, power, st); break;
+                case 7: rc = run_iir_overlap4<7>(ctx, b, sos.data(), bp, gain, power, st); break;
+                default: rc = run_iir_overlap4<8>(ctx, b, sos.data(), bp, gain, power, st); break;
+            }
+            if (rc != HMFE_OK) return rc;
+        }
+        if (power) {
+            TrimHop4Batch tb{b.group_energy, d_clip_off, d_hop_off, trim->d_start_end, n_clips, hop, align, trim->top_db};
+            ctx->prof_begin(HMFE_K_TRIM_INDEX, st);
+            trim_index_hop4_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(tb);
+            HMFE_CHECK_CUDA(cudaGetLastError());
+            ctx->prof_end(st);
+            ctx->last_launches += 1;
+        }
+    } else if (overlap) {
         IirOverlapBatch b{};
         b.x = d_x;
         b.y32 = d_y32;
@@ -762,10 +1180,18 @@ extern "C" int hmfe_ctx_set_iir_algo(hmfe_ctx* ctx, int algo) {
     return HMFE_OK;
 }
 
-extern "C" int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup) {
+extern "C" int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup, int* rows) {
     HMFE_REQUIRE(ctx, "NULL ctx");
     if (algo) *algo = ctx->iir_last_algo;
     if (chunk) *chunk = ctx->iir_last_C;
     if (warmup) *warmup = ctx->iir_last_W;
+    if (rows) *rows = ctx->iir_last_rows;
+    return HMFE_OK;
+}
+
+extern "C" int hmfe_ctx_set_iir_rows(hmfe_ctx* ctx, int rows) {
+    HMFE_REQUIRE(ctx, "NULL ctx");
+    HMFE_REQUIRE(rows == HMFE_IIR_ROWS_AUTO || rows == HMFE_IIR_ROWS_SCALAR, "bad IIR row mode %d", rows);
+    ctx->iir_rows = rows;
     return HMFE_OK;
 }

@@ -195,11 +195,15 @@ class Context:
         """"auto" | "scan" (exact chunked scan) | "overlap" (one pass with warm-up) - include/hmfe.h."""
         check(_lib.hmfe_ctx_set_iir_algo(self._h, _lib.IIR_ALGOS[algo]), "hmfe_ctx_set_iir_algo")
 
+    def set_iir_rows(self, rows: str = "auto"):
+        """"auto" | "scalar" (force the 4-byte row variant of the overlap kernel)."""
+        check(_lib.hmfe_ctx_set_iir_rows(self._h, _lib.IIR_ROWS[rows]), "hmfe_ctx_set_iir_rows")
+
     def last_iir_plan(self) -> dict:
-        a, c, w = C.c_int(), C.c_int(), C.c_int()
-        check(_lib.hmfe_ctx_last_iir_plan(self._h, C.byref(a), C.byref(c), C.byref(w)))
+        a, c, w, r = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(_lib.hmfe_ctx_last_iir_plan(self._h, C.byref(a), C.byref(c), C.byref(w), C.byref(r)))
         return {"algo": {v: k for k, v in _lib.IIR_ALGOS.items()}.get(a.value, "none"), "chunk": c.value,
-                "warmup": w.value}
+                "warmup": w.value, "rows": {v: k for k, v in _lib.IIR_ROWS.items()}.get(r.value, "none")}
 
     def profile_ms(self) -> dict:
         """{kernel name: (total ms, launches)} since the last query (synchronises)."""

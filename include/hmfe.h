@@ -149,8 +149,15 @@ int hmfe_iir_sos_trim_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_of
 #define HMFE_IIR_ALGO_SCAN 1
 #define HMFE_IIR_ALGO_OVERLAP 2
 int hmfe_ctx_set_iir_algo(hmfe_ctx* ctx, int algo);
-/* algorithm, chunk length and warm-up length the last IIR call on this context used */
-int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup);
+/* The overlap kernel moves rows with 16-byte accesses (VECTOR) when d_x and d_y32 sit on the same
+ * 16-byte phase and no float64 output is requested, with 4-byte accesses (SCALAR) otherwise;
+ * hmfe_ctx_set_iir_rows(ctx, HMFE_IIR_ROWS_SCALAR) forces the 4-byte variant (tests). */
+#define HMFE_IIR_ROWS_AUTO 0
+#define HMFE_IIR_ROWS_SCALAR 1
+#define HMFE_IIR_ROWS_VECTOR 2
+int hmfe_ctx_set_iir_rows(hmfe_ctx* ctx, int rows);
+/* algorithm, chunk length, warm-up length and row mode the last IIR call on this context used */
+int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warmup, int* rows);
 
 /* ------------------------------------------------------------------------------------------
  * Kaldi fbank: replaces torchaudio.compliance.kaldi.fbank(w, htk_compat=True,

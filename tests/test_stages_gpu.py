@@ -117,6 +117,18 @@ def test_iir_overlap_matches_scan_and_scipy(order):
         if plan["chunk"] == Cc:
             break
     y32 = fe.iir_sos(wav, off, sos, out_dtype=torch.float32, ctx=ctx_o).cpu().numpy()
+    assert ctx_o.last_iir_plan()["rows"] == "vector", ctx_o.last_iir_plan()
+    # a source view that starts 1 element into the allocation: x and y on different 16-byte phases -> scalar rows
+    shifted = torch.empty(wav.numel() + 1, dtype=torch.float32, device="cuda")
+    shifted[1:].copy_(wav)
+    y32s = fe.iir_sos(shifted[1:], off, sos, out_dtype=torch.float32, ctx=ctx_o).cpu().numpy()
+    assert ctx_o.last_iir_plan()["rows"] == "scalar"
+    # ... and on the same (odd) phase: vector rows again, clips starting at every alignment slot
+    outs = torch.zeros(wav.numel() + 1, dtype=torch.float32, device="cuda")
+    fe.iir_sos(shifted[1:], off, sos, out=outs[1:], ctx=ctx_o)
+    assert ctx_o.last_iir_plan()["rows"] == "vector"
+    assert float(outs[0]) == 0.0  # nothing written in front of the first clip
+    assert np.abs(outs[1:].cpu().numpy() - y32).max() <= 1e-8  # other chunk boundaries: equal up to the last rounding
     ys = fe.iir_sos(wav, off, sos, out_dtype=torch.float64, ctx=ctx_s).cpu().numpy()
     assert ctx_s.last_iir_plan()["algo"] == "scan"
     # scipy's own pairing -> the general (non band-pass-form) cascade code
@@ -130,6 +142,9 @@ def test_iir_overlap_matches_scan_and_scipy(order):
         assert np.abs(y64g[seg] - ref).max() <= min(1e-4 * scale, 1e-6), (i, lens[i])
         assert np.abs(y32[seg] - ref).max() <= 1e-4 * scale, (i, lens[i])
         assert np.abs(y64[seg] - ys[seg]).max() <= 1e-10 * max(scale, 1e-3), (i, lens[i])
+        # the float32 output takes the 128-bit-row kernel: same values up to the final rounding
+        assert np.abs(y32[seg] - ys[seg]).max() <= 2e-7 * max(scale, 1e-3), (i, lens[i])
+        assert np.abs(y32s[seg] - ys[seg]).max() <= 2e-7 * max(scale, 1e-3), (i, lens[i])
 
 
 def test_iir_overlap_refused_for_slow_filters():
@@ -154,7 +169,7 @@ def test_iir_overlap_refused_for_slow_filters():
         fe.iir_sos(wav, off, sos, ctx=ctx)
 
 
-@pytest.mark.parametrize("algo", ["overlap", "scan", "auto"])
+@pytest.mark.parametrize("algo", ["overlap", "overlap-scalar", "scan", "auto"])
 def test_iir_trim_fused_indices_exact(algo):
     """hmfe_iir_sos_trim_batch: indices equal librosa.effects.trim of scipy's lfilter output."""
     from heart_murmur_detection_b200 import frontend as fe
@@ -178,11 +193,14 @@ def test_iir_trim_fused_indices_exact(algo):
         clips.append(x.astype(np.float32))
     wav, off = _batch(clips)
     ctx = fe.Context()
-    ctx.set_iir_algo(algo)
+    ctx.set_iir_algo(algo.split("-")[0])
+    if algo.endswith("scalar"):
+        ctx.set_iir_rows("scalar")
     sos = fe.butter_bandpass_sos(200, 1800, SR, 5)
     y, se = fe.iir_sos_trim(wav, off, sos, ctx=ctx)
-    if algo == "overlap":
+    if algo.startswith("overlap"):
         assert ctx.last_launches == 2  # one filter pass + the index kernel: the signal is not re-read
+        assert ctx.last_iir_plan()["rows"] == ("scalar" if algo.endswith("scalar") else "vector")
     y, se = y.cpu().numpy(), se.cpu().numpy()
     for i, x in enumerate(clips):
         ref = F.butter_bandpass_filter(x, 200, 1800, SR, 5)
