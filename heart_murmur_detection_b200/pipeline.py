@@ -154,11 +154,13 @@ def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types=
 
 
 def log_mel_features(cb: ChunkBatch, f_max=8000, n_mels=64, f_min=50, nfft=1024, hop=512, sample_rate=16000,
-                     mode="normalised") -> FeatureBatch:
+                     mode="normalised", out: torch.Tensor | None = None) -> FeatureBatch:
     plan = fe.logmel_plan(sample_rate, n_mels, f_min, f_max, nfft, hop)
     if len(cb.starts) == 0:
         return FeatureBatch(torch.empty((0, n_mels), device=cb.work.device), np.zeros(1, np.int64), cb, cb.launches)
-    out, fo = fe.logmel_views(plan, cb.work, cb.starts, cb.lengths, mode=mode)
+    if out is not None and out.numel() < int((1 + cb.lengths // hop).sum()) * n_mels:
+        out = None  # caller's buffer is too small for this batch: allocate
+    out, fo = fe.logmel_views(plan, cb.work, cb.starts, cb.lengths, mode=mode, out=out)
     return FeatureBatch(out, fo, cb, cb.launches + plan.last_launches)
 
 
@@ -182,7 +184,7 @@ def fbank_features(cb: ChunkBatch, sample_rate=16000, rows_per_chunk=0, min_samp
 
 
 def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut, max_sec,
-                        ctx=None) -> ChunkBatch:
+                        ctx=None, work=None) -> ChunkBatch:
     """Vectorised planning for get_entire_signal_librosa (one output chunk per recording): the
     same integer formulas as frontend.plan_* evaluated with numpy over the whole batch."""
     ctx = ctx or fe.default_ctx()
@@ -195,7 +197,8 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
     spare = L * (int((lens < L).sum()) + 16) if pad else 0
     frame_len = int(sample_rate / 10)
     if sos is not None:  # band-pass and the trim of the filtered signal in one call
-        work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
+        if work is None or work.numel() < total:  # a caller-provided work buffer is reused across calls
+            work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
         _, se = fe.iir_sos_trim(wav, o, sos, out=work, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     else:
         work = wav
@@ -253,17 +256,21 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
 
 
 def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
-                        pad=False, types="repeat", lowcut=200, highcut=1800, max_sec=None, f_max=8000):
-    """get_entire_signal_librosa over a batch.  Returns FeatureBatch (spectrogram=True) or ChunkBatch."""
+                        pad=False, types="repeat", lowcut=200, highcut=1800, max_sec=None, f_max=8000, work=None,
+                        out=None):
+    """get_entire_signal_librosa over a batch.  Returns FeatureBatch (spectrogram=True) or ChunkBatch.
+
+    ``work`` / ``out`` are optional pre-allocated device buffers (filtered signal + padded copies,
+    feature rows) for callers that run many batches back to back."""
     if not max_sec or max_sec >= input_sec:
         cb = _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut,
-                                 max_sec)
+                                 max_sec, work=work)
     else:  # padded-then-cut corner: generic per-clip planner
         L = int(input_sec * sample_rate)
         cb = prepare_chunks(wav, offsets, entire_signal_chunker(input_sec, sample_rate, pad, types, max_sec),
                             sample_rate=sample_rate, butterworth_filter=butterworth_filter, lowcut=lowcut,
                             highcut=highcut, pad_hint=L if pad else 0)
-    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
+    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate, out=out) if spectrogram else cb
 
 
 def split_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
@@ -334,12 +341,17 @@ def individual_segments_batch(wav, offsets, input_sec=8, sample_rate=16000, hop_
 # ----------------------------------------------------------------------------------------------
 
 
-def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, *, chunk_bytes=256 << 20,
+_host_pipes: dict = {}
+
+
+def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, *, chunk_bytes=512 << 20,
                             device=None, **kw):
     """get_entire_signal_librosa(spectrogram=True) over a batch held in (pinned) HOST memory.
 
     Sub-batches of about ``chunk_bytes`` flow through three streams - copy-in, compute,
-    copy-out - so the PCIe transfers of neighbouring sub-batches overlap the kernels.
+    copy-out - so the PCIe transfers of neighbouring sub-batches overlap the kernels.  All
+    device buffers (two sample buffers, two work buffers, two feature buffers) are allocated
+    once per device and reused across sub-batches and calls.
     Returns (h_out [sum T, 64] host tensor, row_offsets [n_chunks+1], clip_ids, valid).
     """
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -351,46 +363,70 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
         c1 = int(np.searchsorted(o, o[c0] + chunk_bytes // 4, side="right")) - 1
         bounds.append(min(n, max(c0 + 1, c1)))
     subs = list(zip(bounds[:-1], bounds[1:]))
-    max_samples = max(int(o[b] - o[a]) for a, b in subs)
-    s_in, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-    d_in = [torch.empty(max_samples, dtype=torch.float32, device=dev) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
     hop = 512
     input_sec, sr = kw.get("input_sec", 8), kw.get("sample_rate", 16000)
     L = int(input_sec * sr)
+    pad = bool(kw.get("pad", False))
+    lens = np.diff(o)
+    rows_ub = 1 + np.maximum(lens, L if pad else 0) // hop
+    max_samples = max(int(o[b] - o[a]) for a, b in subs)
+    max_work = max(int(o[b] - o[a]) + (L * (b - a + 16) if pad else 0) for a, b in subs)
+    max_rows = max(int(rows_ub[a:b].sum()) for a, b in subs)
     if h_out is None:
-        ub = int(sum(1 + max(int(x), L) // hop for x in np.diff(o)))
-        h_out = torch.empty((ub, 64), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((int(rows_ub.sum()), 64), dtype=torch.float32, pin_memory=True)
+
+    pipe = _host_pipes.get(dev)
+    if pipe is None or pipe["cap"][0] < max_samples or pipe["cap"][1] < max_work or pipe["cap"][2] < max_rows:
+        cap = (max_samples, max_work, max_rows) if pipe is None else tuple(max(x, y) for x, y in zip(pipe["cap"], (max_samples, max_work, max_rows)))
+        pipe = _host_pipes[dev] = {
+            "cap": cap,
+            # sample buffers carry the padding spare too: without a band-pass they double as the work buffer
+            "d_in": [torch.empty(cap[1], dtype=torch.float32, device=dev) for _ in range(2)],
+            "work": [torch.empty(cap[1], dtype=torch.float32, device=dev) for _ in range(2)],
+            "feat": [torch.empty((cap[2], 64), dtype=torch.float32, device=dev) for _ in range(2)],
+            "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],
+        }
+    s_in, s_cmp, s_out = pipe["streams"]
+    d_in, work, feat = pipe["d_in"], pipe["work"], pipe["feat"]
+    cur = torch.cuda.current_stream(dev)
+    for s in pipe["streams"]:
+        s.wait_stream(cur)
+    ev_in = [torch.cuda.Event() for _ in range(2)]     # sample buffer filled
+    ev_free = [torch.cuda.Event() for _ in range(2)]   # sample buffer consumed by the compute stream
+    ev_out = [torch.cuda.Event() for _ in range(2)]    # feature buffer copied out
 
     def copy_in(i):
         a, b = subs[i]
         with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[i % 2]) if i >= 2 else None
+            if i >= 2:
+                s_in.wait_event(ev_free[i % 2])
             d_in[i % 2][: int(o[b] - o[a])].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
             ev_in[i % 2].record(s_in)
 
-    row_offsets, clip_ids, valid = [0], [], np.zeros(n, dtype=bool)
-    keep_alive = []
+    row_offsets, clip_ids, valid = [np.zeros(1, np.int64)], [], np.zeros(n, dtype=bool)
+    base = 0
     copy_in(0)
     for i, (a, b) in enumerate(subs):
         if i + 1 < len(subs):
             copy_in(i + 1)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i % 2])
-            res = entire_signal_batch(d_in[i % 2][: int(o[b] - o[a])], o[a : b + 1] - o[a], spectrogram=True, **kw)
+            if i >= 2:
+                s_cmp.wait_event(ev_out[i % 2])  # feat[i % 2] still being copied out by sub-batch i - 2
+            res = entire_signal_batch(d_in[i % 2], o[a : b + 1] - o[a], spectrogram=True,
+                                      work=work[i % 2], out=feat[i % 2], **kw)
             ev_free[i % 2].record(s_cmp)
             done = torch.cuda.Event()
             done.record(s_cmp)
         rows = int(res.row_offsets[-1])
-        base = row_offsets[-1]
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
             h_out[base : base + rows].copy_(res.features[:rows], non_blocking=True)
-        keep_alive.append(res)  # features must outlive the async copy-out
-        row_offsets.extend((base + res.row_offsets[1:]).tolist())
-        clip_ids.extend((a + res.chunks.clip_ids).tolist())
+            ev_out[i % 2].record(s_out)
+        row_offsets.append(base + res.row_offsets[1:])
+        clip_ids.append(a + res.chunks.clip_ids)
         valid[a:b] = res.chunks.valid
+        base += rows
     s_out.synchronize()
     s_cmp.synchronize()
-    return h_out, np.asarray(row_offsets, dtype=np.int64), np.asarray(clip_ids, dtype=np.int64), valid
+    return h_out, np.concatenate(row_offsets), (np.concatenate(clip_ids) if clip_ids else np.zeros(0, np.int64)), valid

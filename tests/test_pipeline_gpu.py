@@ -138,3 +138,46 @@ def test_c2_pipeline_matches_oracle_per_clip():
         got = res.chunk(i).cpu().numpy()
         assert got.shape == ref.shape, (i, got.shape, ref.shape)
         assert np.abs(got - ref).max() <= 2e-4, i
+
+
+@pytest.mark.parametrize("filt", [5, None])
+def test_host_buffer_pipeline_equals_device_pipeline(filt):
+    """entire_signal_from_host (pinned host in / out, sub-batches over three streams, reused
+    device buffers) returns exactly what entire_signal_batch computes on a resident batch."""
+    from heart_murmur_detection_b200 import pipeline, synth
+
+    lens = synth.clip_lengths("c2", 60, seed=21)
+    lens[3], lens[17], lens[40] = 20000, 90000, 640000  # padded, padded, cut at max_sec
+    wav, off = synth.make_batch(lens, base_seed=500, device="cuda")
+    kw = dict(input_sec=8, butterworth_filter=filt, pad=True, types="zero", max_sec=32)
+    ref = pipeline.entire_signal_batch(wav, off, spectrogram=True, **kw)
+    rows = int(ref.row_offsets[-1])
+    h_wav = torch.empty(wav.numel(), dtype=torch.float32, pin_memory=True)
+    h_wav.copy_(wav)
+    for chunk_bytes in (8 << 20, 3 << 20, 1 << 30):  # many / more (buffers grow and are reused) / one sub-batch
+        h_out, ro, clip_ids, valid = pipeline.entire_signal_from_host(h_wav, off, chunk_bytes=chunk_bytes, **kw)
+        assert np.array_equal(ro, ref.row_offsets) and np.array_equal(clip_ids, ref.chunks.clip_ids)
+        assert np.array_equal(valid, ref.chunks.valid)
+        # sub-batching changes the IIR chunk length (warm-up boundaries): equal up to float32 rounding
+        # of the filtered samples, i.e. far below the 2e-4 budget of the normalised log-mel
+        tol = 0.0 if filt is None else 5e-5
+        assert (h_out[:rows] - ref.features[:rows].cpu()).abs().max().item() <= tol
+    # a second call with a caller-provided output buffer reuses every device buffer
+    h_out2 = torch.empty((rows, 64), dtype=torch.float32, pin_memory=True)
+    pipeline.entire_signal_from_host(h_wav, off, h_out2, chunk_bytes=8 << 20, **kw)
+    assert (h_out2 - ref.features[:rows].cpu()).abs().max().item() <= (0.0 if filt is None else 5e-5)
+
+
+def test_logmel_from_host_equals_device():
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c2", 40, seed=3)
+    wav, off = synth.make_batch(lens, base_seed=900, device="cuda")
+    plan = fe.logmel_plan(16000, 64, 50, 8000, 1024, 512)
+    ref, fo = plan(wav, off)
+    h_wav = torch.empty(wav.numel(), dtype=torch.float32, pin_memory=True)
+    h_wav.copy_(wav)
+    h_out, fo2 = fe.logmel_from_host(plan, h_wav, off, chunk_bytes=4 << 20)
+    assert np.array_equal(fo, fo2)
+    assert torch.equal(h_out, ref.cpu())
