@@ -296,25 +296,41 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
         }
         const float pmax = __uint_as_float(b.stats[2 * clip]);
         const float pmin = __uint_as_float(b.stats[2 * clip + 1]);
-        // numpy evaluates the scalar reference term in float64 and rounds once (oracle/librosa_restated.py)
-        const float ref_db = (float)(10.0 * log10(fmax((double)amin, (double)pmax)));
-        const float smax = 10.0f * log10f(fmaxf(amin, pmax)) - ref_db;
+        // 10 log10(x) = (10 / log2 10) * log2(x) on the special-function unit: ~1e-5 dB from the
+        // correctly rounded value (budget 1e-2 dB).  The reference term goes through the same
+        // formula (product rounded, then subtracted, no contraction) so that the clip maximum maps to
+        // exactly 0 dB and the normalised output spans exactly [0, 1]; an all-equal clip gives 0.
+        const float k10 = 3.01029995663981195f;
+        const float ref_db = __fmul_rn(k10, __log2f(fmaxf(amin, pmax)));
+        auto to_db = [&](float p) { return __fsub_rn(__fmul_rn(k10, __log2f(fmaxf(amin, p))), ref_db); };
+        const float smax = to_db(pmax);
         const float floor_db = smax - top_db;
-        const float smin = fmaxf(10.0f * log10f(fmaxf(amin, pmin)) - ref_db, floor_db);
+        const float smin = fmaxf(to_db(pmin), floor_db);
         const bool normalise = out_mode == HMFE_LOGMEL_OUT_NORMALISED && smax != smin;
-        const float denom = smax - smin;
+        const float denom = normalise ? smax - smin : 1.0f;
+        const float sub = normalise ? smin : 0.0f;
         float4* o4 = reinterpret_cast<float4*>(o);
         const int64_t n4 = count >> 2;
-        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-            float4 v = o4[i];
-            float* p = reinterpret_cast<float*>(&v);
+        constexpr int U = 4;  // float4 loads in flight per thread
+        for (int64_t i0 = threadIdx.x; i0 < n4; i0 += (int64_t)U * blockDim.x) {
+            float4 v[U];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float d = fmaxf(10.0f * log10f(fmaxf(amin, p[j])) - ref_db, floor_db);
-                if (normalise) d = (d - smin) / denom;
-                p[j] = d;
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                if (i < n4) v[u] = o4[i];
             }
-            o4[i] = v;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                if (i >= n4) break;
+                float* p = reinterpret_cast<float*>(&v[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = fmaxf(to_db(p[j]), floor_db);
+                    p[j] = normalise ? (d - sub) / denom : d;
+                }
+                o4[i] = v[u];
+            }
         }
     }
 }

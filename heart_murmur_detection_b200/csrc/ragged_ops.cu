@@ -145,14 +145,20 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ s
     const float* s = src + d.src_off;
     float* o = dst + d.dst_off;
     const int t1 = min(d.len, t0 + kGatherTile);
+    // position inside the repeated source: advanced by 256 per iteration instead of a division per element
+    const unsigned period = (unsigned)d.period;
+    unsigned ph = (unsigned)(((unsigned long long)d.a_phase + (unsigned)(t0 + threadIdx.x)) % period);
+    const unsigned step = 256u % period;
     for (int i = t0 + threadIdx.x; i < t1; i += 256) {
         float v = 0.0f;
         if (i < d.a_end) {
-            v = __ldg(s + (int)(((int64_t)d.a_phase + i) % d.period));
+            v = __ldg(s + ph);
         } else if (i < d.b_end) {
             v = __ldg(s + d.b_start + (i - d.a_end));
         }
         o[i] = v;
+        ph += step;
+        if (ph >= period) ph -= period;
     }
 }
 
