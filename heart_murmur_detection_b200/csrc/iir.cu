@@ -390,6 +390,25 @@ HMFE_D void iir_block32(const IirCoef<S>& cf, float* row, double (&s1)[S], doubl
     }
 }
 
+HMFE_D void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+HMFE_D void cp_async4(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+HMFE_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+HMFE_D void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// The tile of a warp is a ring of four 32-sample column blocks.  Block k of the stream is
+//   loaded   by cp.async (LDGSTS, zero fill outside the clip) four blocks ahead, 4 rows per instruction,
+//   filtered in place by the lane that owns the row,
+//   stored   row-major (STG.128, 4 rows per instruction) and its columns handed to block k + 4,
+// so the global-load latency of a block is covered by the filtering of the three blocks before it.
 template <int S, bool BP, bool POWER>
 __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const IirOverlap4Batch b, const IirCoef<S> cf) {
     extern __shared__ __align__(16) unsigned char iir_smem[];
@@ -425,140 +444,137 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
     const int hi_self = me.hi;
     const int valid_len = me.hi - b.W;  // chunk positions [0, valid_len) exist (<= 0 for idle lanes)
     const int t_end = b.W + b.C;
-    int t_first = me.hi > me.lo ? (me.lo & ~127) : t_end;
+    int t_first = me.hi > me.lo ? (me.lo & ~31) : t_end;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, d));
-    // steps in which one of this warp's rows has an edge that is not a multiple of 4
-    const int edge_lo = (me.hi > me.lo && (me.lo & 3)) ? (me.lo >> 7) : -1;
-    const int edge_hi = (me.hi > me.lo && (me.hi & 3)) ? (me.hi >> 7) : -1;
+    // 32-sample blocks in which this lane's own row has a clip edge that is not a multiple of 4
+    const int edge_lo = (me.hi > me.lo && (me.lo & 3)) ? (me.lo >> 5) : -1;
+    const int edge_hi = (me.hi > me.lo && (me.hi & 3)) ? (me.hi >> 5) : -1;
+    // the rows this lane moves in the row-major phases: 4*i + (lane >> 3), columns 4*(lane & 7) .. +3
+    const int rsub = lane >> 3, c4 = 4 * (lane & 7);
+    IirRow4 mv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mv[i] = rows[4 * i + rsub];
+
+    auto issue_load = [&](int tb) {  // stream positions [tb, tb + 32) of every row -> column block (tb >> 5) & 3
+        const int col = 32 * ((tb >> 5) & 3) + c4;
+        const int t = tb + c4;
+        const bool edge = __any_sync(0xffffffffu, edge_lo == (tb >> 5) || edge_hi == (tb >> 5));
+        if (!edge) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool in = t >= mv[i].lo && t < mv[i].hi;
+                cp_async16(&tile[4 * i + rsub][col], in ? (const void*)(b.x + mv[i].base + t) : (const void*)b.x, in ? 16 : 0);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool in = t + c >= mv[i].lo && t + c < mv[i].hi;
+                    cp_async4(&tile[4 * i + rsub][col + c], in ? (const void*)(b.x + mv[i].base + t + c) : (const void*)b.x,
+                              in ? 4 : 0);
+                }
+        }
+    };
+
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        if (t_first + 32 * k < t_end) issue_load(t_first + 32 * k);
+        cp_async_commit();
+    }
 
     float body = 0.0f, head[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q[4] = {0.0f, 0.0f, 0.0f, 0.0f}, grp = 0.0f;
     int gidx = 0, pos_in_group = 0;
-    const int tl = 4 * lane;
-    for (int t0 = t_first; t0 < t_end; t0 += 128) {
-        const int step = t0 >> 7;
-        const bool edge = __any_sync(0xffffffffu, edge_lo == step || edge_hi == step);
-        const int t = t0 + tl;
-        // ---- load phase: row r, positions t .. t+3 -> tile[r][4*lane ..]
-        if (!edge) {
-#pragma unroll
-            for (int rb = 0; rb < 32; rb += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const IirRow4 rd = rows[rb + u];
-                    v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if ((unsigned)(t - rd.lo) < (unsigned)(rd.hi - rd.lo)) {
-#ifdef HMFE_DEBUG_ALIGN
-                        if (reinterpret_cast<uintptr_t>(b.x + rd.base + t) & 15)
-                            printf("LD misaligned: row %d base %lld t %d lo %d hi %d align %d\n", rb + u, rd.base, t, rd.lo,
-                                   rd.hi, b.align);
-                        else
-#endif
-                        v[u] = __ldg(reinterpret_cast<const float4*>(b.x + rd.base + t));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(&tile[rb + u][tl]) = v[u];
-            }
-        } else {
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const IirRow4 rd = rows[r];
-                float4 v;
-                float* e = reinterpret_cast<float*>(&v);
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    e[c] = (unsigned)(t + c - rd.lo) < (unsigned)(rd.hi - rd.lo) ? __ldg(b.x + rd.base + t + c) : 0.0f;
-                *reinterpret_cast<float4*>(&tile[r][tl]) = v;
-            }
-        }
-        __syncwarp();
-        // ---- filter phase: this lane's row, 4 blocks of 32 samples
-        const bool emit = t0 >= b.W;  // warp uniform (W is a multiple of 128)
 #pragma unroll 1
-        for (int sub = 0; sub < 4; ++sub) {
-            const int tb = t0 + 32 * sub;
-            bool group_start = false;
+    for (int tb = t_first; tb < t_end; tb += 32) {
+        cp_async_wait<3>();
+        __syncwarp();
+        const int col0 = 32 * ((tb >> 5) & 3);
+        const bool emit = tb >= b.W;  // warp uniform
+        bool group_start = false;
+        if (POWER && emit) {
+            if (pos_in_group == b.hop) {  // a group is complete (warp uniform)
+                if (gidx * b.hop < valid_len) {
+                    float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
+                    dst[0] = make_float4(grp, q[0], q[1], q[2]);
+                    dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
+                }
+                ++gidx;
+                pos_in_group = 0;
+                grp = 0.0f;
+            }
+            group_start = pos_in_group == 0;
+            pos_in_group += 32;
+        }
+        // ---- filter: this lane's row
+        const int rem = hi_self - tb;
+        if (rem >= 32) {
+            body = 0.0f;
+            iir_block32<S, BP>(cf, &tile[lane][col0], s1, s2, emit, body, head);
             if (POWER && emit) {
-                if (pos_in_group == b.hop) {  // a group is complete (warp uniform)
-                    if (gidx * b.hop < valid_len) {
-                        float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
-                        dst[0] = make_float4(grp, q[0], q[1], q[2]);
-                        dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
-                    }
-                    ++gidx;
-                    pos_in_group = 0;
-                    grp = 0.0f;
-                }
-                group_start = pos_in_group == 0;
-                pos_in_group += 32;
-            }
-            const int rem = hi_self - tb;
-            if (rem >= 32) {
-                body = 0.0f;
-                iir_block32<S, BP>(cf, &tile[lane][32 * sub], s1, s2, emit, body, head);
-                if (POWER && emit) {
-                    if (group_start) {
+                if (group_start) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) q[c] = head[c];
-                    } else {
-                        body += (head[0] + head[1]) + (head[2] + head[3]);
-                    }
-                    grp += body;
+                    for (int c = 0; c < 4; ++c) q[c] = head[c];
+                } else {
+                    body += (head[0] + head[1]) + (head[2] + head[3]);
                 }
-            } else if (rem > 0) {  // the block that holds the end of the clip
-                float acc = 0.0f;
-                if (POWER && emit && group_start) q[0] = q[1] = q[2] = q[3] = 0.0f;
-#pragma unroll 1
-                for (int k = 0; k < rem; ++k) {
-                    const float f = (float)cascade<S, BP>(cf, (double)tile[lane][32 * sub + k], s1, s2);
-                    tile[lane][32 * sub + k] = f;
-                    if (POWER && emit) {
-                        if (group_start && k < 4)
-                            q[k] = f * f;
-                        else
-                            acc = fmaf(f, f, acc);
-                    }
-                }
-                grp += acc;
-            } else if (POWER && emit && group_start) {
-                q[0] = q[1] = q[2] = q[3] = 0.0f;
+                grp += body;
             }
+        } else if (rem > 0) {  // the block that holds the end of the clip
+            float acc = 0.0f;
+            if (POWER && emit && group_start) q[0] = q[1] = q[2] = q[3] = 0.0f;
+#pragma unroll 1
+            for (int k = 0; k < rem; ++k) {
+                const float f = (float)cascade<S, BP>(cf, (double)tile[lane][col0 + k], s1, s2);
+                tile[lane][col0 + k] = f;
+                if (POWER && emit) {
+                    if (group_start && k < 4) {  // (no dynamic register indexing)
+                        const float sq = f * f;
+                        if (k == 0) q[0] = sq;
+                        if (k == 1) q[1] = sq;
+                        if (k == 2) q[2] = sq;
+                        if (k == 3) q[3] = sq;
+                    } else {
+                        acc = fmaf(f, f, acc);
+                    }
+                }
+            }
+            grp += acc;
+        } else if (POWER && emit && group_start) {
+            q[0] = q[1] = q[2] = q[3] = 0.0f;
         }
         __syncwarp();
-        // ---- store phase
+        // ---- store: rows 4*i + rsub, positions tb + c4 .. + 3
         if (emit) {
+            const int t = tb + c4;
+            const bool edge = __any_sync(0xffffffffu, edge_lo == (tb >> 5) || edge_hi == (tb >> 5));
             if (!edge) {
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const IirRow4 rd = rows[r];
-                    const int olo = max(rd.lo, b.W);
-                    if (t >= olo && t < rd.hi) {
-#ifdef HMFE_DEBUG_ALIGN
-                        if (reinterpret_cast<uintptr_t>(b.y32 + rd.base + t) & 15)
-                            printf("ST misaligned: row %d base %lld t %d lo %d hi %d align %d\n", r, rd.base, t, rd.lo, rd.hi,
-                                   b.align);
-                        else
-#endif
-                        *reinterpret_cast<float4*>(b.y32 + rd.base + t) = *reinterpret_cast<const float4*>(&tile[r][tl]);
-                    }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int olo = max(mv[i].lo, b.W);
+                    if (t >= olo && t < mv[i].hi)
+                        *reinterpret_cast<float4*>(b.y32 + mv[i].base + t) =
+                            *reinterpret_cast<const float4*>(&tile[4 * i + rsub][col0 + c4]);
                 }
             } else {
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const IirRow4 rd = rows[r];
-                    const int olo = max(rd.lo, b.W);
-                    const float4 v = *reinterpret_cast<const float4*>(&tile[r][tl]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int olo = max(mv[i].lo, b.W);
+                    const float4 v = *reinterpret_cast<const float4*>(&tile[4 * i + rsub][col0 + c4]);
                     const float* e = reinterpret_cast<const float*>(&v);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        if (t + c >= olo && t + c < rd.hi) b.y32[rd.base + t + c] = e[c];
+                        if (t + c >= olo && t + c < mv[i].hi) b.y32[mv[i].base + t + c] = e[c];
                 }
             }
             __syncwarp();
         }
+        // ---- hand the column block to stream block tb + 128
+        if (tb + 128 < t_end) issue_load(tb + 128);
+        cp_async_commit();
     }
+    cp_async_wait<0>();
     if (POWER && gidx * b.hop < valid_len) {  // the last group of the chunk
         float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
         dst[0] = make_float4(grp, q[0], q[1], q[2]);
