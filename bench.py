@@ -393,7 +393,8 @@ def main():
             "config": {"workload": WORKLOADS[wl], "workload_id": wl, "clips_per_gpu_per_step": n_clips,
                        "audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
                        "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
-                       "collective": "all_gather_into_tensor(row-padded features)" if world > 1 else "none"},
+                       "collective": "all_gather_into_tensor(row-padded features)" if world > 1 else "none",
+                       **({"iir_plan": ctx.last_iir_plan()} if wl == "c2" else {})},
             "frames_per_s": world * n_frames_valid / (ms_step * 1e-3),
             "audio_seconds_per_s": world * total_samples / SR / (ms_step * 1e-3),
             "e2e": e2e,
