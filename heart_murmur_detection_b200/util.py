@@ -270,3 +270,64 @@ def get_individual_segments_librosa(
     if not spectrogram:
         return [a.astype(cb.ref_dtype(k), copy=False) for k, a in enumerate(_chunks_to_numpy(cb))]
     return [res.chunk(k).cpu().numpy().astype(cb.ref_dtype(k), copy=False) for k in range(len(cb.starts))]
+
+
+# ---------------------------------------------------------------------------------------------
+# ICBHI respiratory-cycle slicing (src/util.py:129-138, 374-422, 447-478).  Index work on the host;
+# the optional band-pass runs on the GPU and, as in the reference, makes the slices float64.
+# ---------------------------------------------------------------------------------------------
+
+
+def _slice_data_librosa(start, end, data, sample_rate):
+    """data[int(start*sr) : int(end*sr)], both ends clamped to the recording (src/util.py:129-138)."""
+    n = len(data)
+    return data[min(int(start * sample_rate), n) : min(int(end * sample_rate), n)]
+
+
+def _get_lungsound_label(crackle, wheeze, n_cls):
+    """src/util.py:447-462: 4 classes = crackle + 2 * wheeze, 2 classes = any adventitious sound."""
+    if n_cls == 4:
+        table = {(0, 0): 0, (1, 0): 1, (0, 1): 2, (1, 1): 3}
+        return table.get((crackle, wheeze))
+    if n_cls == 2:
+        return 0 if (crackle == 0 and wheeze == 0) else 1
+    return None
+
+
+def _get_diagnosis_label(disease, n_cls):
+    """src/util.py:465-478."""
+    if n_cls == 3:
+        if disease in ("COPD", "Bronchiectasis", "Asthma"):
+            return 1
+        if disease in ("URTI", "LRTI", "Pneumonia", "Bronchiolitis"):
+            return 2
+        return 0
+    if n_cls == 2:
+        return 0 if disease == "Healthy" else 1
+    return None
+
+
+def get_individual_cycles_librosa(
+    class_split,
+    recording_annotations,
+    data_folder,
+    filename,
+    sample_rate,
+    n_cls,
+    butterworth_filter=None,
+):
+    """[(audio_chunk, label), ...], one entry per annotated respiratory cycle (src/util.py:374-422).
+    ``recording_annotations`` is the pandas frame the reference builds (columns Start, End and
+    Crackles / Wheezes or Disease)."""
+    data, rate = _load(data_folder, filename, sample_rate)
+    if butterworth_filter:
+        data = _butter_bandpass_filter(data=data, lowcut=200, highcut=1800, fs=sample_rate, order=butterworth_filter)
+    sample_data = []
+    for idx in recording_annotations.index:
+        row = recording_annotations.loc[idx]
+        chunk = _slice_data_librosa(row["Start"], row["End"], data, rate)
+        if class_split == "cycle":
+            sample_data.append((chunk, _get_lungsound_label(row["Crackles"], row["Wheezes"], n_cls)))
+        elif class_split == "diagnosis":
+            sample_data.append((chunk, _get_diagnosis_label(row["Disease"], n_cls)))
+    return sample_data

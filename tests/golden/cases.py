@@ -25,6 +25,11 @@ RECORDINGS = [
 ]
 
 
+# annotated cycles for get_individual_cycles_librosa on r_long: (Start s, End s, Crackles, Wheezes, Disease)
+CYCLES = [(0.5, 2.1, 0, 1, "COPD"), (2.1, 5.037, 1, 0, "Healthy"), (5.037, 9.9, 1, 1, "URTI"), (17.0, 30.0, 0, 0, "Asthma"),
+          (25.0, 26.0, 0, 1, "LRTI")]
+
+
 def sha(arr) -> str:
     a = np.ascontiguousarray(arr)
     h = hashlib.sha256()

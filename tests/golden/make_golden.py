@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from cases import PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, digest, hash_spec, sha, sha_list  # noqa: E402
+from cases import CYCLES, PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, digest, hash_spec, sha, sha_list  # noqa: E402
 from signals import golden_signal  # noqa: E402
 
 from oracle import librosa_restated as lr  # noqa: E402
@@ -155,6 +155,21 @@ def main():
         record(f"fbank/{name}/10", ref_ef.get_split_signal_fbank("mem", name, input_sec=10))
         record(f"segments/{name}/8", ref.get_individual_segments_librosa("mem", name, input_sec=8, spectrogram=True))
         record(f"segments_audio/{name}/4", ref.get_individual_segments_librosa("mem", name, input_sec=4))
+
+    # ---- ICBHI cycle slicing (src/util.py:374-422) ----
+    import pandas as pd
+
+    ann = pd.DataFrame(CYCLES, columns=["Start", "End", "Crackles", "Wheezes", "Disease"])
+    for split, n_cls in (("cycle", 4), ("cycle", 2), ("diagnosis", 3), ("diagnosis", 2)):
+        for bw in (None, 5):
+            out = ref.get_individual_cycles_librosa(split, ann, "mem", "r_long", SR, n_cls, butterworth_filter=bw)
+            C[f"cycles/{split}/{n_cls}/{bw}"] = {
+                "labels": [lab for _, lab in out],
+                "lens": [len(a) for a, _ in out],
+                "dtypes": sorted({str(a.dtype) for a, _ in out}),
+                "sha": sha_list([a for a, _ in out]) if bw is None else None,
+                "digests": [digest(a) for a, _ in out],
+            }
 
     # trim indices straight from the shimmed call the reference makes
     for name, *_ in RECORDINGS:

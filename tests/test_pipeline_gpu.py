@@ -181,3 +181,25 @@ def test_logmel_from_host_equals_device():
     h_out, fo2 = fe.logmel_from_host(plan, h_wav, off, chunk_bytes=4 << 20)
     assert np.array_equal(fo, fo2)
     assert torch.equal(h_out, ref.cpu())
+
+
+def test_individual_cycles_match_reference(wav_dir):
+    """get_individual_cycles_librosa (src/util.py:374-422): labels, slice bounds and dtypes exact;
+    unfiltered audio bit-exact, band-passed audio (float64) within 1e-6 of scipy's lfilter."""
+    import pandas as pd
+
+    from cases import CYCLES
+    from heart_murmur_detection_b200 import util as U
+
+    ann = pd.DataFrame(CYCLES, columns=["Start", "End", "Crackles", "Wheezes", "Disease"])
+    for split, n_cls in (("cycle", 4), ("cycle", 2), ("diagnosis", 3), ("diagnosis", 2)):
+        for bw in (None, 5):
+            g = META[f"cycles/{split}/{n_cls}/{bw}"]
+            out = U.get_individual_cycles_librosa(split, ann, wav_dir, "r_long", SR, n_cls, butterworth_filter=bw)
+            assert [lab for _, lab in out] == g["labels"]
+            assert [len(a) for a, _ in out] == g["lens"]
+            assert sorted({str(a.dtype) for a, _ in out}) == g["dtypes"]
+            if bw is None:
+                assert sha_list([a for a, _ in out]) == g["sha"]
+            for (a, _), d in zip(out, g["digests"]):
+                check_digest(a, d, rtol=1e-6, atol=1e-6)
