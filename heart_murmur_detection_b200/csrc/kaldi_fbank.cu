@@ -58,6 +58,77 @@ struct FbTables {
     const int* row;
 };
 
+// Work item: 4 consecutive frames of one clip.
+struct FbItem {
+    const float* x;
+    float* o;
+    int nsamp, m, f0;
+    bool valid;
+};
+
+HMFE_D FbItem fb_locate(const FbBatch& b, const FbMeta& mm, int64_t item, int64_t it_end, int64_t& clip) {
+    FbItem c;
+    c.valid = item < it_end;
+    if (!c.valid) {
+        c.x = b.wav;
+        c.o = b.out;
+        c.nsamp = c.m = c.f0 = 0;
+        return c;
+    }
+    int64_t q;
+    if (b.uniform_items > 0) {
+        clip = item / b.uniform_items;
+        q = item - clip * b.uniform_items;
+        c.nsamp = b.uniform_n;
+        c.m = b.uniform_m;
+        c.x = b.wav + clip * (int64_t)c.nsamp;
+        c.o = b.out + clip * (int64_t)b.uniform_rows * mm.n_mels;
+    } else {
+        if (clip < 0) {
+            int64_t lo = 0, hi = b.n_clips;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (b.item_prefix[mid] <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            clip = lo;
+        }
+        while (item >= b.item_prefix[clip + 1]) ++clip;
+        q = item - b.item_prefix[clip];
+        c.nsamp = (int)b.clip_len[clip];
+        c.m = c.nsamp >= mm.win ? 1 + (c.nsamp - mm.win) / mm.shift : 0;
+        if (b.row_cap > 0) c.m = min(c.m, b.row_cap);
+        c.x = b.wav + b.clip_start[clip];
+        c.o = b.out + b.frame_off[clip] * mm.n_mels;
+    }
+    c.f0 = (int)q * 4;
+    return c;
+}
+
+// FAST (25 ms / 10 ms at 16 kHz: win 400, shift 160 = 5 * 32): the 4 frames of an item cover 880
+// consecutive samples, and sample n = lane + 32*n2 of frame t is span element lane + 32*(n2 + 5t):
+// each lane reads its 28 span samples once (prefetched one item ahead) and every frame is built
+// from those registers; the previous sample of the pre-emphasis comes from the neighbouring lane.
+constexpr int kFbSpanRegs = 28;
+
+HMFE_D void fb_load_span(const FbItem& c, int lane, float (&raw)[kFbSpanRegs]) {
+    const int base = c.f0 * 160 + lane;
+    if (c.valid && base - lane + 32 * kFbSpanRegs <= c.nsamp) {
+        const float* p = c.x + base;
+#pragma unroll
+        for (int j = 0; j < kFbSpanRegs; ++j) raw[j] = __ldg(p + 32 * j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kFbSpanRegs; ++j) {
+            const int i = base + 32 * j;
+            raw[j] = (c.valid && i < c.nsamp) ? __ldg(c.x + i) : 0.0f;
+        }
+    }
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(kFbWarps * 32, 2)
 fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -90,44 +161,65 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
     const int64_t it_end = min(b.n_items, it_begin + per_cta);
     int64_t clip = -1;
 
-    for (int64_t item = it_begin + warp; item < it_end; item += kFbWarps) {
-        int64_t q;
-        int nsamp, m;
-        const float* x;
-        float* o;
-        if (b.uniform_items > 0) {
-            clip = item / b.uniform_items;
-            q = item - clip * b.uniform_items;
-            nsamp = b.uniform_n;
-            m = b.uniform_m;
-            x = b.wav + clip * (int64_t)nsamp;
-            o = b.out + clip * (int64_t)b.uniform_rows * mm.n_mels;
-        } else {
-            if (clip < 0) {
-                int64_t lo = 0, hi = b.n_clips;
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (b.item_prefix[mid] <= item)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                clip = lo;
-            }
-            while (item >= b.item_prefix[clip + 1]) ++clip;
-            q = item - b.item_prefix[clip];
-            const int64_t c0 = b.clip_start[clip];
-            nsamp = (int)b.clip_len[clip];
-            m = nsamp >= mm.win ? 1 + (nsamp - mm.win) / mm.shift : 0;
-            if (b.row_cap > 0) m = min(m, b.row_cap);
-            x = b.wav + c0;
-            o = b.out + b.frame_off[clip] * mm.n_mels;
-        }
-        const int f0 = (int)q * 4;
+    float raw[FAST ? kFbSpanRegs : 1];
+    FbItem cur = fb_locate(b, mm, it_begin + warp, it_end, clip);
+    if constexpr (FAST) fb_load_span(cur, lane, raw);
 
-        // ---- load 4 frames: DC removal, pre-emphasis, window; pack (A = f0,f0+1 | B = f0+2,f0+3)
+    for (int64_t item = it_begin + warp; item < it_end; item += kFbWarps) {
+        const float* x = cur.x;
+        float* o = cur.o;
+        const int m = cur.m, f0 = cur.f0;
+
+        // ---- 4 frames: DC removal, pre-emphasis, window; pack (A = f0,f0+1 | B = f0+2,f0+3)
         f32x2 re[16], im[16];
-        {
+        if constexpr (FAST) {
+            // d[j] = x[i] - preemph * x[i-1] over the span (frame independent), then per frame
+            // (x[n] - mean) - preemph * (x[n-1] - mean) = d - (1 - preemph) * mean
+            float mean[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int n2 = 0; n2 < 13; ++n2)
+                    if (n2 < 12 || lane < 16) acc += raw[n2 + 5 * t];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                mean[t] = acc / 400.0f;
+            }
+            const float x0[4] = {raw[0], raw[5], raw[10], raw[15]};  // first sample of each frame (lane 0)
+            const float cm = 1.0f - mm.preemph;
+            float prev_row = 0.0f;  // raw[j-1] of this lane
+#pragma unroll
+            for (int j = 0; j < kFbSpanRegs; ++j) {
+                const float give = lane == 31 ? prev_row : raw[j];
+                const float pv = __shfl_sync(0xffffffffu, give, (lane + 31) & 31);
+                prev_row = raw[j];
+                raw[j] = fmaf(-mm.preemph, pv, raw[j]);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                float y[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float v = 0.0f;
+                    if (n2 < 13) {
+                        const float w = s_win[lane + 32 * n2];  // zero for n >= 400
+                        v = fmaf(-cm, mean[t], raw[n2 + 5 * t]);
+                        if (n2 == 0 && lane == 0) {  // replicate padding: x[-1] := x[0]
+                            const float a = x0[t] - mean[t];
+                            v = a - mm.preemph * a;
+                        }
+                        v *= w;
+                    }
+                    y[t] = v;
+                }
+                re[brev(n2, 4)] = f32x2{y[0], y[2]};
+                im[brev(n2, 4)] = f32x2{y[1], y[3]};
+            }
+            // the span of the warp's next item is fetched while this item is transformed
+            cur = fb_locate(b, mm, item + kFbWarps, it_end, clip);
+            fb_load_span(cur, lane, raw);
+        } else {
             // pass 1 over the frame: mean (DC removal); pass 2 re-reads the samples (L1 hits)
             float mean[4];
             const float* xf[4];
@@ -165,6 +257,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 re[brev(n2, 4)] = f32x2{y[0], y[2]};
                 im[brev(n2, 4)] = f32x2{y[1], y[3]};
             }
+            cur = fb_locate(b, mm, item + kFbWarps, it_end, clip);
         }
         fft_dit<16, f32x2>(re, im);
 #pragma unroll
@@ -240,6 +333,26 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
             }
         }
         __syncwarp();
+    }
+}
+
+// rows_per_clip layout: rows [m_i, rows_per_clip) of every clip are zero (the model-side pad);
+// only those rows are cleared, the frames themselves are written once by fbank_kernel.
+__global__ void __launch_bounds__(256) fbank_zero_pad_kernel(const FbBatch b, int n_mels, int win, int shift) {
+    for (int64_t clip = blockIdx.x; clip < b.n_clips; clip += gridDim.x) {
+        int m;
+        float* o;
+        if (b.uniform_items > 0) {
+            m = b.uniform_m;
+            o = b.out + clip * (int64_t)b.uniform_rows * n_mels;
+        } else {
+            const int nsamp = (int)b.clip_len[clip];
+            m = min(nsamp >= win ? 1 + (nsamp - win) / shift : 0, b.row_cap);
+            o = b.out + b.frame_off[clip] * n_mels;
+        }
+        float4* z = reinterpret_cast<float4*>(o + (int64_t)m * n_mels);
+        const int64_t n4 = (int64_t)(b.row_cap - m) * n_mels / 4;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -434,12 +547,18 @@ int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t
         if (rc != HMFE_OK) return rc;
     }
     if (rows_per_clip > 0 && total_rows > 0) {
-        HMFE_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)total_rows * p->n_mels * sizeof(float), st));
+        HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "d_out must be 16-byte aligned");
+        fbank_zero_pad_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)p->sm_count * 8), 256, 0, st>>>(b, p->n_mels, p->win,
+                                                                                                       p->shift);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        p->last_launches += 1;
     }
     if (b.n_items > 0) {
         FbMeta mm = p->meta;
         const size_t smem = p->table_smem + (size_t)kFbWarps * 32 * kXStride * sizeof(xelem<float>);
-        HMFE_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool fast = p->win == 400 && p->shift == 160;
+        auto kern = fast ? fbank_kernel<true> : fbank_kernel<false>;
+        HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t want = (b.n_items + kFbWarps - 1) / kFbWarps;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));
         FbTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
@@ -451,10 +570,10 @@ int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t
             }
             HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
         }
-        fbank_kernel<<<grid, kFbWarps * 32, smem, st>>>(b, tb, mm);
+        kern<<<grid, kFbWarps * 32, smem, st>>>(b, tb, mm);
         HMFE_CHECK_CUDA(cudaGetLastError());
         if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
-        p->last_launches = 1;
+        p->last_launches += 1;
     }
     return p->ring.release(slot, st);
 }
