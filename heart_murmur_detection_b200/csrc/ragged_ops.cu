@@ -162,11 +162,49 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ s
     }
 }
 
+// ---------------------------------------------------------------------------------- PCM16 decode
+// The sample conversion inside librosa.load / soundfile.read(dtype="float32") for 16-bit PCM WAV
+// payloads (/root/reference/src/util.py:153,222,323,391,805): x = int16 / 32768 (exact in float32).
+__global__ void __launch_bounds__(256) pcm16_decode_kernel(const int16_t* __restrict__ pcm, float* __restrict__ out,
+                                                           int64_t n, int64_t n8) {
+    const float k = 1.0f / 32768.0f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(pcm) + i);  // 8 samples
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = (float)(short)(w[j] & 0xffff) * k;
+            f[2 * j + 1] = (float)(short)(w[j] >> 16) * k;
+        }
+        float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (int64_t i = 8 * n8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)pcm[i] * k;
+}
+
 }  // namespace hmfe
 
 using namespace hmfe;
 
 extern "C" {
+
+int hmfe_pcm16_decode(const int16_t* d_pcm, int64_t n, float* d_out, void* stream) {
+    HMFE_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_pcm && d_out, "NULL device pointer");
+    // 16-byte accesses when both pointers allow it, scalar otherwise
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0;
+    const int64_t n8 = aligned ? n / 8 : 0;
+    const int64_t threads = std::max<int64_t>(1, aligned ? n8 : n);
+    const int grid = (int)std::min<int64_t>((threads + 255) / 256, (int64_t)device_sm_count() * 16);
+    pcm16_decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_pcm, d_out, n, n8);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
 
 int hmfe_ctx_create(hmfe_ctx** ctx) {
     HMFE_REQUIRE(ctx != nullptr, "ctx is NULL");

@@ -334,6 +334,21 @@ def iir_sos_trim(wav: torch.Tensor, offsets, sos: np.ndarray, out: torch.Tensor 
     return out, se
 
 
+def pcm16_to_f32(pcm: torch.Tensor, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+    """int16 CUDA samples -> float32 / 32768 (soundfile's PCM16 convention, exact)."""
+    if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()):
+        raise TypeError("pcm must be a contiguous int16 CUDA tensor (no CPU fallback)")
+    if out is None:
+        out = torch.empty(pcm.numel(), dtype=torch.float32, device=pcm.device)
+    _require_cuda_f32(out, "out")
+    if out.numel() < pcm.numel():
+        raise ValueError("out is too small")
+    with torch.cuda.device(pcm.device):
+        check(_lib.hmfe_pcm16_decode(C.c_void_p(pcm.data_ptr()), pcm.numel(), C.c_void_p(out.data_ptr()),
+                                     _stream_ptr(stream)), "hmfe_pcm16_decode")
+    return out
+
+
 def trim_indices(wav: torch.Tensor, offsets, frame_length=1600, hop_length=800, top_db=60.0, ctx: Context | None = None,
                  stream=None) -> torch.Tensor:
     """int64 CUDA tensor [n_clips, 2] of clip-relative (start, end) - ``librosa.effects.trim`` indices."""
@@ -443,6 +458,55 @@ class FbankPlan:
     def __call__(self, wav: torch.Tensor, offsets, rows_per_clip=0, out=None, stream=None):
         o = _as_offsets(offsets)
         return self.views(wav, o[:-1], np.diff(o), rows_per_clip, out, stream)
+
+
+def fbank_from_host(plan: FbankPlan, h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, rows_per_clip=0,
+                    chunk_bytes: int = 64 << 20):
+    """Host-buffer entry of the Kaldi fbank: (pinned) host samples in, (pinned) host features out.
+
+    Chunk i runs on stream i % 2 (H2D copy -> kernel -> D2H copy): the two PCIe directions and the
+    kernel of neighbouring chunks overlap.  Returns (h_out [rows, n_mels], row_offsets)."""
+    if h_wav.is_cuda or h_wav.dtype != torch.float32:
+        raise TypeError("h_wav must be a float32 host tensor")
+    o = _as_offsets(offsets)
+    n = o.size - 1
+    m = plan.num_frames(np.diff(o))
+    rows = np.full_like(m, rows_per_clip) if rows_per_clip else m
+    ro = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rows, out=ro[1:])
+    if h_out is None:
+        h_out = torch.empty((int(ro[-1]), plan.n_mels), dtype=torch.float32, pin_memory=True)
+    dev = plan.device
+    bounds = [0]
+    while bounds[-1] < n:
+        c0 = bounds[-1]
+        c1 = int(np.searchsorted(o, o[c0] + chunk_bytes // 4, side="right")) - 1
+        bounds.append(min(n, max(c0 + 1, c1)))
+    subs = list(zip(bounds[:-1], bounds[1:]))
+    max_samples = max(int(o[b] - o[a]) for a, b in subs)
+    max_rows = max(int(ro[b] - ro[a]) for a, b in subs)
+    cache = plan.__dict__.setdefault("_host_pipe", {})
+    cap = cache.get("cap", (0, 0))
+    if cap[0] < max_samples or cap[1] < max_rows:
+        cap = (max(cap[0], max_samples), max(cap[1], max_rows))
+        cache["wav"] = [torch.empty(cap[0], dtype=torch.float32, device=dev) for _ in range(2)]
+        cache["out"] = [torch.empty((cap[1], plan.n_mels), dtype=torch.float32, device=dev) for _ in range(2)]
+        cache["streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        cache["cap"] = cap
+    cur = torch.cuda.current_stream(dev)
+    for s in cache["streams"]:
+        s.wait_stream(cur)
+    for i, (a, b) in enumerate(subs):
+        s = cache["streams"][i % 2]
+        dw, do = cache["wav"][i % 2], cache["out"][i % 2]
+        ns, nr = int(o[b] - o[a]), int(ro[b] - ro[a])
+        with torch.cuda.stream(s):
+            dw[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+            plan(dw, o[a : b + 1] - o[a], rows_per_clip=rows_per_clip, out=do, stream=s)
+            h_out[int(ro[a]) : int(ro[b])].copy_(do[:nr], non_blocking=True)
+    for s in cache["streams"]:
+        s.synchronize()
+    return h_out, ro
 
 
 class ResamplePlan:

@@ -91,6 +91,13 @@ int hmfe_ctx_set_profile(hmfe_ctx* ctx, int enable);
 int hmfe_ctx_profile_ms(hmfe_ctx* ctx, double* ms_by_kernel, int* launches_by_kernel);
 
 /* ------------------------------------------------------------------------------------------
+ * PCM16 decode: the sample conversion of librosa.load / soundfile for 16-bit WAV payloads
+ * (src/util.py:153,222,323,391,805; extract_feature.py:214): d_out[i] = d_pcm[i] / 32768, exact.
+ * Lets a loader ship the 2-byte file payload over PCIe instead of 4-byte floats.
+ * ------------------------------------------------------------------------------------------ */
+int hmfe_pcm16_decode(const int16_t* d_pcm, int64_t n, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Silence trim: replaces librosa.effects.trim(y, top_db=60, frame_length=sr/10, hop_length=sr/20)
  * (src/util.py:170-172, 237-244, 338-340, 820-822; extract_feature.py:219-221).
  * Writes int64 (start, end) per clip, clip-relative, to d_start_end[n_clips][2]; (0,0) when the

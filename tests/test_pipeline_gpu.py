@@ -203,3 +203,44 @@ def test_individual_cycles_match_reference(wav_dir):
                 assert sha_list([a for a, _ in out]) == g["sha"]
             for (a, _), d in zip(out, g["digests"]):
                 check_digest(a, d, rtol=1e-6, atol=1e-6)
+
+
+def test_fbank_from_host_equals_device():
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import synth
+
+    lens = np.concatenate([synth.clip_lengths("c3", 6, seed=1), [300, 163840 + 77, 20000, 401]])
+    wav, off = synth.make_batch(lens, base_seed=40, device="cuda")
+    plan = fe.fbank_plan(sample_rate=16000)
+    h_wav = torch.empty(wav.numel(), dtype=torch.float32, pin_memory=True)
+    h_wav.copy_(wav)
+    for rows_per_clip in (0, 1024):
+        ref, ro = plan(wav, off, rows_per_clip=rows_per_clip)
+        h_out, ro2 = fe.fbank_from_host(plan, h_wav, off, rows_per_clip=rows_per_clip, chunk_bytes=1 << 20)
+        assert np.array_equal(ro, ro2)
+        assert torch.equal(h_out, ref.cpu())
+
+
+def test_pcm16_host_input_equals_decoded_float_input():
+    """16-bit PCM payload in host memory (decoded on the device) == the same samples decoded on the
+    host the way soundfile / librosa.load do (int16 / 32768), bit for bit."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import pipeline, synth
+
+    lens = synth.clip_lengths("c2", 24, seed=8)
+    wav, off = synth.make_batch(lens, base_seed=70, device="cpu")
+    pcm = torch.clamp(torch.round(wav * 32768.0), -32768, 32767).to(torch.int16)
+    decoded = (pcm.to(torch.float32) / 32768.0).contiguous()
+    for n in (0, 1, 7, 8, 9, 4097):  # vector body + scalar tail
+        d = fe.pcm16_to_f32(pcm[:n].cuda().contiguous()) if n else torch.empty(0)
+        assert torch.equal(d.cpu(), decoded[:n])
+    odd = fe.pcm16_to_f32(pcm.cuda()[1:].contiguous() if False else pcm[1:4098].cuda())  # fresh allocation: aligned
+    assert torch.equal(odd.cpu(), decoded[1:4098])
+    kw = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
+    h_pcm = pcm.pin_memory()
+    h_f32 = decoded.pin_memory()
+    a, ro_a, ids_a, valid_a = pipeline.entire_signal_from_host(h_pcm, off, chunk_bytes=16 << 20, **kw)
+    b, ro_b, ids_b, valid_b = pipeline.entire_signal_from_host(h_f32, off, chunk_bytes=16 << 20, **kw)
+    assert np.array_equal(ro_a, ro_b) and np.array_equal(ids_a, ids_b) and np.array_equal(valid_a, valid_b)
+    rows = int(ro_a[-1])
+    assert torch.equal(a[:rows], b[:rows])
