@@ -88,7 +88,7 @@ class CropDesc(C.Structure):
     """struct hmfe_crop_desc (include/hmfe.h)."""
 
     _fields_ = [("src_row", C.c_int64), ("n_rows", C.c_int32), ("spec_id", C.c_int32), ("gain", C.c_float),
-                ("reserved", C.c_int32)]
+                ("mask_off", C.c_int32)]
 
 
 hmfe_gather_batch = _sig("hmfe_gather_batch", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp)

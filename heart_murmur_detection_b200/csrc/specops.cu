@@ -48,7 +48,7 @@ spec_crop_kernel(const float* __restrict__ spec, float* __restrict__ out, const 
         float v = 0.0f;
         if (r < d.n_rows) {
             const int64_t src_row = d.src_row + r;
-            const bool masked = mask != nullptr && mask[src_row] != 0;
+            const bool masked = mask != nullptr && mask[(int64_t)d.mask_off + r] != 0;
             v = masked ? fill : __ldg(spec + src_row * n_cols + c);
             v *= d.gain;
         }
@@ -94,7 +94,8 @@ int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const h
     if (n_items == 0) return HMFE_OK;
     HMFE_REQUIRE(d_spec && d_out, "NULL device pointer");
     for (int64_t i = 0; i < n_items; ++i)
-        HMFE_REQUIRE(h_descs[i].src_row >= 0 && h_descs[i].n_rows >= 0 && h_descs[i].n_rows <= out_rows && h_descs[i].spec_id >= 0,
+        HMFE_REQUIRE(h_descs[i].src_row >= 0 && h_descs[i].n_rows >= 0 && h_descs[i].n_rows <= out_rows &&
+                         h_descs[i].spec_id >= 0 && h_descs[i].mask_off >= 0,
                      "crop descriptor %lld is inconsistent", (long long)i);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)n_items * sizeof(hmfe_crop_desc);

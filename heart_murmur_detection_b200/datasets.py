@@ -32,29 +32,44 @@ class SpecStore:
         self.data = torch.cat([torch.as_tensor(np.asarray(s), dtype=torch.float32) for s in specs]).to(dev).contiguous()
         self.means = fe.spec_means(self.data, self.row_offsets)
 
+    @classmethod
+    def from_features(cls, features: torch.Tensor, row_offsets):
+        """Wrap spectrograms that are already on the GPU (a pipeline.FeatureBatch): the on-the-fly
+        form of producer + Dataset (heart_pressl.py:58-99 followed by cola_training.py:56-80) with no
+        .npy round trip.  Whole-recording normalisation is preserved because the rows come from
+        the whole-recording log-mel."""
+        self = cls.__new__(cls)
+        self.row_offsets = np.ascontiguousarray(row_offsets, dtype=np.int64)
+        self.n_cols = int(features.shape[1])
+        self.data = features[: int(self.row_offsets[-1])].contiguous()
+        self.means = fe.spec_means(self.data, self.row_offsets)
+        return self
+
     def rows(self, i):
         return int(self.row_offsets[i + 1] - self.row_offsets[i])
 
 
 def cola_batch(store: SpecStore, indices, max_len=251, augment=True):
     """AudioDataset.__getitem__ (method='cola') for a batch of item indices.
-    Returns (x1, x2): float32 CUDA tensors [B, max_len, n_cols]."""
-    total_rows = int(store.row_offsets[-1])
-    mask = np.zeros(total_rows, dtype=np.uint8) if augment else None
+    Returns (x1, x2): float32 CUDA tensors [B, max_len, n_cols].  An index may appear several
+    times in one batch: every occurrence gets its own mask, crops and gains, as in the reference."""
+    masks, mask_base = [], 0
     d1 = np.zeros(len(indices), dtype=fe.CROP_DTYPE)
     d2 = np.zeros(len(indices), dtype=fe.CROP_DTYPE)
     for k, idx in enumerate(indices):
         r0, T = int(store.row_offsets[idx]), store.rows(idx)
         if augment:
-            mask[r0 : r0 + T] = draw_mask_rows(T)  # masks are per draw: items repeated in one batch share rows
+            masks.append(draw_mask_rows(T))  # one fresh mask per item, shared by its two crops
         s1 = int(random.random() * (T - max_len))
         s2 = int(random.random() * (T - max_len))
         g1 = 0.9 + random.random() / 5.0 if augment else 1.0
         g2 = 0.9 + random.random() / 5.0 if augment else 1.0
         n = min(max_len, T)
-        d1[k] = (r0 + max(s1, 0), min(n, T - max(s1, 0)), idx, np.float32(g1), 0)
-        d2[k] = (r0 + max(s2, 0), min(n, T - max(s2, 0)), idx, np.float32(g2), 0)
-    dmask = torch.from_numpy(mask).to(store.data.device) if augment else None
+        s1, s2 = max(s1, 0), max(s2, 0)
+        d1[k] = (r0 + s1, min(n, T - s1), idx, np.float32(g1), mask_base + s1)
+        d2[k] = (r0 + s2, min(n, T - s2), idx, np.float32(g2), mask_base + s2)
+        mask_base += T if augment else 0
+    dmask = torch.from_numpy(np.concatenate(masks)).to(store.data.device) if augment and masks else None
     means = store.means if augment else None
     x1 = fe.spec_crop(store.data, d1, max_len, dmask, means)
     x2 = fe.spec_crop(store.data, d2, max_len, dmask, means)

@@ -372,7 +372,7 @@ GATHER_DTYPE = np.dtype(
 )
 assert GATHER_DTYPE.itemsize == C.sizeof(_lib.GatherDesc)
 
-CROP_DTYPE = np.dtype([("src_row", "<i8"), ("n_rows", "<i4"), ("spec_id", "<i4"), ("gain", "<f4"), ("reserved", "<i4")])
+CROP_DTYPE = np.dtype([("src_row", "<i8"), ("n_rows", "<i4"), ("spec_id", "<i4"), ("gain", "<f4"), ("mask_off", "<i4")])
 assert CROP_DTYPE.itemsize == C.sizeof(_lib.CropDesc)
 
 

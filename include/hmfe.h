@@ -214,16 +214,17 @@ int hmfe_resample_last_launches(const hmfe_resample_plan* plan);
  * mae_training.py:88-109, audioMAE/models_mae.py:1178-1181).  Random draws happen on the host
  * in the reference's order; the kernels apply them.
  * d_spec is a ragged batch of spectrograms [sum T_i, n_cols] with int64 row offsets.
- * Output item k = rows [src_row, src_row + n_rows) of d_spec (global row index), rows whose
- * d_row_mask byte is non-zero replaced by the mean of spectrogram spec_id, everything times
- * gain, zero padded to out_rows:  d_out[n_items][out_rows][n_cols].
+ * Output item k = rows [src_row, src_row + n_rows) of d_spec (global row index); row r of the item
+ * is replaced by the mean of spectrogram spec_id when d_row_mask[mask_off + r] is non-zero (every
+ * item owns its slice of the mask: the reference draws a fresh mask per __getitem__), everything
+ * times gain, zero padded to out_rows:  d_out[n_items][out_rows][n_cols].
  * ------------------------------------------------------------------------------------------ */
 typedef struct hmfe_crop_desc {
     int64_t src_row;
     int32_t n_rows;
     int32_t spec_id;
     float gain;
-    int32_t reserved;
+    int32_t mask_off; /* first byte of this item's rows in d_row_mask (ignored without a mask) */
 } hmfe_crop_desc;
 int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_row_offsets, int64_t n_specs, int n_cols,
                          float* d_mean, void* stream);

@@ -244,3 +244,38 @@ def test_pcm16_host_input_equals_decoded_float_input():
     assert np.array_equal(ro_a, ro_b) and np.array_equal(ids_a, ids_b) and np.array_equal(valid_a, valid_b)
     rows = int(ro_a[-1])
     assert torch.equal(a[:rows], b[:rows])
+
+
+def test_c4_cola_pairs_on_the_fly_match_oracle():
+    """BASELINE config 4: recordings -> whole-recording log-mel (get_entire_signal_librosa,
+    heart_pressl.py:76-81) -> COLA item = random_mask, two random_crops, two random_multiplies
+    (cola_training.py:56-80), all on the GPU with host-drawn random numbers.  Crop starts and
+    masked rows are exact (same Python RNG stream), values within the log-mel tolerance."""
+    from heart_murmur_detection_b200 import datasets, pipeline, synth
+    from oracle import frontend as F
+
+    lens = synth.clip_lengths("c4", 6, seed=11)
+    lens[2] = 7 * SR  # shorter than input_sec: the producer drops it ("audio too short")
+    wav, off = synth.make_batch(lens, base_seed=4400, device="cuda")
+    fb = pipeline.entire_signal_batch(wav, off, input_sec=8, spectrogram=True)
+    assert list(fb.chunks.valid) == [True, True, False, True, True, True]
+    store = datasets.SpecStore.from_features(fb.features, fb.row_offsets)
+    host = wav.cpu().numpy()
+    specs = [F.entire_signal(host[off[i] : off[i + 1]], input_sec=8, spectrogram=True) for i in range(len(lens))]
+    specs = [s for s in specs if s is not None]
+    assert len(specs) == 5 and [s.shape[0] for s in specs] == [store.rows(i) for i in range(5)]
+    items = [3, 0, 4, 1, 2, 0]
+    random.seed(2024)
+    x1, x2 = datasets.cola_batch(store, items, max_len=251, augment=True)
+    state_after = random.getstate()
+    random.seed(2024)
+    for k, idx in enumerate(items):
+        x = F.random_mask(specs[idx])
+        r1 = F.random_crop(x, crop_size=251)
+        r2 = F.random_crop(x, crop_size=251)
+        r1, r2 = F.random_multiply(r1), F.random_multiply(r2)
+        for got, ref in ((x1[k], r1), (x2[k], r2)):
+            got = got.cpu().numpy()
+            assert got.shape == (251, 64)
+            assert np.abs(got[: ref.shape[0]] - ref).max() <= 3e-4
+    assert random.getstate() == state_after  # the same number of draws was consumed

@@ -48,6 +48,57 @@ __global__ void k_ffma2(float* out, int iters, float s) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// packed FMA whose three operands are all different register pairs (the FFT butterflies look like
+// this; the kernels above reuse two constant operands, which the operand-reuse cache serves)
+template <int ILP>
+__global__ void k_ffma2_distinct(float* out, int iters) {
+    unsigned long long a[ILP], b[ILP], c[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        float2 va = make_float2(1.0f + threadIdx.x * 1e-6f + i * 1e-3f, 1.0f - i * 1e-3f);
+        float2 vb = make_float2(0.999f + i * 1e-4f, 1.001f - i * 1e-4f);
+        float2 vc = make_float2(i * 0.5f, threadIdx.x * 0.25f);
+        a[i] = *reinterpret_cast<unsigned long long*>(&va);
+        b[i] = *reinterpret_cast<unsigned long long*>(&vb);
+        c[i] = *reinterpret_cast<unsigned long long*>(&vc);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) c[i] = fma2(a[i], b[(i + 1) % ILP], c[i]);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) a[i] = fma2(c[i], b[i], a[(i + 3) % ILP]);
+    }
+    float r = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        float2 v = *reinterpret_cast<float2*>(&a[i]);
+        float2 w = *reinterpret_cast<float2*>(&c[i]);
+        r += v.x + v.y + w.x + w.y;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int ILP>
+__global__ void k_ffma_distinct(float* out, int iters) {
+    float a[ILP], b[ILP], c[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        a[i] = 1.0f + threadIdx.x * 1e-6f + i * 1e-3f;
+        b[i] = 0.999f + i * 1e-4f;
+        c[i] = i * 0.5f;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) c[i] = fmaf(a[i], b[(i + 1) % ILP], c[i]);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) a[i] = fmaf(c[i], b[i], a[(i + 3) % ILP]);
+    }
+    float r = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) r += a[i] + c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 // mixed: FFMA2 interleaved with shuffles (issue-slot sharing)
 template <int ILP>
 __global__ void k_shfl(float* out, int iters) {
@@ -108,6 +159,13 @@ int main() {
     printf(", \"ffma_tflops\": %.2f, \"ffma_warp_instr_per_ns\": %.2f", 2 * n_thread_ops / ms * 1e-9, n_thread_ops / 32 / ms * 1e-6);
     ms = time_ms([&] { k_ffma2<ILP><<<blocks, threads>>>(out, iters, 0.999f); });
     printf(", \"ffma2_tflops\": %.2f, \"ffma2_warp_instr_per_ns\": %.2f", 4 * n_thread_ops / ms * 1e-9, n_thread_ops / 32 / ms * 1e-6);
+    for (int w : {1, 2, 3, 4, 8}) {  // warps per scheduler: 128 * w threads per SM (one CTA per SM)
+        const double ops = (double)sms * 128 * w * iters * 16 * 2;  // 2 x ILP(16) instructions per iteration
+        ms = time_ms([&] { k_ffma2_distinct<16><<<sms, 128 * w>>>(out, iters); });
+        printf(", \"ffma2_distinct_w%d_tflops\": %.2f", w, 4 * ops / ms * 1e-9);
+        ms = time_ms([&] { k_ffma_distinct<16><<<sms, 128 * w>>>(out, iters); });
+        printf(", \"ffma_distinct_w%d_tflops\": %.2f", w, 2 * ops / ms * 1e-9);
+    }
     ms = time_ms([&] { k_shfl<ILP><<<blocks, threads>>>(out, iters / 4); });
     printf(", \"shfl_warp_instr_per_ns\": %.2f", n_thread_ops / 4 / 32 / ms * 1e-6);
     double* dout;
