@@ -179,6 +179,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, kernel, n_clips):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full
+    capture (profiles/*_traffic.json, written by tools/make_profiles.py); None when the capture was taken at
+    another batch size."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            rec = json.load(open(path)).get(workload, {}).get(kernel)
+        except Exception:
+            continue
+        if rec and int(rec.get("clips_per_launch", -1)) == int(n_clips):
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), os.path.basename(path)
+    return None, None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -428,8 +444,10 @@ def main():
         dom_s = per_launch[dom] * 1e-3
         achieved = alg.get(dom, 0) / dom_s / 1e9
         step_kernel_ms = sum(v[0] for v in kern.values()) / args.steps
+        traffic, traffic_src = measured_traffic(wl, dom, n_clips)
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": dom, "kernel_ms": per_launch[dom],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": dom,
+                "kernel_ms": per_launch[dom],
                 "algorithmic_bytes_per_launch": alg.get(dom),
                 "kernels_ms_per_launch": {k: round(v, 4) for k, v in sorted(per_launch.items())},
                 "kernels_gbs": {k: round(alg[k] / (per_launch[k] * 1e-3) / 1e9, 1) for k in per_launch if k in alg},

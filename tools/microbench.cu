@@ -159,7 +159,7 @@ int main() {
     printf(", \"ffma_tflops\": %.2f, \"ffma_warp_instr_per_ns\": %.2f", 2 * n_thread_ops / ms * 1e-9, n_thread_ops / 32 / ms * 1e-6);
     ms = time_ms([&] { k_ffma2<ILP><<<blocks, threads>>>(out, iters, 0.999f); });
     printf(", \"ffma2_tflops\": %.2f, \"ffma2_warp_instr_per_ns\": %.2f", 4 * n_thread_ops / ms * 1e-9, n_thread_ops / 32 / ms * 1e-6);
-    for (int w : {1, 2, 3, 4, 8}) {  // warps per scheduler: 128 * w threads per SM (one CTA per SM)
+    for (int w : {1, 2, 3, 4}) {  // warps per scheduler: 128 * w threads per SM (one CTA per SM)
         const double ops = (double)sms * 128 * w * iters * 16 * 2;  // 2 x ILP(16) instructions per iteration
         ms = time_ms([&] { k_ffma2_distinct<16><<<sms, 128 * w>>>(out, iters); });
         printf(", \"ffma2_distinct_w%d_tflops\": %.2f", w, 4 * ops / ms * 1e-9);
