@@ -30,6 +30,7 @@ struct LogmelBatch {
     const int64_t* frame_off;    // [n_clips+1] ragged only
     const int64_t* item_prefix;  // [n_clips+1] ragged only
     unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
+    unsigned long long* queue;   // next unclaimed work item (dynamic distribution over the warps)
     int64_t n_clips, n_items;
     int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
     int hop;
@@ -77,8 +78,9 @@ HMFE_D ItemCtx locate_item(const LogmelBatch& b, int n_mels, int64_t item, int64
         c.x = b.wav + clip * (int64_t)c.nsamp;
         c.o = b.out + clip * (int64_t)c.T * n_mels;
     } else {
-        if (clip < 0) {  // first item of this warp: binary search, largest c with prefix[c] <= item
-            int64_t lo = 0, hi = b.n_clips;
+        if (clip < 0 || item >= b.item_prefix[min(clip + 4, b.n_clips)]) {
+            // first item of this warp, or a jump to a far block: binary search, largest c with prefix[c] <= item
+            int64_t lo = max(clip, (int64_t)0), hi = b.n_clips;
             while (hi - lo > 1) {
                 const int64_t mid = (lo + hi) >> 1;
                 if (b.item_prefix[mid] <= item)
@@ -176,18 +178,35 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_mels = mm.n_mels;
     const int n_slots = NSLOTS > 0 ? NSLOTS : mm.n_slots;
-    const int64_t per_cta = (b.n_items + gridDim.x - 1) / gridDim.x;
-    const int64_t it_begin = (int64_t)blockIdx.x * per_cta;
-    const int64_t it_end = min(b.n_items, it_begin + per_cta);
+    // Work items are claimed in blocks of kItemBlock consecutive items per warp from a global counter:
+    // warps that start late (SMs shared with a concurrent collective kernel) or hit long clips simply
+    // claim fewer blocks, instead of holding a fixed 1/grid share of the batch.
+    constexpr int kItemBlock = 8;
+    const int64_t it_end = b.n_items;
+    auto claim = [&]() -> int64_t {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
+        return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    };
+    int64_t blk_end = 0;
+    auto next_item = [&](int64_t item) -> int64_t {  // item following `item` for this warp
+        if (item + 1 < blk_end) return item + 1;
+        if (item >= it_end) return item;  // drained: no further claims
+        const int64_t nb = claim();
+        blk_end = nb + kItemBlock;
+        return nb;
+    };
     int64_t clip_cursor = -1;
 
     // software pipeline: the samples of item i+WARPS are fetched into registers while the mel
     // projection of item i runs (the FFT registers are dead by then)
     float raw[NV][2][32];
-    ItemCtx cur = locate_item<FR>(b, n_mels, it_begin + warp, it_end, clip_cursor);
+    int64_t item = claim();
+    blk_end = item + kItemBlock;
+    ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
     load_raw<NV>(cur, b.hop, lane, raw);
 
-    for (int64_t item = it_begin + warp; item < it_end; item += WARPS) {
+    while (item < it_end) {
         V re[32], im[32];
 #pragma unroll
         for (int n2 = 0; n2 < 32; ++n2) {
@@ -229,7 +248,8 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
         }
         __syncwarp();
 
-        const ItemCtx nxt = locate_item<FR>(b, n_mels, item + WARPS, it_end, clip_cursor);
+        item = next_item(item);
+        const ItemCtx nxt = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
         load_raw<NV>(nxt, b.hop, lane, raw);
 
         float vmax = 0.0f, vmin = INFINITY;
@@ -272,8 +292,9 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     }
 }
 
-__global__ void logmel_init_stats_kernel(unsigned* stats, int64_t n_clips) {
+__global__ void logmel_init_stats_kernel(unsigned* stats, int64_t n_clips, unsigned long long* queue) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *queue = 0ull;
     if (i < n_clips) {
         stats[2 * i] = 0u;
         stats[2 * i + 1] = 0x7f800000u;  // +inf
@@ -518,7 +539,8 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64
     b.n_clips = n_clips;
     b.hop = p->hop;
     const size_t desc_bytes = uniform ? 0 : (4 * (size_t)n_clips + 2) * sizeof(int64_t);
-    const size_t total_bytes = desc_bytes + (size_t)n_clips * 2 * sizeof(unsigned);
+    const size_t stats_bytes = ((size_t)n_clips * 2 * sizeof(unsigned) + 15) & ~(size_t)15;
+    const size_t total_bytes = desc_bytes + stats_bytes + 16;
     void *hbuf = nullptr, *dbuf = nullptr;
     const int slot = p->ring.acquire(total_bytes, &hbuf, &dbuf);
     if (slot < 0) return slot;
@@ -551,8 +573,9 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64
         if (rc != HMFE_OK) return rc;
     }
     b.stats = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dbuf) + desc_bytes);
+    b.queue = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(dbuf) + desc_bytes + stats_bytes);
 
-    logmel_init_stats_kernel<<<(unsigned)((n_clips + 255) / 256), 256, 0, st>>>(b.stats, n_clips);
+    logmel_init_stats_kernel<<<(unsigned)((n_clips + 255) / 256), 256, 0, st>>>(b.stats, n_clips, b.queue);
     HMFE_CHECK_CUDA(cudaGetLastError());
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (p->profile) {
