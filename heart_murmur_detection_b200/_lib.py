@@ -142,6 +142,12 @@ hmfe_spec_crop_batch = _sig(
 )
 
 
+hmfe_htsat_input_batch = _sig(
+    "hmfe_htsat_input_batch", C.c_int, c_voidp, c_voidp, C.c_int, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp, C.c_int,
+    c_voidp, c_voidp,
+)
+
+
 def check(rc: int, what: str = "hmfe call"):
     if rc != 0:
         raise HmfeError(f"{what} failed (rc={rc}): {hmfe_last_error().decode(errors='replace')}")

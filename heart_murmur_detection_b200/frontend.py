@@ -641,6 +641,30 @@ def spec_crop(spec: torch.Tensor, descs: np.ndarray, out_rows: int, row_mask: to
     return out
 
 
+def htsat_input(spec: torch.Tensor, src_rows, n_rows, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-5, spec_size=256,
+                ctx: Context | None = None, stream=None) -> torch.Tensor:
+    """HTS-AT input stage (htsat.py:889-891 bn0 in inference form, :829-858 reshape_wav2img) for items
+    ``spec[src_rows[i] : src_rows[i] + n_rows[i]]``.  Returns ``[n_items, 1, spec_size, spec_size]``."""
+    _require_cuda_f32(spec, "spec")
+    rows = np.ascontiguousarray(src_rows, dtype=np.int64)
+    cnt = np.ascontiguousarray(n_rows, dtype=np.int32)
+    w, bb = np.asarray(bn_weight, dtype=np.float32), np.asarray(bn_bias, dtype=np.float32)
+    mu, var = np.asarray(bn_mean, dtype=np.float32), np.asarray(bn_var, dtype=np.float32)
+    scale = (w / np.sqrt(var + np.float32(eps))).astype(np.float32)  # float32 like torch's batch_norm
+    shift = (bb - mu * scale).astype(np.float32)
+    ctx = ctx or default_ctx()
+    out = torch.empty((rows.size, 1, int(spec_size), int(spec_size)), dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        check(
+            _lib.hmfe_htsat_input_batch(ctx._h, C.c_void_p(spec.data_ptr()), int(spec.shape[-1]),
+                                        rows.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), rows.size,
+                                        scale.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p), int(spec_size),
+                                        C.c_void_p(out.data_ptr()), _stream_ptr(stream)),
+            "hmfe_htsat_input_batch",
+        )
+    return out
+
+
 # =============================================================================================
 # Host index planners - integer work, bit-exact with the reference
 # (src/util.py:504-620, 257-259; extract_feature.py:250-259).  A chunk is either a straight

@@ -137,8 +137,10 @@ def entire_signal_chunker(input_sec=8, sample_rate=16000, pad=False, types="repe
     return chunker
 
 
-def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types="repeat"):
-    """get_split_signal_librosa / get_split_signal_fbank_pad after the trim (src/util.py:348-354)."""
+def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types="repeat", first_only=False):
+    """get_split_signal_librosa / get_split_signal_fbank_pad after the trim (src/util.py:348-354).
+    ``first_only`` keeps chunk 0 only - what the cache writers take with ``[...][0]``
+    (finetuning.py:973-975, 1126-1133; heart_pressl.py:35-37)."""
 
     def chunker(n):
         if n == 0:
@@ -148,7 +150,7 @@ def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types=
         duration = n / sample_rate
         if trim_tail and duration > input_sec and (duration % input_sec) * 2 < input_sec:  # decide_droplast
             chunks.pop()
-        return chunks
+        return chunks[:1] if first_only else chunks
 
     return chunker
 
@@ -274,18 +276,20 @@ def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterwort
 
 
 def split_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
-                       trim_tail=False, lowcut=200, highcut=1800, f_max=8000):
+                       trim_tail=False, lowcut=200, highcut=1800, f_max=8000, first_only=False):
     """get_split_signal_librosa over a batch."""
-    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail), sample_rate=sample_rate,
+    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail, first_only=first_only),
+                        sample_rate=sample_rate,
                         butterworth_filter=butterworth_filter, lowcut=lowcut, highcut=highcut,
                         pad_hint=int(input_sec * sample_rate))
     return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
 
 
 def split_signal_fbank_pad_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None,
-                                 spectrogram=False, trim_tail=False, rows_per_chunk=0):
+                                 spectrogram=False, trim_tail=False, rows_per_chunk=0, first_only=False):
     """get_split_signal_fbank_pad over a batch."""
-    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail), sample_rate=sample_rate,
+    cb = prepare_chunks(wav, offsets, split_signal_chunker(input_sec, sample_rate, trim_tail, first_only=first_only),
+                        sample_rate=sample_rate,
                         butterworth_filter=butterworth_filter, lowcut=200, highcut=1800,
                         pad_hint=int(input_sec * sample_rate))
     return fbank_features(cb, sample_rate, rows_per_chunk) if spectrogram else cb

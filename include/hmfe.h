@@ -231,6 +231,18 @@ int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_ro
 int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const hmfe_crop_desc* h_descs, int64_t n_items,
                          const uint8_t* d_row_mask, const float* d_mean, float* d_out, int out_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HTS-AT input stage (the first thing the OPERA-CT encoder does to the log-mel; src/model/htsat/
+ * htsat.py:889-891 bn0 in inference form, :829-858 reshape_wav2img): per mel bin y = x*scale+shift,
+ * bicubic (align_corners) resize of the time axis to spec_size*ratio frames (ratio = spec_size /
+ * n_cols; no resize for full-length items), fold to d_out[n_items][spec_size][spec_size] with
+ * out[n*n_cols + f][t'] = y[n*(spec_size) + t'][f].  Item i = rows [h_src_row[i], +h_n_rows[i]) of
+ * d_spec [rows][n_cols].  n_cols must be 64.
+ * ------------------------------------------------------------------------------------------ */
+int hmfe_htsat_input_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const int64_t* h_src_row,
+                           const int32_t* h_n_rows, int64_t n_items, const float* h_scale, const float* h_shift,
+                           int spec_size, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

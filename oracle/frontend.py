@@ -348,3 +348,29 @@ def resample_torchaudio(wave, orig_sr, new_sr):
 
     w = torch.as_tensor(np.asarray(wave, dtype=np.float32))
     return torchaudio.functional.resample(w, int(orig_sr), int(new_sr)).numpy()
+
+
+def htsat_input(x, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-5, spec_size=256):
+    """src/model/htsat/htsat.py:889-891 (bn0, inference) + :829-858 (reshape_wav2img) on one
+    spectrogram ``x [T, F]`` -> ``[spec_size, spec_size]`` (torch CPU ops, the library the reference calls)."""
+    import torch
+
+    x = torch.as_tensor(np.asarray(x, dtype=np.float32))[None, None]  # B C T F
+    F_ = x.shape[3]
+    bn = torch.nn.BatchNorm2d(F_, eps=eps)
+    with torch.no_grad():
+        bn.weight.copy_(torch.as_tensor(np.asarray(bn_weight, dtype=np.float32)))
+        bn.bias.copy_(torch.as_tensor(np.asarray(bn_bias, dtype=np.float32)))
+        bn.running_mean.copy_(torch.as_tensor(np.asarray(bn_mean, dtype=np.float32)))
+        bn.running_var.copy_(torch.as_tensor(np.asarray(bn_var, dtype=np.float32)))
+    bn.eval()
+    with torch.no_grad():
+        x = bn(x.transpose(1, 3)).transpose(1, 3)
+        ratio = spec_size // F_
+        target_T = spec_size * ratio
+        if x.shape[2] < target_T:
+            x = torch.nn.functional.interpolate(x, (target_T, F_), mode="bicubic", align_corners=True)
+        x = x.permute(0, 1, 3, 2).contiguous()
+        x = x.reshape(1, 1, F_, ratio, target_T // ratio).permute(0, 1, 3, 2, 4).contiguous()
+        x = x.reshape(1, 1, ratio * F_, target_T // ratio)
+    return x[0, 0].numpy()

@@ -30,6 +30,19 @@ CYCLES = [(0.5, 2.1, 0, 1, "COPD"), (2.1, 5.037, 1, 0, "Healthy"), (5.037, 9.9, 
           (25.0, 26.0, 0, 1, "LRTI")]
 
 
+# HTS-AT input stage: spectrogram lengths (frames) and the deterministic BatchNorm parameters used for the fixtures
+HTSAT_T = [251, 256, 63, 1001, 1024, 1, 4]
+
+
+def htsat_bn_params(F=64):
+    k = np.arange(F, dtype=np.float64)
+    weight = (0.75 + 0.5 * ((k * 37) % 64) / 64).astype(np.float32)
+    bias = (-0.25 + 0.5 * ((k * 11) % 64) / 64).astype(np.float32)
+    mean = (0.2 + 0.4 * ((k * 23) % 64) / 64).astype(np.float32)
+    var = (0.02 + 0.1 * ((k * 5) % 64) / 64).astype(np.float32)
+    return weight, bias, mean, var
+
+
 def sha(arr) -> str:
     a = np.ascontiguousarray(arr)
     h = hashlib.sha256()

@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from cases import CYCLES, PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, digest, hash_spec, sha, sha_list  # noqa: E402
+from cases import (CYCLES, HTSAT_T, PAD_SPLIT_LENGTHS, PAD_SPLIT_SECS, RECORDINGS, SR, digest, hash_spec,  # noqa: E402
+                   htsat_bn_params, sha, sha_list)
 from signals import golden_signal  # noqa: E402
 
 from oracle import librosa_restated as lr  # noqa: E402
@@ -47,9 +48,14 @@ def install_shims(store):
         return store[key].copy(), sr
 
     sys.modules["librosa"] = lr.as_librosa_module(load)
-    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "opensmile"):
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "opensmile", "torchlibrosa", "torchlibrosa.augmentation",
+                 "torchlibrosa.stft"):
         sys.modules[name] = types.ModuleType(name)
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    # src/model/htsat/htsat.py imports these at module level; reshape_wav2img / bn0 do not use them
+    sys.modules["torchlibrosa.augmentation"].SpecAugmentation = object
+    sys.modules["torchlibrosa.stft"].LogmelFilterBank = object
+    sys.modules["torchlibrosa.stft"].Spectrogram = object
     sys.path.insert(0, REFERENCE)
 
 
@@ -170,6 +176,27 @@ def main():
                 "sha": sha_list([a for a, _ in out]) if bw is None else None,
                 "digests": [digest(a) for a, _ in out],
             }
+
+    # ---- HTS-AT input stage (src/model/htsat/htsat.py:889-891 bn0 + :829-858 reshape_wav2img, executed) ----
+    import torch
+
+    import src.model.htsat.htsat as ref_htsat
+
+    weight, bias, mean, var = htsat_bn_params(64)
+    bn0 = torch.nn.BatchNorm2d(64)
+    with torch.no_grad():
+        bn0.weight.copy_(torch.from_numpy(weight))
+        bn0.bias.copy_(torch.from_numpy(bias))
+        bn0.running_mean.copy_(torch.from_numpy(mean))
+        bn0.running_var.copy_(torch.from_numpy(var))
+    bn0.eval()
+    self_like = types.SimpleNamespace(spec_size=256, freq_ratio=4)
+    for T in HTSAT_T:
+        x = torch.from_numpy(hash_spec(T, 64, seed=700 + T))[None, None]
+        with torch.no_grad():
+            y = bn0(x.transpose(1, 3)).transpose(1, 3)  # htsat.py:889-891
+            img = ref_htsat.HTSAT_Swin_Transformer.reshape_wav2img(self_like, y)
+        C[f"htsat_input/{T}"] = digest(img[0, 0].numpy(), n_probe=96)
 
     # trim indices straight from the shimmed call the reference makes
     for name, *_ in RECORDINGS:

@@ -175,3 +175,15 @@ def test_resample_lengths():
     for sr_in, n in ((4000, 32000), (2000, 5001), (8000, 12345), (44100, 44100)):
         y = F.resample_torchaudio(golden_signal(n, 2, sr=sr_in), sr_in, 16000)
         assert len(y) == int(np.ceil(n * 16000 / sr_in))
+
+
+def test_htsat_input_oracle_matches_reference():
+    """oracle.htsat_input restates htsat.py:889-891 + :829-858; fixtures come from executing the
+    reference's own reshape_wav2img."""
+    from cases import HTSAT_T, htsat_bn_params
+
+    w, b, m, v = htsat_bn_params(64)
+    for T in HTSAT_T:
+        img = F.htsat_input(hash_spec(T, 64, seed=700 + T), w, b, m, v)
+        assert img.shape == (256, 256)
+        check_digest(img, META[f"htsat_input/{T}"], rtol=1e-6, atol=1e-6)

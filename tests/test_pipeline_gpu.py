@@ -279,3 +279,39 @@ def test_c4_cola_pairs_on_the_fly_match_oracle():
             assert got.shape == (251, 64)
             assert np.abs(got[: ref.shape[0]] - ref).max() <= 3e-4
     assert random.getstate() == state_after  # the same number of draws was consumed
+
+
+def test_cache_writers_match_per_file_entry_points(wav_dir, tmp_path):
+    """The batched cache writers (entire_spec_npy, spectrogram_pad8.npy, fbank_audiomae.npy) hold what
+    the reference's loops would save: the per-file drop-in results, which are pinned to the reference
+    by test_dropin_entry_points_match_reference."""
+    from heart_murmur_detection_b200 import caches
+    from heart_murmur_detection_b200 import util as U
+
+    names = [name for name, *_ in RECORDINGS]
+    files = [os.path.join(wav_dir, n + ".wav") for n in names]
+    feature_dir = str(tmp_path)
+    written, invalid = caches.write_entire_spec_cache(files, feature_dir, input_sec=8, batch_bytes=1 << 20)
+    per_file = {n: U.get_entire_signal_librosa(wav_dir, n, spectrogram=True, input_sec=8) for n in names}
+    assert invalid == sum(v is None for v in per_file.values()) and invalid >= 1
+    assert [os.path.basename(w) for w in written] == [n for n in names if per_file[n] is not None]
+    assert list(np.load(os.path.join(feature_dir, "entire_spec_filenames.npy"))) == written
+    for w in written:
+        got = np.load(w + ".npy")
+        ref = per_file[os.path.basename(w)]
+        assert got.dtype == np.float32 and got.shape == ref.shape and np.array_equal(got, ref)
+
+    pad8 = caches.build_spectrogram_pad_cache(files, input_sec=8.18, batch_bytes=1 << 20, save_to=os.path.join(feature_dir, "spectrogram_pad8.npy"))
+    assert pad8.shape == (len(names), 256, 64) and pad8.dtype == np.float32
+    state = random.getstate()
+    for i, n in enumerate(names):
+        ref = U.get_split_signal_librosa(wav_dir, n, spectrogram=True, input_sec=8.18, trim_tail=False)[0]
+        assert np.array_equal(pad8[i], ref), n
+    random.setstate(state)
+    assert np.array_equal(np.load(os.path.join(feature_dir, "spectrogram_pad8.npy")), pad8)
+
+    fb = caches.build_fbank_cache(files, input_sec=10, batch_bytes=1 << 20)
+    assert fb.shape == (len(names), 998, 128)
+    for i, n in enumerate(names):
+        ref = U.get_split_signal_fbank_pad(wav_dir, n, spectrogram=True, input_sec=10, trim_tail=False)[0]
+        assert np.array_equal(fb[i], ref.numpy()), n

@@ -416,3 +416,28 @@ def test_pad_to_model_size():
     out = D.pad_or_crop_batch(store, [0, 1, 2, 3], max_len=1024).cpu().numpy()
     for i, s in enumerate(specs):
         np.testing.assert_array_equal(out[i], F.pad_to_model(s, 1024, 128))
+
+
+def test_htsat_input_stage_matches_reference():
+    """hmfe_htsat_input_batch (bn0 + bicubic time resize + fold, htsat.py:889-891, 829-858) against the
+    torch-CPU oracle (<= 2e-5) and the fixtures produced by the reference's reshape_wav2img."""
+    from cases import HTSAT_T, check_digest, htsat_bn_params
+    from heart_murmur_detection_b200 import frontend as fe
+    from oracle import frontend as F
+
+    w, b, m, v = htsat_bn_params(64)
+    specs = [hash_spec(T, 64, seed=700 + T) for T in HTSAT_T]
+    ro = np.zeros(len(specs) + 1, dtype=np.int64)
+    np.cumsum([s.shape[0] for s in specs], out=ro[1:])
+    dev = torch.from_numpy(np.concatenate(specs)).cuda()
+    out = fe.htsat_input(dev, ro[:-1], np.diff(ro), w, b, m, v).cpu().numpy()
+    assert out.shape == (len(specs), 1, 256, 256)
+    for i, (T, s) in enumerate(zip(HTSAT_T, specs)):
+        ref = F.htsat_input(s, w, b, m, v)
+        assert np.abs(out[i, 0] - ref).max() <= 2e-5, T
+        check_digest(out[i, 0], META[f"htsat_input/{T}"], rtol=2e-5, atol=2e-5)
+    # a crop of a longer spectrogram (row range inside the batch) and the full-length identity path
+    crop = fe.htsat_input(dev, [int(ro[3]) + 17], [900], w, b, m, v).cpu().numpy()[0, 0]
+    assert np.abs(crop - F.htsat_input(specs[3][17:917], w, b, m, v)).max() <= 2e-5
+    with pytest.raises(Exception):
+        fe.htsat_input(dev, [0], [1025], w, b, m, v)
