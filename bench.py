@@ -224,6 +224,10 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (0 = the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "copy", "multicast", "nccl"],
+                    help="N > 1: all-gather through peer memory (dist.PeerAllGather: copy engines or NVLink multicast "
+                         "push) or NCCL.  auto = copy engines up to 4 GPUs, NCCL beyond (measured, DESIGN.md section 8)")
+    ap.add_argument("--push-ctas", type=int, default=16)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -297,11 +301,22 @@ def main():
         t = torch.tensor([rows], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         max_rows = int(t.item())
-    # two send buffers (and two gather targets): the all-gather of step i runs on its own stream while
+    # two send buffers (and two gather targets): the all-gather of step i runs on its own stream(s) while
     # step i + 1 computes into the other buffer; the timed region ends after the last gather.
-    send = [torch.zeros((max_rows, n_cols), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+    peer_ag = None
+    if args.gather == "auto":
+        args.gather = "copy" if world <= 4 else "nccl"
+    if world > 1 and args.gather != "nccl":
+        from heart_murmur_detection_b200.dist import PeerAllGather
+
+        # kernels write straight into this rank's slot of the gathered buffer
+        peer_ag = PeerAllGather(max_rows, n_cols, mode=args.gather, push_ctas=args.push_ctas)
+        send = [peer_ag.slot(0), peer_ag.slot(1)]
+        comm = peer_ag.comm
+    else:
+        send = [torch.zeros((max_rows, n_cols), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
     out = send[0]
-    if world > 1:
+    if world > 1 and peer_ag is None:
         gathered = [torch.empty((world * max_rows, n_cols), dtype=torch.float32, device=dev) for _ in range(2)]
         comm = torch.cuda.Stream(device=dev)
         ev_ready = [torch.cuda.Event() for _ in range(2)]
@@ -312,6 +327,11 @@ def main():
         i = step_no[0] % len(send)
         step_no[0] += 1
         main = torch.cuda.current_stream()
+        if peer_ag is not None:
+            peer_ag.wait_reusable(i, main)
+            step(send[i])
+            peer_ag.gather(i, main)
+            return
         if world > 1 and step_no[0] > 2:
             main.wait_event(ev_sent[i])  # the gather that read send[i] two steps ago
         step(send[i])
@@ -381,7 +401,11 @@ def main():
                 pipeline.entire_signal_from_host(h_wav, off, h_out, **C2_KW)
             else:
                 frontend.fbank_from_host(fb_plan, h_wav, off, h_out, rows_per_clip=1024)
-            if world > 1:
+            if world > 1 and peer_ag is not None:
+                peer_ag.wait_reusable(0)
+                peer_ag.gather(0)
+                peer_ag.finish()
+            elif world > 1:
                 dist.all_gather_into_tensor(gathered[0], send[0])
 
         e2e_steps = max(3, min(args.steps, 5))
@@ -461,7 +485,7 @@ def main():
             "config": {"workload": WORKLOADS[wl], "workload_id": wl, "clips_per_gpu_per_step": n_clips,
                        "audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
                        "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
-                       "collective": "all_gather_into_tensor(row-padded features), overlapped with the next step's kernels" if world > 1 else "none",
+                       "collective": ("none" if world == 1 else f"peer-memory all-gather of the row-padded features (symmetric memory, {peer_ag.mode}, device barrier), overlapped with the next step's kernels" if peer_ag is not None else "NCCL all_gather_into_tensor(row-padded features), overlapped with the next step's kernels"),
                        **({"iir_plan": ctx.last_iir_plan()} if wl == "c2" else {})},
             "frames_per_s": world * n_frames_valid / (ms_step * 1e-3),
             "audio_seconds_per_s": world * total_samples / SR / (ms_step * 1e-3),

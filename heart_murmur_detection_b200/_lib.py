@@ -67,6 +67,7 @@ hmfe_ctx_profile_ms = _sig("hmfe_ctx_profile_ms", C.c_int, c_voidp, C.POINTER(C.
 KERNEL_NAMES = ["iir_zero_state", "iir_carry", "iir_final", "trim_power", "trim_index", "gather", "spec_mean", "spec_crop",
                 "iir_overlap"]
 
+hmfe_multicast_push = _sig("hmfe_multicast_push", C.c_int, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp)
 hmfe_pcm16_decode = _sig("hmfe_pcm16_decode", C.c_int, c_voidp, C.c_int64, c_voidp, c_voidp)
 
 hmfe_trim_num_frames = _sig("hmfe_trim_num_frames", C.c_int64, C.c_int64, C.c_int, C.c_int)

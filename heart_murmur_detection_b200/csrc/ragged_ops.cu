@@ -185,11 +185,41 @@ __global__ void __launch_bounds__(256) pcm16_decode_kernel(const int16_t* __rest
     for (int64_t i = 8 * n8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)pcm[i] * k;
 }
 
+// ---------------------------------------------------------------------------------- multicast push
+// One store instruction, N destinations: `mc_dst` is the NVLink-switch multicast mapping of a buffer
+// that exists on every GPU of the node (torch symmetric memory); multimem.st makes the switch
+// replicate the 16 bytes into all of them.  An all-gather then costs every GPU ONE egress copy of
+// its block instead of N-1.  Few CTAs are enough (the transfer is NVLink-bound), so the kernels of
+// the next step keep the SMs.
+__global__ void __launch_bounds__(512) multicast_push_kernel(const float4* __restrict__ src, float4* mc_dst, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(src + i);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+    __threadfence_system();
+}
+
 }  // namespace hmfe
 
 using namespace hmfe;
 
 extern "C" {
+
+int hmfe_multicast_push(const float* d_src, float* mc_dst, int64_t n, int n_ctas, void* stream) {
+    HMFE_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4");
+    if (n == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_src && mc_dst, "NULL pointer");
+    HMFE_REQUIRE(((reinterpret_cast<uintptr_t>(d_src) | reinterpret_cast<uintptr_t>(mc_dst)) & 15) == 0,
+                 "pointers must be 16-byte aligned");
+    HMFE_REQUIRE(n_ctas >= 1 && n_ctas <= 1024, "n_ctas out of range");
+    multicast_push_kernel<<<n_ctas, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(d_src), reinterpret_cast<float4*>(mc_dst), n / 4);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
 
 int hmfe_pcm16_decode(const int16_t* d_pcm, int64_t n, float* d_out, void* stream) {
     HMFE_REQUIRE(n >= 0, "n < 0");

@@ -95,3 +95,96 @@ def all_gather_features(local: torch.Tensor, rows_per_clip, shard, n_clips_total
     idx = np.concatenate([np.arange(s, s + n, dtype=np.int64) for s, n in zip(src_start, rows_global)]) if n_clips_total else np.zeros(0, np.int64)
     out = gathered.index_select(0, torch.from_numpy(idx).to(dev))
     return out, row_offsets
+
+
+class PeerAllGather:
+    """All-gather of equally sized row blocks through peer memory, without SM time.
+
+    Every rank owns a ``[world * rows, cols]`` buffer in symmetric memory (torch.distributed
+    ._symmetric_memory: the same allocation mapped into every process of the node over NVLink).  A rank
+    produces its block IN PLACE in its own slot and pushes it into the same slot of the other ranks'
+    buffers with device-to-device copies (copy engines over NVLink / NVSwitch), one copy stream per
+    peer, then joins a device-side barrier: when the barrier releases, every rank holds all blocks.
+    Compared with an SM-driven collective the kernels of the next step keep all SMs; the reference has
+    no counterpart (single GPU, src/pretrain/cola_training.py:275-278).
+
+    Buffers are double (``n_buffers``) so that the gather of step i overlaps the compute of step i+1.
+    """
+
+    def __init__(self, rows: int, cols: int, group=None, n_buffers: int = 2, dtype=torch.float32, mode: str = "auto",
+                 push_ctas: int = 16):
+        """mode: "multicast" (one multimem.st push through the NVLink switch), "copy" (one copy-engine
+        transfer per peer) or "auto" (multicast when the fabric offers it)."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.rows, self.cols = int(rows), int(cols)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = (self.world * self.rows, self.cols)
+        self.buffers = [symm_mem.empty(shape, dtype=dtype, device=dev) for _ in range(n_buffers)]
+        self.handles = [symm_mem.rendezvous(b, self.group) for b in self.buffers]
+        self.peer = [[h.get_buffer(r, shape, dtype) for r in range(self.world)] for h in self.handles]
+        self.comm = torch.cuda.Stream(device=dev)
+        self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.world - 1))]
+        self.ready = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.done = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.used = [False] * n_buffers
+        self.push_ctas = int(push_ctas)
+        has_mc = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.handles)
+        if mode == "multicast" and not has_mc:
+            raise RuntimeError("NVLink multicast is not available for this group")
+        self.mode = "multicast" if (mode in ("auto", "multicast") and has_mc and dtype == torch.float32) else "copy"
+
+    def slot(self, i: int) -> torch.Tensor:
+        """This rank's block of buffer i: produce the features here."""
+        return self.buffers[i][self.rank * self.rows : (self.rank + 1) * self.rows]
+
+    def wait_reusable(self, i: int, stream=None):
+        """Make ``stream`` wait until the previous gather of buffer i has completed on every rank."""
+        if self.used[i]:
+            (stream or torch.cuda.current_stream()).wait_event(self.done[i])
+
+    def gather(self, i: int, stream=None):
+        """Push slot(i) (produced on ``stream``) to every peer and barrier; asynchronous."""
+        main = stream or torch.cuda.current_stream()
+        self.ready[i].record(main)
+        lo, hi = self.rank * self.rows, (self.rank + 1) * self.rows
+        src = self.buffers[i][lo:hi]
+        if self.mode == "multicast":
+            import ctypes as C
+
+            from . import _lib
+
+            n = src.numel()
+            mc = int(self.handles[i].multicast_ptr) + lo * self.cols * 4
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ready[i])
+                self.handles[i].barrier(channel=0)  # every rank has produced its block, nobody still reads buffer i
+                _lib.check(_lib.hmfe_multicast_push(C.c_void_p(src.data_ptr()), C.c_void_p(mc), (n // 4) * 4, self.push_ctas,
+                                                    C.c_void_p(self.comm.cuda_stream)), "hmfe_multicast_push")
+                self.handles[i].barrier(channel=1)  # every rank's push has landed
+                self.done[i].record(self.comm)
+            self.used[i] = True
+            return self.buffers[i]
+        evs = []
+        for k in range(self.world - 1):
+            r = (self.rank + 1 + k) % self.world  # stagger the targets: rank r sends to r+1, r+2, ...
+            cs = self.copy_streams[k]
+            cs.wait_event(self.ready[i])
+            with torch.cuda.stream(cs):
+                self.peer[i][r][lo:hi].copy_(src, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(cs)
+                evs.append(e)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[i])
+            for e in evs:
+                self.comm.wait_event(e)
+            self.handles[i].barrier(channel=0)
+            self.done[i].record(self.comm)
+        self.used[i] = True
+        return self.buffers[i]
+
+    def finish(self, stream=None):
+        (stream or torch.cuda.current_stream()).wait_stream(self.comm)

@@ -232,6 +232,15 @@ int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const h
                          const uint8_t* d_row_mask, const float* d_mean, float* d_out, int out_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU: push `n` floats from local memory into the same offset of a buffer on EVERY GPU of the
+ * node with NVLink-switch multicast stores (multimem.st).  `mc_dst` is the multicast mapping of a
+ * symmetric allocation (e.g. torch.distributed._symmetric_memory: handle.multicast_ptr + byte
+ * offset).  Used by dist.PeerAllGather for the all-gather of the feature blocks, the single
+ * collective of the path (the reference itself is single GPU, cola_training.py:275-278).
+ * ------------------------------------------------------------------------------------------ */
+int hmfe_multicast_push(const float* d_src, float* mc_dst, int64_t n, int n_ctas, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * HTS-AT input stage (the first thing the OPERA-CT encoder does to the log-mel; src/model/htsat/
  * htsat.py:889-891 bn0 in inference form, :829-858 reshape_wav2img): per mel bin y = x*scale+shift,
  * bicubic (align_corners) resize of the time axis to spec_size*ratio frames (ratio = spec_size /
