@@ -101,6 +101,12 @@ hmfe_iir_sos_trim_batch = _sig(
     "hmfe_iir_sos_trim_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, C.c_int,
     C.c_int, C.c_float, c_voidp, c_voidp,
 )
+hmfe_sosfiltfilt_padlen = _sig("hmfe_sosfiltfilt_padlen", C.c_int, c_voidp, C.c_int)
+hmfe_sosfiltfilt_workspace_bytes = _sig("hmfe_sosfiltfilt_workspace_bytes", C.c_int64, c_voidp, C.c_int64, C.c_int)
+hmfe_sosfiltfilt_batch = _sig(
+    "hmfe_sosfiltfilt_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, C.c_int, c_voidp, C.c_int64,
+    c_voidp, c_voidp, c_voidp,
+)
 IIR_ALGOS = {"auto": 0, "scan": 1, "overlap": 2}
 hmfe_ctx_set_iir_algo = _sig("hmfe_ctx_set_iir_algo", C.c_int, c_voidp, C.c_int)
 IIR_ROWS = {"auto": 0, "scalar": 1, "vector": 2}

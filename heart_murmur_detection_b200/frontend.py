@@ -334,6 +334,33 @@ def iir_sos_trim(wav: torch.Tensor, offsets, sos: np.ndarray, out: torch.Tensor 
     return out, se
 
 
+def sosfiltfilt(wav: torch.Tensor, offsets, sos: np.ndarray, out_dtype=torch.float64, padlen: int | None = None,
+                ctx: Context | None = None, stream=None) -> torch.Tensor:
+    """Zero-phase SOS filtering of every clip: ``scipy.signal.sosfiltfilt(sos, x)`` (odd padding).
+    The reference's own band-pass is the causal ``iir_sos`` (lfilter); this is the extra mode."""
+    _require_cuda_f32(wav, "wav")
+    o = _as_offsets(offsets)
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    ctx = ctx or default_ctx()
+    pl_ = -1 if padlen is None else int(padlen)
+    edge = int(_lib.hmfe_sosfiltfilt_padlen(sos.ctypes.data_as(C.c_void_p), sos.shape[0])) if pl_ < 0 else pl_
+    nbytes = int(_lib.hmfe_sosfiltfilt_workspace_bytes(o.ctypes.data_as(C.c_void_p), o.size - 1, edge))
+    work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=wav.device)
+    out = torch.empty(wav.numel(), dtype=out_dtype, device=wav.device)
+    y32 = C.c_void_p(out.data_ptr()) if out.dtype == torch.float32 else C.c_void_p()
+    y64 = C.c_void_p(out.data_ptr()) if out.dtype == torch.float64 else C.c_void_p()
+    if not (y32 or y64):
+        raise TypeError("out_dtype must be float32 or float64")
+    with torch.cuda.device(wav.device):
+        check(
+            _lib.hmfe_sosfiltfilt_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
+                                        sos.ctypes.data_as(C.c_void_p), sos.shape[0], pl_, C.c_void_p(work.data_ptr()), nbytes,
+                                        y32, y64, _stream_ptr(stream)),
+            "hmfe_sosfiltfilt_batch",
+        )
+    return out
+
+
 def pcm16_to_f32(pcm: torch.Tensor, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
     """int16 CUDA samples -> float32 / 32768 (soundfile's PCM16 convention, exact)."""
     if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()):

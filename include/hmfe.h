@@ -147,6 +147,17 @@ int hmfe_iir_sos_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets
 int hmfe_iir_sos_trim_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
                             const double* h_sos, int n_sections, float* d_y32, double* d_y64, int frame_length,
                             int hop_length, float top_db, int64_t* d_start_end, void* stream);
+/* Zero-phase variant: scipy.signal.sosfiltfilt(sos, x) with the default odd padding (padlen < 0 ->
+ * scipy's default 3 * ntaps; hmfe_sosfiltfilt_padlen returns it).  BASELINE.json's north_star names
+ * sosfiltfilt; the reference itself calls the causal lfilter (src/util.py:113-126), which is what
+ * hmfe_iir_sos_batch reproduces - this is the additional mode, not the drop-in default.  Clips must be
+ * longer than padlen (scipy raises otherwise).  d_workspace: hmfe_sosfiltfilt_workspace_bytes() bytes of
+ * device memory.  Either output may be NULL. */
+int hmfe_sosfiltfilt_padlen(const double* h_sos, int n_sections);
+int64_t hmfe_sosfiltfilt_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int padlen);
+int hmfe_sosfiltfilt_batch(hmfe_ctx* ctx, const float* d_x, const int64_t* h_offsets, int64_t n_clips,
+                           const double* h_sos, int n_sections, int padlen, void* d_workspace, int64_t workspace_bytes,
+                           float* d_y32, double* d_y64, void* stream);
 /* Two realisations of the same filter.  SCAN: exact chunked scan (zero-state pass, carry scan with
  * the chunk transition matrix, final pass), any stable or unstable cascade.  OVERLAP: one pass in
  * which every chunk starts W samples early from a zero state, W chosen so that the cascade's

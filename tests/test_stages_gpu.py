@@ -441,3 +441,32 @@ def test_htsat_input_stage_matches_reference():
     assert np.abs(crop - F.htsat_input(specs[3][17:917], w, b, m, v)).max() <= 2e-5
     with pytest.raises(Exception):
         fe.htsat_input(dev, [0], [1025], w, b, m, v)
+
+
+@pytest.mark.parametrize("order", [5, 2])
+def test_sosfiltfilt_matches_scipy(order):
+    """Zero-phase mode (named in BASELINE.json's north_star; not what the reference calls):
+    <= 1e-4 * max|y| against scipy.signal.sosfiltfilt, in practice ~1e-7 (float32 intermediate)."""
+    from scipy.signal import butter, sosfiltfilt
+
+    from heart_murmur_detection_b200 import _lib
+    from heart_murmur_detection_b200 import frontend as fe
+
+    sos_scipy = butter(order, [200 / 8000, 1800 / 8000], btype="band", output="sos")
+    edge = 3 * (2 * len(sos_scipy) + 1)
+    lens = [edge + 1, edge + 2, 100, 1000, 4097, 128000, 90001, 300000]
+    clips = [golden_signal(n, seed=9 + i) for i, n in enumerate(lens)]
+    clips[3] = np.ones(1000, np.float32) * 0.25  # constant: the steady-state initial conditions matter
+    wav, off = _batch(clips)
+    for sos in (sos_scipy, fe.butter_bandpass_sos(200, 1800, SR, order)):
+        y = fe.sosfiltfilt(wav, off, sos).cpu().numpy()
+        assert y.dtype == np.float64
+        y32 = fe.sosfiltfilt(wav, off, sos, out_dtype=torch.float32).cpu().numpy()
+        for i, x in enumerate(clips):
+            ref = sosfiltfilt(sos_scipy, x)
+            scale = max(np.abs(ref).max(), np.abs(x).max() * 1e-3, 1e-12)
+            assert np.abs(y[off[i] : off[i + 1]] - ref).max() <= 2e-6 * scale, (i, lens[i])
+            assert np.abs(y32[off[i] : off[i + 1]] - ref).max() <= 1e-4 * scale, (i, lens[i])
+    short, soff = _batch([golden_signal(edge, 1)])
+    with pytest.raises(_lib.HmfeError):
+        fe.sosfiltfilt(short, soff, sos_scipy)  # scipy: "The length of the input vector x must be greater than padlen"
