@@ -315,3 +315,67 @@ def test_cache_writers_match_per_file_entry_points(wav_dir, tmp_path):
     for i, n in enumerate(names):
         ref = U.get_split_signal_fbank_pad(wav_dir, n, spectrogram=True, input_sec=10, trim_tail=False)[0]
         assert np.array_equal(fb[i], ref.numpy()), n
+
+
+def test_c2_full_size_properties():
+    """BASELINE config 2 at full size (5 272 ragged clips, 1.78 G samples) through size-independent
+    properties: the one-pass overlap band-pass equals the exact chunked scan on every sample; trim
+    indices are identical for both; every clip's normalised log-mel spans exactly [0, 1] with the
+    reference's frame count; 20 clips spread over the batch equal the per-clip CPU oracle."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import pipeline as pl
+    from heart_murmur_detection_b200 import synth
+    from oracle import frontend as F
+
+    lens = synth.clip_lengths("c2", 5272, seed=1234)
+    wav, off = synth.make_batch(lens, base_seed=0, device="cuda")
+    sos = fe.butter_bandpass_sos(200, 1800, SR, 5)
+    ctx_o, ctx_s = fe.Context(), fe.Context()
+    ctx_s.set_iir_algo("scan")
+    y_o, se_o = fe.iir_sos_trim(wav, off, sos, ctx=ctx_o)
+    assert ctx_o.last_iir_plan()["algo"] == "overlap" and ctx_o.last_iir_plan()["rows"] == "vector"
+    y_s, se_s = fe.iir_sos_trim(wav, off, sos, ctx=ctx_s)
+    assert ctx_s.last_iir_plan()["algo"] == "scan"
+    assert (y_o - y_s).abs().max().item() <= 2e-7  # both float32 outputs of float64 recurrences: last-bit differences only
+    assert torch.equal(se_o, se_s)
+    del y_o, y_s
+    kw = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
+    res = pl.entire_signal_batch(wav, off, spectrogram=True, **kw)
+    assert res.chunks.valid.all() and len(res.chunks.starts) == 5272
+    T = np.diff(res.row_offsets)
+    n_trim = (se_o[:, 1] - se_o[:, 0]).cpu().numpy()
+    expect = 1 + np.minimum(np.maximum(n_trim, 8 * SR), 32 * SR) // 512  # pad to 8 s, cut at 32 s, 1 + n // hop frames
+    assert np.array_equal(T, expect)
+    feats = res.features[: int(res.row_offsets[-1])]
+    assert torch.isfinite(feats).all()
+    seg = torch.from_numpy(np.repeat(np.arange(5272), T)).cuda()
+    mx = torch.full((5272,), -1.0, device="cuda").scatter_reduce(0, seg, feats.amax(dim=1), "amax")
+    mn = torch.full((5272,), 2.0, device="cuda").scatter_reduce(0, seg, feats.amin(dim=1), "amin")
+    assert torch.all(mx == 1.0) and torch.all(mn == 0.0)
+    host_idx = np.linspace(0, 5271, 20).astype(int)
+    for i in host_idx:
+        x = wav[off[i] : off[i + 1]].cpu().numpy()
+        ref = F.entire_signal(x, spectrogram=True, **kw)
+        got = res.chunk(int(i)).cpu().numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 2e-4, int(i)
+
+
+def test_c3_full_size_properties():
+    """BASELINE config 3 at full size (1000 x 10.24 s -> [1024, 128]): pad rows are zero, frames are
+    finite, a batch equals its clips run alone, and shifting a clip by one frame shift (160 samples)
+    shifts its fbank rows by one, within the fbank tolerance (snip_edges framing has no other coupling)."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c3", 1000)
+    wav, off = synth.make_batch(lens, base_seed=21, device="cuda")
+    plan = fe.fbank_plan(sample_rate=16000)
+    out, ro = plan(wav, off, rows_per_clip=1024)
+    out = out.view(1000, 1024, 128)
+    assert torch.isfinite(out).all() and torch.all(out[:, 1022:] == 0.0) and torch.all(out[:, :1022].amax(dim=2) > -15.9)
+    for i in (0, 500, 999):
+        single, _ = plan(wav[off[i] : off[i + 1]].clone(), np.array([0, lens[i]]), rows_per_clip=1024)
+        assert torch.equal(single.view(1024, 128), out[i])
+    # the frames land in other lanes / packed pairs of the warp: equal within the fbank tolerance, not bit for bit
+    shifted, _ = plan(wav[off[7] + 160 : off[8]].clone(), np.array([0, lens[7] - 160]))
+    assert (shifted - out[7, 1:1022]).abs().max().item() <= 2.3e-3
