@@ -48,6 +48,7 @@ struct FbBatch {
     int64_t n_clips, n_items;
     int uniform_n, uniform_m, uniform_items, uniform_rows;
     int row_cap;  // > 0: frames beyond this row count are dropped (padded layout)
+    unsigned long long* queue;  // next unclaimed work item (warps claim blocks of items dynamically)
 };
 
 struct FbTables {
@@ -84,8 +85,8 @@ HMFE_D FbItem fb_locate(const FbBatch& b, const FbMeta& mm, int64_t item, int64_
         c.x = b.wav + clip * (int64_t)c.nsamp;
         c.o = b.out + clip * (int64_t)b.uniform_rows * mm.n_mels;
     } else {
-        if (clip < 0) {
-            int64_t lo = 0, hi = b.n_clips;
+        if (clip < 0 || item >= b.item_prefix[min(clip + 4, b.n_clips)]) {
+            int64_t lo = max(clip, (int64_t)0), hi = b.n_clips;
             while (hi - lo > 1) {
                 const int64_t mid = (lo + hi) >> 1;
                 if (b.item_prefix[mid] <= item)
@@ -156,16 +157,32 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t per_cta = (b.n_items + gridDim.x - 1) / gridDim.x;
-    const int64_t it_begin = (int64_t)blockIdx.x * per_cta;
-    const int64_t it_end = min(b.n_items, it_begin + per_cta);
+    // warps claim blocks of 8 consecutive items from a global counter (as in logmel.cu) and start staggered
+    constexpr int kItemBlock = 8;
+    const int64_t it_end = b.n_items;
+    auto claim = [&]() -> int64_t {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
+        return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    };
+    int64_t blk_end = 0;
+    auto next_item = [&](int64_t it) -> int64_t {
+        if (it + 1 < blk_end) return it + 1;
+        if (it >= it_end) return it;
+        const int64_t nb = claim();
+        blk_end = nb + kItemBlock;
+        return nb;
+    };
     int64_t clip = -1;
+    __nanosleep((unsigned)(warp * 500));
 
     float raw[FAST ? kFbSpanRegs : 1];
-    FbItem cur = fb_locate(b, mm, it_begin + warp, it_end, clip);
+    int64_t item = claim();
+    blk_end = item + kItemBlock;
+    FbItem cur = fb_locate(b, mm, item, it_end, clip);
     if constexpr (FAST) fb_load_span(cur, lane, raw);
 
-    for (int64_t item = it_begin + warp; item < it_end; item += kFbWarps) {
+    while (item < it_end) {
         const float* x = cur.x;
         float* o = cur.o;
         const int m = cur.m, f0 = cur.f0;
@@ -217,7 +234,8 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 im[brev(n2, 4)] = f32x2{y[1], y[3]};
             }
             // the span of the warp's next item is fetched while this item is transformed
-            cur = fb_locate(b, mm, item + kFbWarps, it_end, clip);
+            item = next_item(item);
+            cur = fb_locate(b, mm, item, it_end, clip);
             fb_load_span(cur, lane, raw);
         } else {
             // pass 1 over the frame: mean (DC removal); pass 2 re-reads the samples (L1 hits)
@@ -257,7 +275,8 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 re[brev(n2, 4)] = f32x2{y[0], y[2]};
                 im[brev(n2, 4)] = f32x2{y[1], y[3]};
             }
-            cur = fb_locate(b, mm, item + kFbWarps, it_end, clip);
+            item = next_item(item);
+            cur = fb_locate(b, mm, item, it_end, clip);
         }
         fft_dit<16, f32x2>(re, im);
 #pragma unroll
@@ -512,8 +531,10 @@ int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t
     };
     const size_t desc_bytes = uniform ? 0 : (4 * (size_t)n_clips + 2) * sizeof(int64_t);
     void *hbuf = nullptr, *dbuf = nullptr;
-    const int slot = p->ring.acquire(std::max<size_t>(desc_bytes, 16), &hbuf, &dbuf);
+    const int slot = p->ring.acquire(desc_bytes + 16, &hbuf, &dbuf);
     if (slot < 0) return slot;
+    b.queue = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(dbuf) + desc_bytes);
+    HMFE_CHECK_CUDA(cudaMemsetAsync(b.queue, 0, sizeof(unsigned long long), st));
     int64_t total_rows = 0;
     if (uniform) {
         const int64_t m = frames_of(n0);
