@@ -369,6 +369,7 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    iir_plan = ctx.last_iir_plan() if wl == "c2" else None  # what the timed steps used (later calls overwrite it)
     kern = {k: v for k, v in ctx.profile_ms().items() if v[1]}
     p_ms, f_ms, p_n = lm_plan.profile_ms()
     if p_n:
@@ -486,7 +487,7 @@ def main():
                        "audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
                        "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
                        "collective": ("none" if world == 1 else f"peer-memory all-gather of the row-padded features (symmetric memory, {peer_ag.mode}, device barrier), overlapped with the next step's kernels" if peer_ag is not None else "NCCL all_gather_into_tensor(row-padded features), overlapped with the next step's kernels"),
-                       **({"iir_plan": ctx.last_iir_plan()} if wl == "c2" else {})},
+                       **({"iir_plan": iir_plan} if iir_plan else {})},
             "frames_per_s": world * n_frames_valid / (ms_step * 1e-3),
             "audio_seconds_per_s": world * total_samples / SR / (ms_step * 1e-3),
             "e2e": e2e,
