@@ -328,14 +328,28 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
         // formula (product rounded, then subtracted, no contraction) so that the clip maximum maps to
         // exactly 0 dB and the normalised output spans exactly [0, 1]; an all-equal clip gives 0.
         const float k10 = 3.01029995663981195f;
-        const float ref_db = __fmul_rn(k10, __log2f(fmaxf(amin, pmax)));
-        auto to_db = [&](float p) { return __fsub_rn(__fmul_rn(k10, __log2f(fmaxf(amin, p))), ref_db); };
+        // lg2.approx.ftz: the argument is >= amin = 1e-10, a normal number, so no denormal pre-scaling is needed
+        auto lg2 = [](float x) {
+            float r;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+            return r;
+        };
+        const float ref_db = __fmul_rn(k10, lg2(fmaxf(amin, pmax)));
+        auto to_db = [&](float p) { return __fsub_rn(__fmul_rn(k10, lg2(fmaxf(amin, p))), ref_db); };
         const float smax = to_db(pmax);
         const float floor_db = smax - top_db;
         const float smin = fmaxf(to_db(pmin), floor_db);
         const bool normalise = out_mode == HMFE_LOGMEL_OUT_NORMALISED && smax != smin;
         const float denom = normalise ? smax - smin : 1.0f;
         const float sub = normalise ? smin : 0.0f;
+        // (d - smin) / denom as a reciprocal multiply plus one residual correction: correctly rounded for
+        // these operands (0 <= d - smin <= denom), in particular exactly 1 at the clip maximum
+        const float inv = 1.0f / denom;
+        auto norm = [&](float d) {
+            const float n = d - sub;
+            const float q = n * inv;
+            return fmaf(fmaf(-q, denom, n), inv, q);
+        };
         float4* o4 = reinterpret_cast<float4*>(o);
         const int64_t n4 = count >> 2;
         constexpr int U = 4;  // float4 loads in flight per thread
@@ -354,7 +368,7 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float d = fmaxf(to_db(p[j]), floor_db);
-                    p[j] = normalise ? (d - sub) / denom : d;
+                    p[j] = normalise ? norm(d) : d;
                 }
                 o4[i] = v[u];
             }
