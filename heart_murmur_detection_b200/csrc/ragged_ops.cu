@@ -145,20 +145,31 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ s
     const float* s = src + d.src_off;
     float* o = dst + d.dst_off;
     const int t1 = min(d.len, t0 + kGatherTile);
-    // position inside the repeated source: advanced by 256 per iteration instead of a division per element
+    // position inside the repeated source: advanced by 256 per element instead of a division per element;
+    // four independent loads are issued before their stores
     const unsigned period = (unsigned)d.period;
     unsigned ph = (unsigned)(((unsigned long long)d.a_phase + (unsigned)(t0 + threadIdx.x)) % period);
     const unsigned step = 256u % period;
-    for (int i = t0 + threadIdx.x; i < t1; i += 256) {
-        float v = 0.0f;
-        if (i < d.a_end) {
-            v = __ldg(s + ph);
-        } else if (i < d.b_end) {
-            v = __ldg(s + d.b_start + (i - d.a_end));
+    for (int i0 = t0 + threadIdx.x; i0 < t1; i0 += 1024) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 256 * u;
+            v[u] = 0.0f;
+            if (i < t1) {
+                if (i < d.a_end)
+                    v[u] = __ldg(s + ph);
+                else if (i < d.b_end)
+                    v[u] = __ldg(s + d.b_start + (i - d.a_end));
+            }
+            ph += step;
+            if (ph >= period) ph -= period;
         }
-        o[i] = v;
-        ph += step;
-        if (ph >= period) ph -= period;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 256 * u;
+            if (i < t1) o[i] = v[u];
+        }
     }
 }
 
