@@ -120,6 +120,11 @@ hmfe_fbank_plan_create = _sig(
     "hmfe_fbank_plan_create", C.c_int, C.POINTER(c_voidp), C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
     C.c_double, C.c_double,
 )
+FB_REMOVE_DC, FB_MAGNITUDE, FB_LOG_OFFSET = 1, 2, 4
+hmfe_fbank_plan_create_custom = _sig(
+    "hmfe_fbank_plan_create_custom", C.c_int, C.POINTER(c_voidp), C.c_int, C.c_int, C.c_int, C.c_int, c_voidp, c_voidp, C.c_int,
+    C.c_double, C.c_double,
+)
 hmfe_fbank_plan_destroy = _sig("hmfe_fbank_plan_destroy", None, c_voidp)
 hmfe_fbank_num_frames = _sig("hmfe_fbank_num_frames", C.c_int64, c_voidp, C.c_int64)
 hmfe_fbank_mel_basis = _sig("hmfe_fbank_mel_basis", C.c_int, c_voidp, c_voidp)

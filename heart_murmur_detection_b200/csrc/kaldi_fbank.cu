@@ -36,6 +36,8 @@ struct FbMeta {
     int trip[kFbMaxSlots], wbase[kFbMaxSlots];
     int win, shift;
     float preemph;
+    int flags;         // HMFE_FB_*
+    float log_offset;  // HMFE_FB_LOG_OFFSET: log(x + log_offset) instead of log(max(x, FLT_EPSILON))
 };
 
 struct FbBatch {
@@ -192,26 +194,30 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
         if constexpr (FAST) {
             // d[j] = x[i] - preemph * x[i-1] over the span (frame independent), then per frame
             // (x[n] - mean) - preemph * (x[n-1] - mean) = d - (1 - preemph) * mean
-            float mean[4];
+            float mean[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (mm.flags & HMFE_FB_REMOVE_DC) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float acc = 0.0f;
+                for (int t = 0; t < 4; ++t) {
+                    float acc = 0.0f;
 #pragma unroll
-                for (int n2 = 0; n2 < 13; ++n2)
-                    if (n2 < 12 || lane < 16) acc += raw[n2 + 5 * t];
+                    for (int n2 = 0; n2 < 13; ++n2)
+                        if (n2 < 12 || lane < 16) acc += raw[n2 + 5 * t];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                mean[t] = acc / 400.0f;
+                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                    mean[t] = acc / 400.0f;
+                }
             }
             const float x0[4] = {raw[0], raw[5], raw[10], raw[15]};  // first sample of each frame (lane 0)
             const float cm = 1.0f - mm.preemph;
-            float prev_row = 0.0f;  // raw[j-1] of this lane
+            if (mm.preemph != 0.0f) {
+                float prev_row = 0.0f;  // raw[j-1] of this lane
 #pragma unroll
-            for (int j = 0; j < kFbSpanRegs; ++j) {
-                const float give = lane == 31 ? prev_row : raw[j];
-                const float pv = __shfl_sync(0xffffffffu, give, (lane + 31) & 31);
-                prev_row = raw[j];
-                raw[j] = fmaf(-mm.preemph, pv, raw[j]);
+                for (int j = 0; j < kFbSpanRegs; ++j) {
+                    const float give = lane == 31 ? prev_row : raw[j];
+                    const float pv = __shfl_sync(0xffffffffu, give, (lane + 31) & 31);
+                    prev_row = raw[j];
+                    raw[j] = fmaf(-mm.preemph, pv, raw[j]);
+                }
             }
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
@@ -255,7 +261,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                mean[t] = acc / (float)mm.win;
+                mean[t] = (mm.flags & HMFE_FB_REMOVE_DC) ? acc / (float)mm.win : 0.0f;
             }
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
@@ -312,9 +318,21 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 const float give_r = k2 == 0 ? zr[(32 - k1) & 31] : zr[31 - k1];
                 const float give_i = k2 == 0 ? zi[(32 - k1) & 31] : zi[31 - k1];
                 const float pr = __shfl_sync(0xffffffffu, give_r, src), pi = __shfl_sync(0xffffffffu, give_i, src);
-                pt[16 * k1 + k2] = frame_powers<float>(zr[k1], zi[k1], pr, pi);
+                xelem<float> pw = frame_powers<float>(zr[k1], zi[k1], pr, pi);
+                if (mm.flags & HMFE_FB_MAGNITUDE) {
+                    pw.a = sqrtf(pw.a);
+                    pw.b = sqrtf(pw.b);
+                }
+                pt[16 * k1 + k2] = pw;
             }
-            if (k2 == 0) pt[256] = frame_powers<float>(zr[16], zi[16], zr[16], zi[16]);
+            if (k2 == 0) {
+                xelem<float> pw = frame_powers<float>(zr[16], zi[16], zr[16], zi[16]);
+                if (mm.flags & HMFE_FB_MAGNITUDE) {
+                    pw.a = sqrtf(pw.a);
+                    pw.b = sqrtf(pw.b);
+                }
+                pt[256] = pw;
+            }
         }
         __syncwarp();
 
@@ -348,7 +366,9 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 const float acc[4] = {a0, a1, a2, a3};
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (f0 + t < m) o[(int64_t)(f0 + t) * mm.n_mels + row] = logf(fmaxf(acc[t], FLT_EPSILON));
+                    if (f0 + t < m)
+                        o[(int64_t)(f0 + t) * mm.n_mels + row] =
+                            (mm.flags & HMFE_FB_LOG_OFFSET) ? logf(acc[t] + mm.log_offset) : logf(fmaxf(acc[t], FLT_EPSILON));
             }
         }
         __syncwarp();
@@ -413,12 +433,11 @@ void hmfe_fbank_plan_destroy(hmfe_fbank_plan* p) {
     delete p;
 }
 
-int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame_length_ms, double frame_shift_ms,
-                           int n_mels, double low_freq, double high_freq, double preemph) {
+static int fbank_plan_init(hmfe_fbank_plan** plan, int sample_rate, int win, int shift, int n_mels,
+                           const std::vector<float>& half_window, std::vector<float> mel_dense, int flags, double preemph,
+                           double log_offset) {
     HMFE_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
-    HMFE_REQUIRE(sample_rate > 0 && frame_length_ms > 0 && frame_shift_ms > 0, "bad frame parameters");
-    const int win = (int)(sample_rate * frame_length_ms * 0.001), shift = (int)(sample_rate * frame_shift_ms * 0.001);
     if (win <= 256 || win > kFbPad || shift < 1) {
         set_error("window of %d samples unsupported: the kernel is specialised for a 512-point padded FFT "
                   "(25 ms at 16 kHz, src/util.py:845-856)", win);
@@ -433,10 +452,10 @@ int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame
     p->shift = shift;
     p->n_mels = n_mels;
     p->sm_count = device_sm_count();
-    p->mel_dense = mel_banks_kaldi(n_mels, kFbPad, sample_rate, low_freq, high_freq);
+    p->mel_dense = std::move(mel_dense);
     const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1, 16, kFbPStride);
     if (!verify_banded(bm, p->mel_dense, kFbPStride)) {
-        set_error("internal error: banded mel tables do not reproduce the mel basis");
+        set_error("the mel matrix is not banded (every row must have one contiguous support that fits the tile)");
         delete p;
         return HMFE_ERR_INVALID;
     }
@@ -446,11 +465,13 @@ int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame
     p->meta.win = win;
     p->meta.shift = shift;
     p->meta.preemph = (float)preemph;
+    p->meta.flags = flags;
+    p->meta.log_offset = (float)log_offset;
     for (int s = 0; s < bm.n_slots; ++s) {
         p->meta.trip[s] = bm.trip[s];
         p->meta.wbase[s] = bm.wbase[s];
     }
-    int rc = fb_upload(half_hann_symmetric(win), &p->d_win);
+    int rc = fb_upload(half_window, &p->d_win);
     if (rc == HMFE_OK) rc = fb_upload(twiddle_plane(kFbPad, 16), reinterpret_cast<float**>(&p->d_tw));
     if (rc == HMFE_OK) rc = fb_upload(bm.w, &p->d_melw);
     if (rc == HMFE_OK) rc = fb_upload(bm.start, &p->d_start);
@@ -463,6 +484,32 @@ int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame
     p->table_smem = (tbytes + 15) & ~(size_t)15;
     *plan = p;
     return HMFE_OK;
+}
+
+int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame_length_ms, double frame_shift_ms,
+                           int n_mels, double low_freq, double high_freq, double preemph) {
+    HMFE_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    HMFE_REQUIRE(sample_rate > 0 && frame_length_ms > 0 && frame_shift_ms > 0, "bad frame parameters");
+    const int win = (int)(sample_rate * frame_length_ms * 0.001), shift = (int)(sample_rate * frame_shift_ms * 0.001);
+    if (win <= 256 || win > kFbPad || shift < 1 || n_mels < 32 || n_mels % 32 || n_mels > 32 * kFbMaxSlots)
+        return fbank_plan_init(plan, sample_rate, win, shift, n_mels, {}, {}, 0, 0.0, 0.0);  // reports the error
+    return fbank_plan_init(plan, sample_rate, win, shift, n_mels, half_hann_symmetric(win),
+                           mel_banks_kaldi(n_mels, kFbPad, sample_rate, low_freq, high_freq), HMFE_FB_REMOVE_DC, preemph, 0.0);
+}
+
+int hmfe_fbank_plan_create_custom(hmfe_fbank_plan** plan, int sample_rate, int win, int shift, int n_mels,
+                                  const float* h_window, const float* h_mel, int flags, double preemph, double log_offset) {
+    HMFE_REQUIRE(plan != nullptr, "plan is NULL");
+    *plan = nullptr;
+    HMFE_REQUIRE(h_window && h_mel, "NULL argument");
+    HMFE_REQUIRE((flags & ~(HMFE_FB_REMOVE_DC | HMFE_FB_MAGNITUDE | HMFE_FB_LOG_OFFSET)) == 0, "unknown flag bits 0x%x", flags);
+    if (win <= 256 || win > kFbPad || shift < 1 || n_mels < 32 || n_mels % 32 || n_mels > 32 * kFbMaxSlots)
+        return fbank_plan_init(plan, sample_rate, win, shift, n_mels, {}, {}, 0, 0.0, 0.0);  // reports the error
+    std::vector<float> hw((size_t)win);
+    for (int i = 0; i < win; ++i) hw[i] = 0.5f * h_window[i];  // 1/4 of the two-frames-per-FFT separation, exact
+    std::vector<float> mel(h_mel, h_mel + (size_t)n_mels * (kFbPad / 2 + 1));
+    return fbank_plan_init(plan, sample_rate, win, shift, n_mels, hw, std::move(mel), flags, preemph, log_offset);
 }
 
 int64_t hmfe_fbank_num_frames(const hmfe_fbank_plan* p, int64_t n_samples) {

@@ -435,6 +435,30 @@ class FbankPlan:
                 "hmfe_fbank_plan_create",
             )
 
+    @classmethod
+    def custom(cls, window, mel, sample_rate=16000, shift=160, remove_dc=False, preemphasis=0.0, magnitude=False,
+               log_offset=None, device=None):
+        """Same kernel with the caller's window [win] and dense mel matrix [n_mels, 257] (one contiguous band
+        per row): sibling front-ends such as VGGish (periodic Hann, |X|, log(x + 0.01))."""
+        self = cls.__new__(cls)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        window = np.ascontiguousarray(window, dtype=np.float32)
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        if mel.ndim != 2 or mel.shape[1] != 257:
+            raise ValueError("mel must be [n_mels, 257] (512-point FFT)")
+        self.n_mels, self.win, self.shift = int(mel.shape[0]), int(window.size), int(shift)
+        flags = (_lib.FB_REMOVE_DC if remove_dc else 0) | (_lib.FB_MAGNITUDE if magnitude else 0) | (
+            _lib.FB_LOG_OFFSET if log_offset is not None else 0)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(
+                _lib.hmfe_fbank_plan_create_custom(C.byref(self._h), int(sample_rate), self.win, self.shift, self.n_mels,
+                                                   window.ctypes.data_as(C.c_void_p), mel.ctypes.data_as(C.c_void_p), flags,
+                                                   float(preemphasis), float(log_offset or 0.0)),
+                "hmfe_fbank_plan_create_custom",
+            )
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:

@@ -189,6 +189,15 @@ int hmfe_ctx_last_iir_plan(const hmfe_ctx* ctx, int* algo, int* chunk, int* warm
 typedef struct hmfe_fbank_plan hmfe_fbank_plan;
 int hmfe_fbank_plan_create(hmfe_fbank_plan** plan, int sample_rate, double frame_length_ms, double frame_shift_ms,
                            int n_mels, double low_freq, double high_freq, double preemph);
+/* Same frame -> 512-point FFT -> banded mel -> log kernel with the caller's window [win] and dense mel
+ * matrix [n_mels][257] (every row one contiguous band), for the sibling front-ends that differ from
+ * Kaldi's only in these constants - e.g. VGGish (src/benchmark/baseline/vggish/mel_features.py:125-170,
+ * 196-260, 342-400): periodic Hann, no DC removal / pre-emphasis, |X| instead of |X|^2, log(x + 0.01). */
+#define HMFE_FB_REMOVE_DC 1   /* subtract the frame mean (Kaldi remove_dc_offset)       */
+#define HMFE_FB_MAGNITUDE 2   /* mel of |X| instead of |X|^2                            */
+#define HMFE_FB_LOG_OFFSET 4  /* log(x + log_offset) instead of log(max(x, FLT_EPSILON)) */
+int hmfe_fbank_plan_create_custom(hmfe_fbank_plan** plan, int sample_rate, int win, int shift, int n_mels,
+                                  const float* h_window, const float* h_mel, int flags, double preemph, double log_offset);
 void hmfe_fbank_plan_destroy(hmfe_fbank_plan* plan);
 int64_t hmfe_fbank_num_frames(const hmfe_fbank_plan* plan, int64_t n_samples);
 int hmfe_fbank_mel_basis(const hmfe_fbank_plan* plan, float* h_out);

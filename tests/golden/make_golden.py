@@ -198,6 +198,17 @@ def main():
             img = ref_htsat.HTSAT_Swin_Transformer.reshape_wav2img(self_like, y)
         C[f"htsat_input/{T}"] = digest(img[0, 0].numpy(), n_probe=96)
 
+    # ---- VGGish input front-end (src/benchmark/baseline/vggish/vggish_input.py:52-125, executed) ----
+    sys.path.insert(0, os.path.join(REFERENCE, "src", "benchmark", "baseline", "vggish"))
+    import vggish_input as ref_vgg  # imports the reference's mel_features / vggish_params
+
+    for name in ("r_short", "r_mid", "r_long"):
+        ex = ref_vgg.waveform_to_examples(store[name], 16000)
+        C[f"vggish/{name}"] = {"shape": list(ex.shape), "dtype": str(ex.dtype), "digest": digest(ex, n_probe=96)}
+    arrays["vggish/r_short"] = ref_vgg.waveform_to_examples(store["r_short"], 16000).astype(np.float32)
+    arrays["vggish/mel_matrix"] = ref_vgg.mel_features.spectrogram_to_mel_matrix(
+        num_mel_bins=64, num_spectrogram_bins=257, audio_sample_rate=16000, lower_edge_hertz=125, upper_edge_hertz=7500)
+
     # trim indices straight from the shimmed call the reference makes
     for name, *_ in RECORDINGS:
         _, idx = lr.trim(store[name], frame_length=1600, hop_length=800)

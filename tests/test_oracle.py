@@ -187,3 +187,21 @@ def test_htsat_input_oracle_matches_reference():
         img = F.htsat_input(hash_spec(T, 64, seed=700 + T), w, b, m, v)
         assert img.shape == (256, 256)
         check_digest(img, META[f"htsat_input/{T}"], rtol=1e-6, atol=1e-6)
+
+
+def test_vggish_mel_matrix_restated_exactly():
+    """The host-side restatement of mel_features.spectrogram_to_mel_matrix / periodic_hann (no GPU needed)
+    equals the matrix produced by executing the reference's own function."""
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("vgg_restated", os.path.join(here, "..", "heart_murmur_detection_b200",
+                                                                               "vggish_input.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    # only the pure-numpy helpers are needed here: execute the module text up to the plan cache
+    exec(compile(src.split("_plan_lock = ")[0].replace("from . import frontend as fe", ""), spec.origin, "exec"), ns)
+    arr = {k.replace("|", "/"): v for k, v in np.load(os.path.join(here, "golden", "ref_util.npz")).items()}
+    got = ns["spectrogram_to_mel_matrix"](num_mel_bins=64, num_spectrogram_bins=257, audio_sample_rate=16000,
+                                          lower_edge_hertz=125, upper_edge_hertz=7500)
+    assert np.array_equal(got, arr["vggish/mel_matrix"])

@@ -470,3 +470,21 @@ def test_sosfiltfilt_matches_scipy(order):
     short, soff = _batch([golden_signal(edge, 1)])
     with pytest.raises(_lib.HmfeError):
         fe.sosfiltfilt(short, soff, sos_scipy)  # scipy: "The length of the input vector x must be greater than padlen"
+
+
+def test_vggish_examples_match_reference():
+    """vggish_input.waveform_to_examples (sibling front-end, vggish_input.py:52-125) on the fbank kernel with
+    VGGish constants: shapes / dtype exact, values within 2e-5 of the float64 reference (fixtures produced by
+    executing the reference's vggish_input + mel_features)."""
+    from cases import RECORDINGS, check_digest
+    from heart_murmur_detection_b200 import vggish_input as V
+
+    arr = {k.replace("|", "/"): v for k, v in np.load(os.path.join(HERE, "golden", "ref_util.npz")).items()}
+    rec = {name: golden_signal(n, seed, SR, lead, tail) for name, n, seed, lead, tail in RECORDINGS}
+    for name in ("r_short", "r_mid", "r_long"):
+        g = META[f"vggish/{name}"]
+        ex = V.waveform_to_examples(rec[name], 16000)
+        assert list(ex.shape) == g["shape"] and str(ex.dtype) == g["dtype"]
+        check_digest(ex, g["digest"], rtol=2e-5, atol=2e-5)
+    assert np.abs(V.waveform_to_examples(rec["r_short"], 16000) - arr["vggish/r_short"]).max() <= 2e-5
+    assert V.waveform_to_examples(rec["r_short"][:15000], 16000).shape == (0, 96, 64)  # shorter than one example
