@@ -474,8 +474,9 @@ def test_sosfiltfilt_matches_scipy(order):
 
 def test_vggish_examples_match_reference():
     """vggish_input.waveform_to_examples (sibling front-end, vggish_input.py:52-125) on the fbank kernel with
-    VGGish constants: shapes / dtype exact, values within 2e-5 of the float64 reference (fixtures produced by
-    executing the reference's vggish_input + mel_features)."""
+    VGGish constants: shapes / dtype exact, values within 1e-4 of the float64 reference (fixtures produced by
+    executing the reference's vggish_input + mel_features).  The log offset 0.01 turns the float32 FFT's absolute
+    error (~5e-7 for unit-scale frames) into 5e-5 in the log domain near the floor log(0.01)."""
     from cases import RECORDINGS, check_digest
     from heart_murmur_detection_b200 import vggish_input as V
 
@@ -485,6 +486,6 @@ def test_vggish_examples_match_reference():
         g = META[f"vggish/{name}"]
         ex = V.waveform_to_examples(rec[name], 16000)
         assert list(ex.shape) == g["shape"] and str(ex.dtype) == g["dtype"]
-        check_digest(ex, g["digest"], rtol=2e-5, atol=2e-5)
-    assert np.abs(V.waveform_to_examples(rec["r_short"], 16000) - arr["vggish/r_short"]).max() <= 2e-5
+        check_digest(ex, g["digest"], rtol=1e-4, atol=1e-4)
+    assert np.abs(V.waveform_to_examples(rec["r_short"], 16000) - arr["vggish/r_short"]).max() <= 1e-4
     assert V.waveform_to_examples(rec["r_short"][:15000], 16000).shape == (0, 96, 64)  # shorter than one example
