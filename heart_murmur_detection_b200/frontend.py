@@ -127,8 +127,9 @@ def logmel_from_host(plan: LogMelPlan, h_wav: torch.Tensor, offsets, h_out: torc
     i % 2 (H2D copy -> kernels -> D2H copy), so the copies of one chunk overlap the kernels of
     the other.  Returns (h_out [sum T_i, n_mels], frame_offsets).  Synchronous on return.
     """
-    if h_wav.is_cuda or h_wav.dtype != torch.float32:
-        raise TypeError("h_wav must be a float32 host tensor")
+    if h_wav.is_cuda or h_wav.dtype not in (torch.float32, torch.int16):
+        raise TypeError("h_wav must be a float32 (samples) or int16 (16-bit PCM payload) host tensor")
+    pcm = h_wav.dtype == torch.int16
     o = _as_offsets(offsets)
     n = o.size - 1
     fo = plan.frame_offsets(o)
@@ -145,6 +146,7 @@ def logmel_from_host(plan: LogMelPlan, h_wav: torch.Tensor, offsets, h_out: torc
     cache = plan.__dict__.setdefault("_host_pipe", {})
     if cache.get("cap", (0, 0)) < (max_samples, max_frames) or cache.get("cap", (0, 0))[1] < max_frames:
         cache["wav"] = [torch.empty(max_samples, dtype=torch.float32, device=dev) for _ in range(2)]
+        cache["pcm"] = [torch.empty(max_samples, dtype=torch.int16, device=dev) for _ in range(2)]
         cache["out"] = [torch.empty((max_frames, plan.n_mels), dtype=torch.float32, device=dev) for _ in range(2)]
         cache["streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
         cache["cap"] = (max_samples, max_frames)
@@ -156,7 +158,12 @@ def logmel_from_host(plan: LogMelPlan, h_wav: torch.Tensor, offsets, h_out: torc
         dw, do = cache["wav"][i % 2], cache["out"][i % 2]
         ns, nf = int(o[b] - o[a]), int(fo[b] - fo[a])
         with torch.cuda.stream(s):
-            dw[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+            if pcm:  # 2-byte payload over PCIe, / 32768 on the device
+                dp = cache["pcm"][i % 2]
+                dp[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+                pcm16_to_f32(dp[:ns], out=dw, stream=s)
+            else:
+                dw[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
             plan(dw, o[a : b + 1] - o[a], out=do, mode=mode, stream=s)
             h_out[int(fo[a]) : int(fo[b])].copy_(do[:nf], non_blocking=True)
     for s in cache["streams"]:
@@ -517,8 +524,9 @@ def fbank_from_host(plan: FbankPlan, h_wav: torch.Tensor, offsets, h_out: torch.
 
     Chunk i runs on stream i % 2 (H2D copy -> kernel -> D2H copy): the two PCIe directions and the
     kernel of neighbouring chunks overlap.  Returns (h_out [rows, n_mels], row_offsets)."""
-    if h_wav.is_cuda or h_wav.dtype != torch.float32:
-        raise TypeError("h_wav must be a float32 host tensor")
+    if h_wav.is_cuda or h_wav.dtype not in (torch.float32, torch.int16):
+        raise TypeError("h_wav must be a float32 (samples) or int16 (16-bit PCM payload) host tensor")
+    pcm = h_wav.dtype == torch.int16
     o = _as_offsets(offsets)
     n = o.size - 1
     m = plan.num_frames(np.diff(o))
@@ -541,6 +549,7 @@ def fbank_from_host(plan: FbankPlan, h_wav: torch.Tensor, offsets, h_out: torch.
     if cap[0] < max_samples or cap[1] < max_rows:
         cap = (max(cap[0], max_samples), max(cap[1], max_rows))
         cache["wav"] = [torch.empty(cap[0], dtype=torch.float32, device=dev) for _ in range(2)]
+        cache["pcm"] = [torch.empty(cap[0], dtype=torch.int16, device=dev) for _ in range(2)]
         cache["out"] = [torch.empty((cap[1], plan.n_mels), dtype=torch.float32, device=dev) for _ in range(2)]
         cache["streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
         cache["cap"] = cap
@@ -552,7 +561,12 @@ def fbank_from_host(plan: FbankPlan, h_wav: torch.Tensor, offsets, h_out: torch.
         dw, do = cache["wav"][i % 2], cache["out"][i % 2]
         ns, nr = int(o[b] - o[a]), int(ro[b] - ro[a])
         with torch.cuda.stream(s):
-            dw[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+            if pcm:
+                dp = cache["pcm"][i % 2]
+                dp[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+                pcm16_to_f32(dp[:ns], out=dw, stream=s)
+            else:
+                dw[:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
             plan(dw, o[a : b + 1] - o[a], rows_per_clip=rows_per_clip, out=do, stream=s)
             h_out[int(ro[a]) : int(ro[b])].copy_(do[:nr], non_blocking=True)
     for s in cache["streams"]:

@@ -244,6 +244,15 @@ def test_pcm16_host_input_equals_decoded_float_input():
     assert np.array_equal(ro_a, ro_b) and np.array_equal(ids_a, ids_b) and np.array_equal(valid_a, valid_b)
     rows = int(ro_a[-1])
     assert torch.equal(a[:rows], b[:rows])
+    # the log-mel and fbank host-buffer entries take the same payload
+    lm = fe.logmel_plan(16000, 64, 50, 8000, 1024, 512)
+    x1, _ = fe.logmel_from_host(lm, h_pcm, off, chunk_bytes=8 << 20)
+    x2, _ = fe.logmel_from_host(lm, h_f32, off, chunk_bytes=8 << 20)
+    assert torch.equal(x1, x2)
+    fb = fe.fbank_plan(sample_rate=16000)
+    y1, _ = fe.fbank_from_host(fb, h_pcm, off, chunk_bytes=8 << 20)
+    y2, _ = fe.fbank_from_host(fb, h_f32, off, chunk_bytes=8 << 20)
+    assert torch.equal(y1, y2)
 
 
 def test_c4_cola_pairs_on_the_fly_match_oracle():
