@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "scalar", "packed"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "scalar", "packed", "pair"])
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (0 = the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -7,7 +7,7 @@
 // accuracy are validated against the oracle before any GPU time is spent
 // (tests/test_host_emulation.py).  Test infrastructure, not part of libhmfe.so.
 //
-// usage: host_check logmel <scalar|packed> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>
+// usage: host_check logmel <scalar|packed|pair> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -79,6 +79,71 @@ static void run_logmel(const std::vector<float>& x, int hop, int n_mels, double 
                     if (fa < T) out[(size_t)fa * n_mels + row] = vget(aa, t);
                     if (fa + 1 < T) out[(size_t)(fa + 1) * n_mels + row] = vget(ab, t);
                 }
+            }
+    }
+}
+
+// Mirrors logmel_power_pair_kernel (logmel.cu) lane for lane: one complex transform per item, elements paired.
+static void run_logmel_pair(const std::vector<float>& x, int hop, int n_mels, double fmin, double fmax, std::vector<float>& out) {
+    const int nsamp = (int)x.size();
+    const int T = 1 + nsamp / hop;
+    const std::vector<float> dense = mel_filterbank_slaney(16000, kNfft, n_mels, fmin, fmax);
+    const BandedMel bm = build_banded(dense, n_mels, kNfft / 2 + 1, 16, kBinsPad);
+    if (!verify_banded(bm, dense, kBinsPad)) {
+        fprintf(stderr, "banded mel verification failed\n");
+        exit(3);
+    }
+    const std::vector<float> win = half_hann_periodic(kNfft);
+    const std::vector<float> twv = twiddle_plane_paired(kNfft);
+    const float4* tw = reinterpret_cast<const float4*>(twv.data());
+    out.assign((size_t)T * n_mels, 0.0f);
+    std::vector<float> planes(2 * kPlane);
+    float* pre = planes.data();
+    float* pim = pre + kPlane;
+    std::vector<f32x2> ptile(kBinsPad);
+    struct Lane {
+        f32x2 re[16], im[16];
+    };
+    std::vector<Lane> L(32);
+    for (int f0 = 0; f0 < T; f0 += 2) {
+        for (int lane = 0; lane < 32; ++lane) {
+            auto fetch = [&](bool second, int n) -> float {
+                const int f = f0 + (second ? 1 : 0);
+                if (f >= T) return 0.0f;
+                const int i = f * hop - kNfft / 2 + n;
+                return (i >= 0 && i < nsamp) ? x[i] : 0.0f;
+            };
+            pair_load_window(lane, win.data(), fetch, L[lane].re, L[lane].im);
+            fft32_paired(L[lane].re, L[lane].im);
+            pair_twiddle(lane, tw, L[lane].re, L[lane].im);
+            pair_exchange_store(lane, pre, pim, L[lane].re, L[lane].im);
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            pair_exchange_load(lane, pre, pim, L[lane].re, L[lane].im);
+            fft32_paired(L[lane].re, L[lane].im);
+        }
+        for (auto& e : ptile) e = f32x2{0.0f, 0.0f};
+        for (int lane = 0; lane < 32; ++lane) {
+            const int src = (32 - lane) & 31;
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const int preg = src == 0 ? ((32 - k1) & 31) : 31 - k1;  // what lane `src` provides
+                const xelem<float> pw = frame_powers<float>(L[lane].re[k1].x, L[lane].im[k1].x, pair_get(L[src].re, preg),
+                                                            pair_get(L[src].im, preg));
+                ptile[lane + 32 * k1] = f32x2{pw.a, pw.b};
+            }
+            if (lane == 0) {
+                const xelem<float> pw = frame_powers<float>(L[0].re[0].y, L[0].im[0].y, L[0].re[0].y, L[0].im[0].y);
+                ptile[512] = f32x2{pw.a, pw.b};
+            }
+        }
+        for (int lane = 0; lane < 32; ++lane)
+            for (int s = 0; s < bm.n_slots; ++s) {
+                f32x2 acc;
+                mel_slot_ab(lane, ptile.data(), bm.w.data() + (size_t)bm.wbase[s] * 32, bm.start[s * 32 + lane], bm.trip[s], acc);
+                const int row = bm.row[s * 32 + lane];
+                if (row < 0) continue;
+                if (f0 < T) out[(size_t)f0 * n_mels + row] = acc.x;
+                if (f0 + 1 < T) out[(size_t)(f0 + 1) * n_mels + row] = acc.y;
             }
     }
 }
@@ -218,7 +283,9 @@ int main(int argc, char** argv) {
         const double fmin = atof(argv[5]), fmax = atof(argv[6]);
         const std::vector<float> x = read_f32(argv[7]);
         std::vector<float> out;
-        if (packed)
+        if (!strcmp(argv[2], "pair"))
+            run_logmel_pair(x, hop, n_mels, fmin, fmax, out);
+        else if (packed)
             run_logmel<f32x2>(x, hop, n_mels, fmin, fmax, out);
         else
             run_logmel<float>(x, hop, n_mels, fmin, fmax, out);
@@ -232,6 +299,6 @@ int main(int argc, char** argv) {
         write_f32(argv[4], out);
         return 0;
     }
-    fprintf(stderr, "usage: host_check logmel <scalar|packed> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>\n");
+    fprintf(stderr, "usage: host_check logmel <scalar|packed|pair> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>\n");
     return 1;
 }

@@ -298,6 +298,145 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "pair" variant (logmel_core.cuh): one complex transform (2 frames) per warp iteration with the
+// packed FP32 instructions applied across elements.  64 registers of FFT data per thread instead
+// of 128 and an 8.7 KB exchange area per warp instead of 16.9 KB: 20 warps per SM instead of 12.
+// ---------------------------------------------------------------------------------------------
+template <int WARPS, int MINB, int NSLOTS>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+logmel_power_pair_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm) {
+    constexpr int FR = 2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* s_tw = reinterpret_cast<float4*>(smem);  // [16][32]
+    float* s_win = reinterpret_cast<float*>(s_tw + 512);
+    float* s_melw = s_win + 1024;
+    int* s_start = reinterpret_cast<int*>(s_melw + mm.total_trip * 32);
+    int* s_row = s_start + mm.n_slots * 32;
+    int* s_meta = s_row + mm.n_slots * 32;  // trip[kMaxSlots], wbase[kMaxSlots]
+    size_t tbytes = (size_t)(512 * 16 + 1024 * 4 + mm.total_trip * 128 + mm.n_slots * 256 + 2 * kMaxSlots * 4);
+    tbytes = (tbytes + 15) & ~(size_t)15;
+    float* pre = reinterpret_cast<float*>(smem + tbytes) + (threadIdx.x >> 5) * (2 * kPlane);
+    float* pim = pre + kPlane;
+    f32x2* ptile = reinterpret_cast<f32x2*>(pre);  // power tile (p_a, p_b) per bin, overlays the planes
+
+    for (int i = threadIdx.x; i < 512; i += WARPS * 32) s_tw[i] = reinterpret_cast<const float4*>(tb.tw)[i];
+    for (int i = threadIdx.x; i < 1024; i += WARPS * 32) s_win[i] = tb.win[i];
+    for (int i = threadIdx.x; i < mm.total_trip * 32; i += WARPS * 32) s_melw[i] = tb.melw[i];
+    for (int i = threadIdx.x; i < mm.n_slots * 32; i += WARPS * 32) {
+        s_start[i] = tb.start[i];
+        s_row[i] = tb.row[i];
+    }
+    if (threadIdx.x < kMaxSlots) {
+        s_meta[threadIdx.x] = mm.trip[threadIdx.x];
+        s_meta[kMaxSlots + threadIdx.x] = mm.wbase[threadIdx.x];
+    }
+    // the mel windows read up to kBinsPad power entries under zero weights: no stale NaN bit patterns
+    for (int i = threadIdx.x & 31; i < 2 * kPlane; i += 32) pre[i] = 0.0f;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mels = mm.n_mels;
+    const int n_slots = NSLOTS > 0 ? NSLOTS : mm.n_slots;
+    constexpr int kItemBlock = 16;  // 16 items = 32 frames per claim, as in the packed kernel
+    const int64_t it_end = b.n_items;
+    auto claim = [&]() -> int64_t {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
+        return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    };
+    int64_t blk_end = 0;
+    auto next_item = [&](int64_t item) -> int64_t {
+        if (item + 1 < blk_end) return item + 1;
+        if (item >= it_end) return item;
+        const int64_t nb = claim();
+        blk_end = nb + kItemBlock;
+        return nb;
+    };
+    int64_t clip_cursor = -1;
+    if (b.stagger_ns > 0) __nanosleep((unsigned)(warp * b.stagger_ns));
+
+    float raw[1][2][32];
+    int64_t item = claim();
+    blk_end = item + kItemBlock;
+    ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
+    load_raw<1>(cur, b.hop, lane, raw);
+
+    while (item < it_end) {
+        f32x2 re[16], im[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int n2 = 2 * brev(q, 4);
+            const f32x2 w{s_win[lane + 32 * n2], s_win[lane + 32 * (n2 + 1)]};
+            re[q] = vmul(f32x2{raw[0][0][n2], raw[0][0][n2 + 1]}, w);
+            im[q] = vmul(f32x2{raw[0][1][n2], raw[0][1][n2 + 1]}, w);
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            fft32_paired(re, im);
+            if (pass == 0) {
+                pair_twiddle(lane, s_tw, re, im);
+                pair_exchange_store(lane, pre, pim, re, im);
+                __syncwarp();
+                pair_exchange_load(lane, pre, pim, re, im);
+                __syncwarp();
+            }
+        }
+        {
+            const int src = (32 - lane) & 31;
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const float give_r = lane == 0 ? pair_get(re, (32 - k1) & 31) : pair_get(re, 31 - k1);
+                const float give_i = lane == 0 ? pair_get(im, (32 - k1) & 31) : pair_get(im, 31 - k1);
+                const float pr = __shfl_sync(0xffffffffu, give_r, src), pi = __shfl_sync(0xffffffffu, give_i, src);
+                const xelem<float> pw = frame_powers<float>(re[k1].x, im[k1].x, pr, pi);
+                ptile[lane + 32 * k1] = f32x2{pw.a, pw.b};
+            }
+            if (lane == 0) {
+                const xelem<float> pw = frame_powers<float>(re[0].y, im[0].y, re[0].y, im[0].y);
+                ptile[512] = f32x2{pw.a, pw.b};
+            }
+        }
+        __syncwarp();
+
+        item = next_item(item);
+        const ItemCtx nxt = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
+        load_raw<1>(nxt, b.hop, lane, raw);
+
+        float vmax = 0.0f, vmin = INFINITY;
+#pragma unroll
+        for (int s = 0; s < (NSLOTS > 0 ? NSLOTS : kMaxSlots); ++s) {
+            if (NSLOTS == 0 && s >= n_slots) break;
+            f32x2 acc;
+            mel_slot_ab(lane, ptile, s_melw + s_meta[kMaxSlots + s] * 32, s_start[s * 32 + lane], s_meta[s], acc);
+            const int row = s_row[s * 32 + lane];
+            if (row >= 0) {
+                if (cur.f0 < cur.T) {
+                    cur.o[(int64_t)cur.f0 * n_mels + row] = acc.x;
+                    vmax = fmaxf(vmax, acc.x);
+                    vmin = fminf(vmin, acc.x);
+                }
+                if (cur.f0 + 1 < cur.T) {
+                    cur.o[(int64_t)(cur.f0 + 1) * n_mels + row] = acc.y;
+                    vmax = fmaxf(vmax, acc.y);
+                    vmin = fminf(vmin, acc.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+        }
+        if (lane == 0 && cur.valid) {
+            atomicMax(b.stats + 2 * cur.clip, __float_as_uint(vmax));
+            atomicMin(b.stats + 2 * cur.clip + 1, __float_as_uint(vmin));
+        }
+        __syncwarp();
+        cur = nxt;
+    }
+}
+
 __global__ void logmel_init_stats_kernel(unsigned* stats, int64_t n_clips, unsigned long long* queue) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *queue = 0ull;
@@ -426,6 +565,32 @@ static int launch_power(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t 
     }
 }
 
+constexpr int kPairWarps = 20;
+
+template <int NSLOTS>
+static int launch_pair_n(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    // tables: float4 twiddles (8 KB) instead of float2 (8 KB): same size as the other variants' layout
+    const size_t tbytes = ((size_t)(512 * 16 + 1024 * 4 + p->meta.total_trip * 128 + p->meta.n_slots * 256 + 2 * kMaxSlots * 4) + 15) &
+                          ~(size_t)15;
+    const size_t smem = tbytes + (size_t)kPairWarps * 2 * kPlane * sizeof(float);
+    auto kern = logmel_power_pair_kernel<kPairWarps, 1, NSLOTS>;
+    HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (b.n_items + kPairWarps - 1) / kPairWarps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count));
+    LogmelTables tb{p->d_win, p->d_tw, p->d_melw, p->d_start, p->d_row};
+    kern<<<grid, kPairWarps * 32, smem, st>>>(b, tb, p->meta);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
+static int launch_pair(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    switch (p->meta.n_slots) {
+        case 2: return launch_pair_n<2>(p, b, st);
+        case 4: return launch_pair_n<4>(p, b, st);
+        default: return launch_pair_n<0>(p, b, st);
+    }
+}
+
 extern "C" {
 
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
@@ -441,7 +606,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
                  n_mels, 32 * kMaxSlots);
     HMFE_REQUIRE(sample_rate > 0 && f_min >= 0 && f_max > f_min && f_max <= 0.5 * sample_rate + 1e-9,
                  "bad frequency range [%g, %g] for sr=%d", f_min, f_max, sample_rate);
-    HMFE_REQUIRE(variant >= 0 && variant <= 2, "bad variant %d", variant);
+    HMFE_REQUIRE(variant >= 0 && variant <= 3, "bad variant %d", variant);
     hmfe_logmel_plan* p = new (std::nothrow) hmfe_logmel_plan();
     HMFE_REQUIRE(p != nullptr, "out of host memory");
     p->sample_rate = sample_rate;
@@ -469,7 +634,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
         p->meta.wbase[s] = s < bm.n_slots ? bm.wbase[s] : 0;
     }
     const std::vector<float> win = half_hann_periodic(n_fft);
-    const std::vector<float> tw = twiddle_plane(n_fft, 32);
+    const std::vector<float> tw = p->variant == HMFE_VARIANT_PAIR ? twiddle_plane_paired(n_fft) : twiddle_plane(n_fft, 32);
     int rc = upload_vec(win, &p->d_win);
     if (rc == HMFE_OK) rc = upload_vec(tw, reinterpret_cast<float**>(&p->d_tw));
     if (rc == HMFE_OK) rc = upload_vec(bm.w, &p->d_melw);
@@ -609,7 +774,9 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64
         }
         HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
     }
-    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st) : launch_power<float, 8, 2>(p, b, st);
+    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
+             : p->variant == HMFE_VARIANT_PAIR ? launch_pair(p, b, st)
+                                               : launch_power<float, 8, 2>(p, b, st);
     if (rc != HMFE_OK) return rc;
     if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
     p->last_launches = 2;

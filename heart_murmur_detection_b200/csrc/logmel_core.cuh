@@ -139,4 +139,95 @@ HMFE_HD void mel_slot(int lane, const xelem<V>* __restrict__ ptile, const float*
     acc_b = vadd(b0, b1);
 }
 
+// =====================================================================================
+// "pair" variant: ONE complex transform (two real frames) per warp iteration, with the packed
+// FP32 instructions applied across ELEMENTS instead of across transforms: register q holds the
+// elements at DIT positions q and q+16.  Stages M = 2..16 of the 32-point DIT act on the two
+// halves alike (= fft_dit<16, f32x2>), only the last stage combines the halves of a register.
+// Half the registers per warp of the "packed" variant (64 instead of 128 for the FFT data), so
+// twice as many warps fit on an SM to hide the shared-memory and dependency latencies.
+// =====================================================================================
+constexpr int kPStride = 34;             // exchange-plane row stride in floats (even: 8-byte row pairs)
+constexpr int kPlane = 32 * kPStride;    // floats per plane (re plane, im plane)
+
+template <int P>
+struct pair_last_stage {
+    static HMFE_HD void run(f32x2 (&re)[16], f32x2 (&im)[16]) {
+        butterfly<P, float>(re[P].x, im[P].x, re[P].y, im[P].y);  // positions P and P+16, twiddle exp(-2 pi i P / 32)
+        if constexpr (P + 1 < 16) pair_last_stage<P + 1>::run(re, im);
+    }
+};
+
+// in: register q = DIT positions (q, q+16) = input elements (2 brev4(q), 2 brev4(q) + 1); out: register p = bins (p, p+16)
+HMFE_HD void fft32_paired(f32x2 (&re)[16], f32x2 (&im)[16]) {
+    fft_dit<16, f32x2>(re, im);
+    pair_last_stage<0>::run(re, im);
+}
+
+// windowed samples of frame a (re) / frame b (im): `fetch(second, n)` returns sample n of the frame
+template <typename Fetch>
+HMFE_HD void pair_load_window(int lane, const float* __restrict__ win, Fetch fetch, f32x2 (&re)[16], f32x2 (&im)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = lane + 32 * (2 * brev(q, 4));
+        const float w0 = win[n], w1 = win[n + 32];
+        re[q] = vmul(f32x2{fetch(false, n), fetch(false, n + 32)}, f32x2{w0, w1});
+        im[q] = vmul(f32x2{fetch(true, n), fetch(true, n + 32)}, f32x2{w0, w1});
+    }
+}
+
+// plane[p*32 + lane] = (cos_p, cos_{p+16}, -sin_p, -sin_{p+16}) of 2 pi lane k2 / 1024
+HMFE_HD void pair_twiddle(int lane, const float4* __restrict__ plane, f32x2 (&re)[16], f32x2 (&im)[16]) {
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        const float4 w = plane[p * 32 + lane];
+        const f32x2 wr{w.x, w.y}, wi{w.z, w.w};
+        const f32x2 nr = vsub(vmul(re[p], wr), vmul(im[p], wi));
+        const f32x2 ni = vfma(re[p], wi, vmul(im[p], wr));
+        re[p] = nr;
+        im[p] = ni;
+    }
+}
+
+HMFE_HD void pair_exchange_store(int lane, float* __restrict__ pre, float* __restrict__ pim, const f32x2 (&re)[16],
+                                 const f32x2 (&im)[16]) {
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        pre[p * kPStride + lane] = re[p].x;
+        pre[(p + 16) * kPStride + lane] = re[p].y;
+        pim[p * kPStride + lane] = im[p].x;
+        pim[(p + 16) * kPStride + lane] = im[p].y;
+    }
+}
+// row `lane`, elements (2m, 2m+1) -> register q with m = brev4(q): one 8-byte load per plane
+HMFE_HD void pair_exchange_load(int lane, const float* __restrict__ pre, const float* __restrict__ pim, f32x2 (&re)[16],
+                                f32x2 (&im)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int c = 2 * brev(q, 4);
+        re[q] = *reinterpret_cast<const f32x2*>(pre + lane * kPStride + c);
+        im[q] = *reinterpret_cast<const f32x2*>(pim + lane * kPStride + c);
+    }
+}
+
+// value of Z at second-pass output index k1 (0..31) from the paired registers
+HMFE_HD float pair_get(const f32x2 (&v)[16], int k1) { return k1 < 16 ? v[k1].x : v[k1 - 16].y; }
+
+// mel for the two frames of an item at once: the power tile element (p_a, p_b) is one f32x2
+HMFE_HD void mel_slot_ab(int lane, const f32x2* __restrict__ ptile, const float* __restrict__ w, int start, int trip,
+                         f32x2& acc) {
+    f32x2 a0{}, a1{};
+    const f32x2* p = ptile + start;
+    const float* wl = w + lane;
+    for (int i = 0; i < trip; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const float w0 = wl[(i + j) * 32], w1 = wl[(i + j + 1) * 32];
+            a0 = vfmas(p[i + j], w0, a0);
+            a1 = vfmas(p[i + j + 1], w1, a1);
+        }
+    }
+    acc = vadd(a0, a1);
+}
+
 }  // namespace hmfe

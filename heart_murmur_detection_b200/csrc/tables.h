@@ -236,4 +236,19 @@ inline std::vector<float> twiddle_plane(int n, int n_k2) {
     return t;
 }
 
+// paired variant: plane[(p*32 + lane)*4 + {0,1,2,3}] = (cos_p, cos_{p+16}, -sin_p, -sin_{p+16}), k2 = p / p+16
+inline std::vector<float> twiddle_plane_paired(int n) {
+    std::vector<float> t((size_t)16 * 32 * 4);
+    for (int p = 0; p < 16; ++p)
+        for (int l = 0; l < 32; ++l) {
+            const double a0 = 2.0 * kPi * ((double)l * p) / n, a1 = 2.0 * kPi * ((double)l * (p + 16)) / n;
+            float* q = &t[((size_t)p * 32 + l) * 4];
+            q[0] = (float)cos(a0);
+            q[1] = (float)cos(a1);
+            q[2] = (float)(-sin(a0));
+            q[3] = (float)(-sin(a1));
+        }
+    return t;
+}
+
 }  // namespace hmfe

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import check
 
 OUT_MODES = {"normalised": 0, "db": 1, "power": 2}
-VARIANTS = {"auto": 0, "scalar": 1, "packed": 2}
+VARIANTS = {"auto": 0, "scalar": 1, "packed": 2, "pair": 3}
 
 
 def _stream_ptr(stream=None):

@@ -48,6 +48,7 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 #define HMFE_VARIANT_AUTO 0
 #define HMFE_VARIANT_SCALAR 1 /* one complex FFT (2 frames) per warp iteration            */
 #define HMFE_VARIANT_PACKED 2 /* two complex FFTs (4 frames), packed FP32 (FFMA2)          */
+#define HMFE_VARIANT_PAIR 3   /* one complex FFT, FFMA2 across element pairs, 20 warps / SM */
 
 /* n_fft must be 1024 (the only value the reference uses); n_mels a multiple of 32, <= 256. */
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,

@@ -16,7 +16,7 @@ def host_check():
     return build.build_host_check()
 
 
-@pytest.mark.parametrize("variant", ["scalar", "packed"])
+@pytest.mark.parametrize("variant", ["scalar", "packed", "pair"])
 def test_logmel_power_emulation(host_check, variant, tmp_path):
     from oracle import frontend as F
 

@@ -47,7 +47,7 @@ def _check(plan, clips, f_max=8000, hop=512):
         assert np.abs(n - norm).max() <= NORM_TOL
 
 
-@pytest.mark.parametrize("variant", ["scalar", "packed"])
+@pytest.mark.parametrize("variant", ["scalar", "packed", "pair"])
 def test_ragged_batch_matches_oracle(variant):
     from heart_murmur_detection_b200.frontend import LogMelPlan
 
@@ -57,7 +57,7 @@ def test_ragged_batch_matches_oracle(variant):
     _check(plan, clips)
 
 
-@pytest.mark.parametrize("variant", ["scalar", "packed"])
+@pytest.mark.parametrize("variant", ["scalar", "packed", "pair"])
 def test_uniform_batch_matches_oracle(variant):
     from heart_murmur_detection_b200.frontend import LogMelPlan
 
