@@ -41,17 +41,21 @@ WORKLOADS = {
     "c3": "Audio-MAE front-end: kaldi fbank 128 mel, 25 ms / 10 ms, 1000 clips x 10.24 s padded to [1024,128] "
           "(src/util.py:845-856, audioMAE/models_mae.py:1178-1181)",
 }
-DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000}
-CPU_SAMPLE = {"c1": 2048, "c2": 768, "c3": 2048}
+WORKLOADS["c2nf"] = ("OPERA-CT linear-probe front-end exactly as the reference's callers invoke it (no band-pass, SURVEY F4): "
+                     "silence trim + zero/tile pad to >=8 s + cut at 32 s + 64-mel log-spectrogram over 5272 ragged clips "
+                     "(model_util.py:161-163)")
+DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000, "c2nf": 5272}
+CPU_SAMPLE = {"c1": 2048, "c2": 768, "c3": 2048, "c2nf": 1024}
 C2_KW = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
+C2NF_KW = dict(input_sec=8, butterworth_filter=None, pad=True, types="zero", max_sec=32)
 
 # ----------------------------------------------------------------------------- CPU reference arm
 
 def _cpu_process(workload, x, F):
     if workload == "c1":
         return F.log_mel(x, f_max=8000).shape[0]
-    if workload == "c2":
-        out = F.entire_signal(x, spectrogram=True, **C2_KW)
+    if workload in ("c2", "c2nf"):
+        out = F.entire_signal(x, spectrogram=True, **(C2_KW if workload == "c2" else C2NF_KW))
         return 0 if out is None else out.shape[0]
     fb = F.kaldi_fbank_chunk(x)
     return 0 if fb is None else int(F.pad_to_model(fb.numpy()).shape[0])
@@ -93,7 +97,7 @@ def cpu_reference(workload: str, n_clips: int, repeats: int = 1):
     from heart_murmur_detection_b200 import synth
 
     cores = os.cpu_count() or 1
-    lens = synth.clip_lengths(workload, n_clips, seed=4321)
+    lens = synth.clip_lengths("c2" if workload == "c2nf" else workload, n_clips, seed=4321)
     ctx = mp.get_context("fork")
     barrier, queue = ctx.Barrier(cores), ctx.Queue()
     procs = [ctx.Process(target=_cpu_worker, args=(r, cores, workload, lens, repeats, barrier, queue)) for r in range(cores)]
@@ -257,7 +261,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n_clips = args.clips or DEFAULT_CLIPS[wl]
-    lens = synth.clip_lengths(wl, n_clips, seed=1234 + rank)
+    lens = synth.clip_lengths("c2" if wl == "c2nf" else wl, n_clips, seed=1234 + rank)
+    kw2 = C2NF_KW if wl == "c2nf" else C2_KW
     wav, off = synth.make_batch(lens, base_seed=10_000_000 * rank, device=dev)
     total_samples = int(off[-1])
     ctx = frontend.default_ctx()
@@ -275,14 +280,14 @@ def main():
         def step(out):
             lm_plan(wav, off, out=out)
             state.update(features=out, rows=out_rows, launches=lm_plan.last_launches)
-    elif wl == "c2":
-        probe = pipeline.entire_signal_batch(wav, off, spectrogram=True, **C2_KW)
+    elif wl in ("c2", "c2nf"):
+        probe = pipeline.entire_signal_batch(wav, off, spectrogram=True, **kw2)
         out_rows = int(probe.row_offsets[-1])
         work_buf = torch.empty(probe.chunks.work.numel(), dtype=torch.float32, device=dev)
         del probe
 
         def step(out):
-            res = pipeline.entire_signal_batch(wav, off, spectrogram=True, work=work_buf, out=out, **C2_KW)
+            res = pipeline.entire_signal_batch(wav, off, spectrogram=True, work=work_buf, out=out, **kw2)
             state.update(features=res.features, rows=int(res.row_offsets[-1]), launches=res.launches, res=res)
     else:
         out_rows = n_clips * 1024
@@ -291,7 +296,7 @@ def main():
             fb_plan(wav, off, rows_per_clip=1024, out=out)
             state.update(features=out, rows=out_rows, launches=fb_plan.last_launches)
 
-    if wl == "c2" and args.variant != "auto":  # make the pipeline pick the requested log-mel variant
+    if wl in ("c2", "c2nf") and args.variant != "auto":  # make the pipeline pick the requested log-mel variant
         frontend._plans[("logmel", torch.cuda.current_device(), 16000, 64, 50.0, 8000.0, 1024, 512, "auto")] = lm_plan
 
     n_cols = 128 if wl == "c3" else 64
@@ -398,8 +403,8 @@ def main():
         def e2e_step():
             if wl == "c1":
                 frontend.logmel_from_host(lm_plan, h_wav, off, h_out)
-            elif wl == "c2":
-                pipeline.entire_signal_from_host(h_wav, off, h_out, **C2_KW)
+            elif wl in ("c2", "c2nf"):
+                pipeline.entire_signal_from_host(h_wav, off, h_out, **kw2)
             else:
                 frontend.fbank_from_host(fb_plan, h_wav, off, h_out, rows_per_clip=1024)
             if world > 1 and peer_ag is not None:
@@ -425,17 +430,17 @@ def main():
         e2e = {"value": world * n_clips / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": total_samples * 4,
                "d2h_bytes_per_step": rows * n_cols * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": {"c1": "frontend.logmel_from_host", "c2": "pipeline.entire_signal_from_host",
-                       "c3": "frontend.fbank_from_host"}[wl]}
+                       "c2nf": "pipeline.entire_signal_from_host", "c3": "frontend.fbank_from_host"}[wl]}
         if True:  # same call with the 16-bit WAV payload as the host buffer (decoded on the device)
             h_pcm = torch.clamp(torch.round(h_wav * 32768.0), -32768, 32767).to(torch.int16).pin_memory()
-            ub = int((1 + np.maximum(np.diff(off), 8 * SR) // 512).sum()) if wl == "c2" else rows
+            ub = int((1 + np.maximum(np.diff(off), 8 * SR) // 512).sum()) if wl in ("c2", "c2nf") else rows
             h_out16 = torch.empty((ub, n_cols), dtype=torch.float32, pin_memory=True)
 
             def pcm_step():
                 if wl == "c1":
                     frontend.logmel_from_host(lm_plan, h_pcm, off, h_out16)
-                elif wl == "c2":
-                    pipeline.entire_signal_from_host(h_pcm, off, h_out16, **C2_KW)
+                elif wl in ("c2", "c2nf"):
+                    pipeline.entire_signal_from_host(h_pcm, off, h_out16, **kw2)
                 else:
                     frontend.fbank_from_host(fb_plan, h_pcm, off, h_out16, rows_per_clip=1024)
 
@@ -460,7 +465,7 @@ def main():
         hbm_peak, peak_src = peaks()
         # algorithmic bytes per launch of each kernel
         out_bytes = rows * n_cols * 4
-        if wl == "c2":
+        if wl in ("c2", "c2nf"):
             chunk_samples = int(state["res"].chunks.lengths.sum())
         else:
             chunk_samples = total_samples

@@ -52,6 +52,9 @@ hmfe_logmel_batch = _sig(
 hmfe_logmel_batch_views = _sig(
     "hmfe_logmel_batch_views", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
 )
+hmfe_logmel_batch_views2 = _sig(
+    "hmfe_logmel_batch_views2", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
+)
 hmfe_logmel_last_launches = _sig("hmfe_logmel_last_launches", C.c_int, c_voidp)
 hmfe_logmel_set_profile = _sig("hmfe_logmel_set_profile", C.c_int, c_voidp, C.c_int)
 hmfe_logmel_profile_ms = _sig(

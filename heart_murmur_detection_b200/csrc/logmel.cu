@@ -25,6 +25,7 @@ struct MelMeta {
 
 struct LogmelBatch {
     const float* wav;
+    const float* wav_alt;        // second sample buffer: clips with a negative start s live at wav_alt[-s - 1]
     float* out;
     const int64_t* clip_start;   // [n_clips] ragged only: first sample of each clip in wav
     const int64_t* clip_len;     // [n_clips] ragged only
@@ -97,7 +98,8 @@ HMFE_D ItemCtx locate_item(const LogmelBatch& b, int n_mels, int64_t item, int64
         c.nsamp = (int)b.clip_len[clip];
         const int64_t f0g = b.frame_off[clip];
         c.T = (int)(b.frame_off[clip + 1] - f0g);
-        c.x = b.wav + b.clip_start[clip];
+        const int64_t s0 = b.clip_start[clip];
+        c.x = s0 >= 0 ? b.wav + s0 : b.wav_alt + (-s0 - 1);
         c.o = b.out + f0g * n_mels;
     }
     c.clip = clip;
@@ -699,6 +701,11 @@ int hmfe_logmel_profile_ms(hmfe_logmel_plan* p, double* power_ms, double* finali
 
 int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_starts, const int64_t* h_lengths,
                             int64_t n_clips, float* d_out, int out_mode, void* stream) {
+    return hmfe_logmel_batch_views2(p, d_wav, nullptr, h_starts, h_lengths, n_clips, d_out, out_mode, stream);
+}
+
+int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const float* d_wav_alt, const int64_t* h_starts,
+                             const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream) {
     HMFE_REQUIRE(p && h_starts && h_lengths, "NULL argument");
     HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
     HMFE_REQUIRE(out_mode >= 0 && out_mode <= 2, "bad out_mode %d", out_mode);
@@ -713,13 +720,15 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* p, const float* d_wav, const int64
     const int64_t n0 = h_lengths[0];
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t n = h_lengths[i];
-        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30 && h_starts[i] >= 0, "clip %lld has invalid start/length %lld/%lld",
+        HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30 && (h_starts[i] >= 0 || d_wav_alt != nullptr),
+                     "clip %lld has invalid start/length %lld/%lld",
                      (long long)i, (long long)h_starts[i], (long long)n);
         uniform = uniform && n == n0 && h_starts[i] == i * n0;
     }
 
     LogmelBatch b{};
     b.wav = d_wav;
+    b.wav_alt = d_wav_alt;
     b.out = d_out;
     b.n_clips = n_clips;
     b.hop = p->hop;

@@ -8,6 +8,7 @@
 
 #include "api_common.h"
 #include "ctx.h"
+#include "trim_common.cuh"
 
 namespace hmfe {
 
@@ -123,6 +124,61 @@ __global__ void __launch_bounds__(256) trim_index_kernel(const TrimBatch b) {
             b.start_end[2 * clip + 1] = en;
         }
         __syncthreads();
+    }
+}
+
+// frame_length == 2 * hop (the reference's 1600 / 800): every sample is read ONCE into per-hop energy sums
+// e_h = sum x^2 over [h*hop, (h+1)*hop); frame t is (e_{t-1} + e_t) / frame_length (trim_index_hop_kernel).
+// One warp per hop block.
+struct HopEnergyBatch {
+    const float* wav;
+    const int64_t* clip_off;  // [n_clips+1]
+    const int64_t* hop_off;   // [n_clips+1]
+    float* energy;            // [total hop blocks]
+    int64_t n_clips, n_blocks_total;
+    int hop;
+};
+
+__global__ void __launch_bounds__(256) hop_energy_kernel(const HopEnergyBatch b) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t per = (b.n_blocks_total + n_warps - 1) / n_warps;
+    const int64_t h_begin = warp_global * per, h_end = min(b.n_blocks_total, h_begin + per);
+    if (h_begin >= h_end) return;
+    int64_t lo = 0, hi = b.n_clips;  // largest clip with hop_off[clip] <= h_begin
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (b.hop_off[mid] <= h_begin)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    int64_t clip = lo;
+    for (int64_t h = h_begin; h < h_end; ++h) {
+        while (h >= b.hop_off[clip + 1]) ++clip;
+        const int64_t c0 = b.clip_off[clip];
+        const int n = (int)(b.clip_off[clip + 1] - c0);
+        const int s0 = (int)(h - b.hop_off[clip]) * b.hop;
+        const int len = min(b.hop, n - s0);
+        const float* x = b.wav + c0 + s0;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int i = lane;
+        for (; i + 96 < len; i += 128) {  // four independent loads in flight
+            const float v0 = __ldg(x + i), v1 = __ldg(x + i + 32), v2 = __ldg(x + i + 64), v3 = __ldg(x + i + 96);
+            a0 = fmaf(v0, v0, a0);
+            a1 = fmaf(v1, v1, a1);
+            a2 = fmaf(v2, v2, a2);
+            a3 = fmaf(v3, v3, a3);
+        }
+        for (; i < len; i += 32) {
+            const float v = __ldg(x + i);
+            a0 = fmaf(v, v, a0);
+        }
+        float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) b.energy[h] = acc;
     }
 }
 
@@ -312,29 +368,53 @@ int hmfe_trim_batch(hmfe_ctx* ctx, const float* d_wav, const int64_t* h_offsets,
     if (slot < 0) return slot;
     int64_t* hc = static_cast<int64_t*>(hbuf);
     int64_t* hf = hc + (n_clips + 1);
+    const bool by_hop = frame_length == 2 * hop_length;  // every sample read once (hop energies) instead of twice (frames)
     hf[0] = 0;
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t n = h_offsets[i + 1] - h_offsets[i];
         HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30, "clip %lld has invalid length %lld", (long long)i, (long long)n);
         hc[i] = h_offsets[i];
-        hf[i + 1] = hf[i] + hmfe_trim_num_frames(n, frame_length, hop_length);
+        hf[i + 1] = hf[i] + (by_hop ? (n + hop_length - 1) / hop_length : hmfe_trim_num_frames(n, frame_length, hop_length));
     }
     hc[n_clips] = h_offsets[n_clips];
     int rc = ctx->ring.upload(slot, desc_bytes, st);
     if (rc != HMFE_OK) return rc;
+    const int64_t* d_clip_off = static_cast<int64_t*>(dbuf);
+    const int64_t* d_unit_off = d_clip_off + (n_clips + 1);
+    const int64_t n_units = hf[n_clips];
+    rc = ctx->reserve_scratch((size_t)std::max<int64_t>(1, n_units) * sizeof(float));
+    if (rc != HMFE_OK) return rc;
+    float* d_units = static_cast<float*>(ctx->scratch);
+    const int index_grid = (int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8);
+    if (by_hop) {
+        if (n_units > 0) {
+            HopEnergyBatch hb{d_wav, d_clip_off, d_unit_off, d_units, n_clips, n_units, hop_length};
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_units + 7) / 8, (int64_t)ctx->sm_count * 8));
+            ctx->prof_begin(HMFE_K_TRIM_POWER, st);
+            hop_energy_kernel<<<grid, 256, 0, st>>>(hb);
+            HMFE_CHECK_CUDA(cudaGetLastError());
+            ctx->prof_end(st);
+            ctx->last_launches++;
+        }
+        TrimHopBatch tb{d_units, d_clip_off, d_unit_off, d_start_end, n_clips, hop_length, top_db};
+        ctx->prof_begin(HMFE_K_TRIM_INDEX, st);
+        trim_index_hop_kernel<<<index_grid, 256, 0, st>>>(tb);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        ctx->prof_end(st);
+        ctx->last_launches++;
+        return ctx->ring.release(slot, st);
+    }
     TrimBatch b{};
     b.wav = d_wav;
-    b.clip_off = static_cast<int64_t*>(dbuf);
-    b.frame_off = b.clip_off + (n_clips + 1);
+    b.clip_off = d_clip_off;
+    b.frame_off = d_unit_off;
     b.n_clips = n_clips;
-    b.n_frames_total = hf[n_clips];
+    b.n_frames_total = n_units;
     b.frame_length = frame_length;
     b.hop = hop_length;
     b.top_db = top_db;
     b.start_end = d_start_end;
-    rc = ctx->reserve_scratch((size_t)std::max<int64_t>(1, b.n_frames_total) * sizeof(float));
-    if (rc != HMFE_OK) return rc;
-    b.power = static_cast<float*>(ctx->scratch);
+    b.power = d_units;
     if (b.n_frames_total > 0) {
         const int64_t warps_wanted = b.n_frames_total;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_wanted + 7) / 8, (int64_t)ctx->sm_count * 8));
@@ -345,7 +425,7 @@ int hmfe_trim_batch(hmfe_ctx* ctx, const float* d_wav, const int64_t* h_offsets,
         ctx->last_launches++;
     }
     ctx->prof_begin(HMFE_K_TRIM_INDEX, st);
-    trim_index_kernel<<<(int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(b);
+    trim_index_kernel<<<index_grid, 256, 0, st>>>(b);
     HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->prof_end(st);
     ctx->last_launches++;

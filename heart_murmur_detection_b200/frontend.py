@@ -647,9 +647,12 @@ def resample_plan(orig_freq, new_freq=16000, **kw) -> ResamplePlan:
         return p
 
 
-def logmel_views(plan: LogMelPlan, wav: torch.Tensor, starts, lengths, out=None, mode="normalised", stream=None):
-    """Log-mel of the clips wav[starts[i] : starts[i]+lengths[i]].  Returns (out, frame_offsets)."""
+def logmel_views(plan: LogMelPlan, wav: torch.Tensor, starts, lengths, out=None, mode="normalised", stream=None, alt=None):
+    """Log-mel of the clips wav[starts[i] : starts[i]+lengths[i]]; with ``alt`` given, a negative start s
+    selects alt[-s-1 : -s-1+length] (padded copies kept apart from the signal).  Returns (out, frame_offsets)."""
     _require_cuda_f32(wav, "wav")
+    if alt is not None:
+        _require_cuda_f32(alt, "alt")
     st = np.ascontiguousarray(starts, dtype=np.int64)
     ln = np.ascontiguousarray(lengths, dtype=np.int64)
     fo = np.zeros(len(ln) + 1, dtype=np.int64)
@@ -658,10 +661,11 @@ def logmel_views(plan: LogMelPlan, wav: torch.Tensor, starts, lengths, out=None,
         out = torch.empty((int(fo[-1]), plan.n_mels), dtype=torch.float32, device=wav.device)
     with torch.cuda.device(wav.device):
         check(
-            _lib.hmfe_logmel_batch_views(plan._h, C.c_void_p(wav.data_ptr()), st.ctypes.data_as(C.c_void_p),
-                                         ln.ctypes.data_as(C.c_void_p), len(ln), C.c_void_p(out.data_ptr()),
-                                         OUT_MODES[mode], _stream_ptr(stream)),
-            "hmfe_logmel_batch_views",
+            _lib.hmfe_logmel_batch_views2(plan._h, C.c_void_p(wav.data_ptr()),
+                                          C.c_void_p(alt.data_ptr()) if alt is not None else C.c_void_p(),
+                                          st.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p), len(ln),
+                                          C.c_void_p(out.data_ptr()), OUT_MODES[mode], _stream_ptr(stream)),
+            "hmfe_logmel_batch_views2",
         )
     return out, fo
 

@@ -38,6 +38,12 @@ class ChunkBatch:
     launches: int = 0
     is_view: np.ndarray | None = None   # [n_chunks] True for straight views (no padding applied)
     filtered: bool = False              # band-pass applied (the reference's data is float64 then)
+    alt: torch.Tensor | None = None     # padded copies kept apart from a read-only signal: start s < 0 -> alt[-s-1:]
+
+    def samples(self, k: int) -> torch.Tensor:
+        """Device view of chunk k."""
+        s, n = int(self.starts[k]), int(self.lengths[k])
+        return self.work[s : s + n] if s >= 0 else self.alt[-s - 1 : -s - 1 + n]
 
     def ref_dtype(self, k: int):
         """dtype the reference produces for chunk k: float64 for untouched views of band-passed
@@ -162,7 +168,7 @@ def log_mel_features(cb: ChunkBatch, f_max=8000, n_mels=64, f_min=50, nfft=1024,
         return FeatureBatch(torch.empty((0, n_mels), device=cb.work.device), np.zeros(1, np.int64), cb, cb.launches)
     if out is not None and out.numel() < int((1 + cb.lengths // hop).sum()) * n_mels:
         out = None  # caller's buffer is too small for this batch: allocate
-    out, fo = fe.logmel_views(plan, cb.work, cb.starts, cb.lengths, mode=mode, out=out)
+    out, fo = fe.logmel_views(plan, cb.work, cb.starts, cb.lengths, mode=mode, out=out, alt=cb.alt)
     return FeatureBatch(out, fo, cb, cb.launches + plan.last_launches)
 
 
@@ -198,11 +204,13 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
     lens = np.diff(o)
     spare = L * (int((lens < L).sum()) + 16) if pad else 0
     frame_len = int(sample_rate / 10)
+    alt, pad_buf = None, None
     if sos is not None:  # band-pass and the trim of the filtered signal in one call
         if work is None or work.numel() < total:  # a caller-provided work buffer is reused across calls
             work = torch.empty(total + spare, dtype=torch.float32, device=wav.device)
         _, se = fe.iir_sos_trim(wav, o, sos, out=work, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     else:
+        pad_buf = work if (work is not None and work.data_ptr() != wav.data_ptr()) else None  # caller's scratch for the padded copies
         work = wav
         se = fe.trim_indices(work, o, frame_length=frame_len, hop_length=int(frame_len / 2), ctx=ctx)
     launches += ctx.last_launches
@@ -243,18 +251,22 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
             d["b_end"] = L
             dup = True
         need = total + L * padded.size
-        if need > work.numel():
-            bigger = torch.empty(need, dtype=torch.float32, device=work.device)
-            bigger[:total].copy_(work[:total])
-            work = bigger
-        fe.gather(work, work, d, ctx=ctx)
+        if need <= work.numel():  # spare capacity behind the signal (band-passed copy or a caller's roomy buffer)
+            fe.gather(work, work, d, ctx=ctx)
+            starts[padded] = d["dst_off"]
+        else:  # read-only signal without room: padded copies go to their own buffer, addressed by negative starts
+            if pad_buf is None or pad_buf.numel() < L * padded.size:
+                pad_buf = torch.empty(L * padded.size, dtype=torch.float32, device=work.device)
+            d["dst_off"] -= total
+            fe.gather(work, pad_buf, d, ctx=ctx)
+            alt = pad_buf
+            starts[padded] = -(d["dst_off"] + 1)
         launches += ctx.last_launches
-        starts[padded] = d["dst_off"]
         lengths[padded] = L
         is_view[padded] = False
     keep = np.flatnonzero(valid)
     return ChunkBatch(work, starts[keep], lengths[keep], keep.astype(np.int64), n_clips, valid, se, dup, launches,
-                      is_view[keep], sos is not None)
+                      is_view[keep], sos is not None, alt)
 
 
 def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,

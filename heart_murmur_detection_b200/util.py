@@ -121,10 +121,7 @@ def pre_process_audio_mel_t(audio, sample_rate=16000, n_mels=64, f_min=50, f_max
 
 
 def _chunks_to_numpy(cb: pl.ChunkBatch):
-    out = []
-    for s, n in zip(cb.starts, cb.lengths):
-        out.append(cb.work[int(s) : int(s) + int(n)].cpu().numpy())
-    return out
+    return [cb.samples(k).cpu().numpy() for k in range(len(cb.starts))]
 
 
 def split_pad_sample(sample, desired_length, sample_rate, types="repeat"):

@@ -64,6 +64,10 @@ int hmfe_logmel_batch(hmfe_logmel_plan* plan, const float* d_wav, const int64_t*
  * or leave gaps: trimmed recordings, 50 %-overlap chunks and padded copies are all views) */
 int hmfe_logmel_batch_views(hmfe_logmel_plan* plan, const float* d_wav, const int64_t* h_starts,
                             const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream);
+/* same with a second sample buffer: a clip with a negative start s is the view
+ * d_wav_alt[-s - 1 : -s - 1 + length] (padded copies kept apart from a read-only signal buffer) */
+int hmfe_logmel_batch_views2(hmfe_logmel_plan* plan, const float* d_wav, const float* d_wav_alt, const int64_t* h_starts,
+                             const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream);
 /* number of kernel launches the last hmfe_logmel_batch call on this plan issued */
 int hmfe_logmel_last_launches(const hmfe_logmel_plan* plan);
 /* Measurement hook: when enabled, every hmfe_logmel_batch call records CUDA events on its
