@@ -131,9 +131,15 @@ HMFE_D void fb_load_span(const FbItem& c, int lane, float (&raw)[kFbSpanRegs]) {
     }
 }
 
-template <bool FAST>
+// CUSTOM = false: Kaldi's switches (DC removal, pre-emphasis, power, log floor) are compile-time facts;
+// CUSTOM = true: they come from the plan (hmfe_fbank_plan_create_custom).
+template <bool FAST, bool CUSTOM>
 __global__ void __launch_bounds__(kFbWarps * 32, 2)
 fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
+    const bool remove_dc = CUSTOM ? (mm.flags & HMFE_FB_REMOVE_DC) != 0 : true;
+    const bool use_preemph = CUSTOM ? mm.preemph != 0.0f : true;
+    const bool magnitude = CUSTOM ? (mm.flags & HMFE_FB_MAGNITUDE) != 0 : false;
+    const bool log_offset = CUSTOM ? (mm.flags & HMFE_FB_LOG_OFFSET) != 0 : false;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* s_tw = reinterpret_cast<float2*>(smem);                   // 512
     float* s_win = reinterpret_cast<float*>(s_tw + 512);              // 512 (zero padded)
@@ -195,7 +201,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
             // d[j] = x[i] - preemph * x[i-1] over the span (frame independent), then per frame
             // (x[n] - mean) - preemph * (x[n-1] - mean) = d - (1 - preemph) * mean
             float mean[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (mm.flags & HMFE_FB_REMOVE_DC) {
+            if (remove_dc) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     float acc = 0.0f;
@@ -209,7 +215,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
             }
             const float x0[4] = {raw[0], raw[5], raw[10], raw[15]};  // first sample of each frame (lane 0)
             const float cm = 1.0f - mm.preemph;
-            if (mm.preemph != 0.0f) {
+            if (use_preemph) {
                 float prev_row = 0.0f;  // raw[j-1] of this lane
 #pragma unroll
                 for (int j = 0; j < kFbSpanRegs; ++j) {
@@ -261,7 +267,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                mean[t] = (mm.flags & HMFE_FB_REMOVE_DC) ? acc / (float)mm.win : 0.0f;
+                mean[t] = remove_dc ? acc / (float)mm.win : 0.0f;
             }
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
@@ -319,7 +325,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 const float give_i = k2 == 0 ? zi[(32 - k1) & 31] : zi[31 - k1];
                 const float pr = __shfl_sync(0xffffffffu, give_r, src), pi = __shfl_sync(0xffffffffu, give_i, src);
                 xelem<float> pw = frame_powers<float>(zr[k1], zi[k1], pr, pi);
-                if (mm.flags & HMFE_FB_MAGNITUDE) {
+                if (magnitude) {
                     pw.a = sqrtf(pw.a);
                     pw.b = sqrtf(pw.b);
                 }
@@ -327,7 +333,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
             }
             if (k2 == 0) {
                 xelem<float> pw = frame_powers<float>(zr[16], zi[16], zr[16], zi[16]);
-                if (mm.flags & HMFE_FB_MAGNITUDE) {
+                if (magnitude) {
                     pw.a = sqrtf(pw.a);
                     pw.b = sqrtf(pw.b);
                 }
@@ -367,8 +373,7 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                     if (f0 + t < m)
-                        o[(int64_t)(f0 + t) * mm.n_mels + row] =
-                            (mm.flags & HMFE_FB_LOG_OFFSET) ? logf(acc[t] + mm.log_offset) : logf(fmaxf(acc[t], FLT_EPSILON));
+                        o[(int64_t)(f0 + t) * mm.n_mels + row] = logf(log_offset ? acc[t] + mm.log_offset : fmaxf(acc[t], FLT_EPSILON));
             }
         }
         __syncwarp();
@@ -625,7 +630,9 @@ int hmfe_fbank_batch_views(hmfe_fbank_plan* p, const float* d_wav, const int64_t
         FbMeta mm = p->meta;
         const size_t smem = p->table_smem + (size_t)kFbWarps * 32 * kXStride * sizeof(xelem<float>);
         const bool fast = p->win == 400 && p->shift == 160;
-        auto kern = fast ? fbank_kernel<true> : fbank_kernel<false>;
+        const bool custom = p->meta.flags != HMFE_FB_REMOVE_DC || p->meta.preemph == 0.0f;
+        auto kern = fast ? (custom ? fbank_kernel<true, true> : fbank_kernel<true, false>)
+                         : (custom ? fbank_kernel<false, true> : fbank_kernel<false, false>);
         HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t want = (b.n_items + kFbWarps - 1) / kFbWarps;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count * 2));

@@ -6,7 +6,7 @@ T=${TAG:-r01}
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$T.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$T.log
 timeout 900 python bench.py > gpurun_out/BENCH_$T.json 2> gpurun_out/BENCH_$T.err; echo "bench rc=$?"
 timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/BENCH_${T}_reference.json 2> gpurun_out/BENCH_${T}_reference.err; echo "ref rc=$?"
-for w in c1 c3; do
+for w in c1 c3 c2nf; do
   timeout 900 python bench.py --workload $w > gpurun_out/BENCH_${T}_$w.json 2> gpurun_out/BENCH_${T}_$w.err; echo "bench $w rc=$?"
 done
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
