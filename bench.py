@@ -315,7 +315,13 @@ def main():
         from heart_murmur_detection_b200.dist import PeerAllGather
 
         # kernels write straight into this rank's slot of the gathered buffer
-        peer_ag = PeerAllGather(max_rows, n_cols, mode=args.gather, push_ctas=args.push_ctas)
+        try:
+            peer_ag = PeerAllGather(max_rows, n_cols, mode=args.gather, push_ctas=args.push_ctas)
+        except Exception as e:  # no symmetric memory on this box: the NCCL collective is always available
+            if rank == 0:
+                print(f"bench: peer-memory all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            peer_ag, args.gather = None, "nccl"
+    if peer_ag is not None:
         send = [peer_ag.slot(0), peer_ag.slot(1)]
         comm = peer_ag.comm
     else:
