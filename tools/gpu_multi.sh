@@ -12,6 +12,4 @@ for line in open('gpurun_out/scale_n${n}_$tag.json'):
 PY
 }
 N=${N:-2}
-run $N copy --gather copy ${EXTRA}
-run $N nccl --gather nccl ${EXTRA}
-run $N multicast --gather multicast ${EXTRA}
+run $N auto --gather auto ${EXTRA}
