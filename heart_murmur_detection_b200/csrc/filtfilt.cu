@@ -61,12 +61,12 @@ __global__ void __launch_bounds__(256) odd_ext_kernel(const float* __restrict__ 
 // y[n] += first * h[n] for the first `len` samples of every extended clip (first = ext[0] of the pass input)
 __global__ void __launch_bounds__(256) add_zi_response_kernel(double* __restrict__ y, const float* __restrict__ pass_in,
                                                               const double* __restrict__ h, int len, const FiltfiltBatch b) {
-    const int64_t c = blockIdx.y;
-    const int64_t e0 = b.ext_off[c], ne = b.ext_off[c + 1] - e0;
-    const double first = (double)pass_in[e0];
-    const int64_t m = min((int64_t)len, ne);
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < m; n += (int64_t)gridDim.x * blockDim.x)
-        y[e0 + n] = fma(first, h[n], y[e0 + n]);
+    for (int64_t c = blockIdx.x; c < b.n_clips; c += gridDim.x) {  // one CTA per clip
+        const int64_t e0 = b.ext_off[c], ne = b.ext_off[c + 1] - e0;
+        const double first = (double)pass_in[e0];
+        const int64_t m = min((int64_t)len, ne);
+        for (int64_t n = threadIdx.x; n < m; n += blockDim.x) y[e0 + n] = fma(first, h[n], y[e0 + n]);
+    }
 }
 
 // out32[k] = (float) y[ne - 1 - k] per extended clip
@@ -195,8 +195,7 @@ extern "C" int hmfe_sosfiltfilt_batch(hmfe_ctx* ctx, const float* d_x, const int
     double* pass_out = reinterpret_cast<double*>(ws + ((total_ext * 4 + 255) & ~(int64_t)255));
     const float* x0 = d_x + h_offsets[0];
     const int grid = (int)std::min<int64_t>((total_ext + 255) / 256, (int64_t)ctx->sm_count * 16);
-    const dim3 zi_grid((unsigned)std::min<size_t>((h.size() + 255) / 256, 64), (unsigned)n_clips);
-    HMFE_REQUIRE(n_clips <= 65535, "more than 65535 clips per call are not supported by the zero-phase mode");
+    const int zi_grid = (int)std::min<int64_t>(n_clips, (int64_t)ctx->sm_count * 16);
 
     odd_ext_kernel<<<grid, 256, 0, st>>>(x0, pass_in, b, total_ext);
     HMFE_CHECK_CUDA(cudaGetLastError());
