@@ -164,6 +164,30 @@ def test_logmel_vs_torchaudio(store):
         assert np.abs(db - dbt).max() <= 1e-2
 
 
+def test_librosa_restatement_vs_transformers_audio_utils(store):
+    """Second independent check of the (unpinned) librosa restatement: transformers.audio_utils is a
+    numpy re-implementation of librosa's mel filter bank / STFT / power_to_db that its own test-suite
+    pins against librosa outputs.  float64 throughout, so the agreement is tighter than with torchaudio."""
+    au = pytest.importorskip("transformers.audio_utils")
+    for fmax in (8000.0, 2000.0):
+        fb = au.mel_filter_bank(513, 64, 50.0, fmax, 16000, norm="slaney", mel_scale="slaney").T
+        ours = lr.mel_filterbank(16000, 1024, n_mels=64, fmin=50, fmax=fmax)
+        assert np.abs(ours - fb).max() <= 1e-6 * ours.max()
+        np.testing.assert_array_equal(ours == 0, fb == 0)
+    fb = au.mel_filter_bank(513, 64, 50.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+    win = au.window_function(1024, "hann", periodic=True)
+    np.testing.assert_allclose(win, lr.hann_periodic(1024), rtol=0, atol=1e-15)
+    for name in ("r_mid", "r_8s", "r_short"):
+        x = store[name]
+        _, db, S = F.log_mel(x, f_max=8000, return_parts=True)
+        St = au.spectrogram(x, win, frame_length=1024, hop_length=512, fft_length=1024, power=2.0, center=True,
+                            pad_mode="constant", mel_filters=fb, mel_floor=0.0).T
+        assert S.shape == St.shape == (1 + len(x) // 512, 64)
+        assert np.abs(S - St).max() <= 1e-5 * np.abs(S).max()
+        dbt = au.power_to_db(St, reference=float(St.max()), min_value=1e-10, db_range=80.0)
+        assert np.abs(db - dbt).max() <= 1e-3  # dB
+
+
 def test_frame_counts():
     for n in (1, 511, 512, 513, 32000, 65440, 128000, 130880, 512000):
         T = F.log_mel(golden_signal(n, 1), f_max=8000).shape[0]
