@@ -44,6 +44,7 @@ hmfe_logmel_plan_create = _sig(
     C.c_int,
 )
 hmfe_logmel_plan_destroy = _sig("hmfe_logmel_plan_destroy", None, c_voidp)
+hmfe_logmel_plan_set_pad_mode = _sig("hmfe_logmel_plan_set_pad_mode", C.c_int, c_voidp, C.c_int)
 hmfe_logmel_num_frames = _sig("hmfe_logmel_num_frames", C.c_int64, C.c_int64, C.c_int)
 hmfe_logmel_mel_basis = _sig("hmfe_logmel_mel_basis", C.c_int, c_voidp, c_voidp)
 hmfe_logmel_batch = _sig(
@@ -161,6 +162,22 @@ hmfe_htsat_input_batch = _sig(
     "hmfe_htsat_input_batch", C.c_int, c_voidp, c_voidp, C.c_int, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp, C.c_int,
     c_voidp, c_voidp,
 )
+
+hmfe_hear_plan_create = _sig(
+    "hmfe_hear_plan_create", C.c_int, C.POINTER(c_voidp), c_voidp, c_voidp, C.c_int, C.c_double, C.c_double, C.c_double,
+    C.c_double, C.c_double,
+)
+hmfe_hear_plan_destroy = _sig("hmfe_hear_plan_destroy", None, c_voidp)
+hmfe_hear_num_frames = _sig("hmfe_hear_num_frames", C.c_int, C.c_int)
+hmfe_hear_workspace_bytes = _sig("hmfe_hear_workspace_bytes", C.c_size_t, c_voidp, C.c_int64, C.c_int)
+hmfe_hear_mel_pcen_batch = _sig(
+    "hmfe_hear_mel_pcen_batch", C.c_int, c_voidp, c_voidp, C.c_int64, C.c_int, C.c_int, C.c_int, c_voidp, c_voidp, C.c_size_t,
+    c_voidp,
+)
+hmfe_hear_mel_batch = _sig(
+    "hmfe_hear_mel_batch", C.c_int, c_voidp, c_voidp, C.c_int64, C.c_int, C.c_int, c_voidp, c_voidp, C.c_size_t, c_voidp
+)
+hmfe_hear_last_launches = _sig("hmfe_hear_last_launches", C.c_int, c_voidp)
 
 
 def check(rc: int, what: str = "hmfe call"):

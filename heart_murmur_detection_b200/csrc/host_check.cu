@@ -8,6 +8,8 @@
 // (tests/test_host_emulation.py).  Test infrastructure, not part of libhmfe.so.
 //
 // usage: host_check logmel <scalar|packed|pair> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>
+//        host_check fbank <n_mels> <in.f32> <out.f32>
+//        host_check hear <n_samples> <n_padded> <out_rows> <audio.f32> <window.f32> <mel.f32> <out_mel.f32> <out_pcen.f32>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +19,7 @@
 
 #include <math.h>
 
+#include "hear_core.cuh"
 #include "logmel_core.cuh"
 #include "tables.h"
 
@@ -252,6 +255,103 @@ static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float
     }
 }
 
+// Mirrors hear_mel_kernel + hear_pcen_resize_kernel (hear_pcen.cu) lane for lane.  audio = [n_clips][n_samples],
+// window = [400], mel = [201][n_mels] (the reference's layout).
+static void run_hear(const std::vector<float>& audio, int n_samples, int n_padded, int out_rows, const std::vector<float>& window,
+                     const std::vector<float>& mel, std::vector<float>& out_mel, std::vector<float>& out_pcen) {
+    const int n_mels = (int)(mel.size() / kHearBins);
+    const int n_clips = n_samples > 0 ? (int)(audio.size() / n_samples) : 1;
+    const int T = (n_padded + kHearShift - 1) / kHearShift;
+    std::vector<float> dense((size_t)n_mels * kHearBins);
+    for (int k = 0; k < kHearBins; ++k)
+        for (int m = 0; m < n_mels; ++m) dense[(size_t)m * kHearBins + k] = mel[(size_t)k * n_mels + m];
+    const BandedMel bm = build_banded(dense, n_mels, kHearBins, 8, kHearPRows);
+    if (!verify_banded(bm, dense, kHearPRows)) {
+        fprintf(stderr, "banded mel verification failed\n");
+        exit(3);
+    }
+    std::vector<float> win(kHearN);
+    for (int n = 0; n < kHearN; ++n) win[n] = 0.5f * window[n];
+    std::vector<float2> plane(25 * 16);
+    for (int k1 = 0; k1 < 25; ++k1)
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const double a = 2.0 * kPi * (double)((n2 * k1) % kHearN) / (double)kHearN;
+            plane[k1 * 16 + n2] = make_float2((float)cos(a), (float)-sin(a));
+        }
+    float mn = n_samples < n_padded ? 0.0f : INFINITY, mx = n_samples < n_padded ? 0.0f : -INFINITY;
+    for (float v : audio) {
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    const HearScale sc = hear_make_scale(mn, mx);
+    out_mel.assign((size_t)n_clips * T * n_mels, 0.0f);
+    std::vector<float2> tile(2 * kHearXTile);
+    std::vector<xelem<f32x2>> ptile(kHearPRows);
+    float* pf = reinterpret_cast<float*>(ptile.data());
+    struct Z {
+        float zr[16], zi[16];
+    };
+    std::vector<Z> L(32);
+    for (int clip = 0; clip < n_clips; ++clip) {
+        const float* x = audio.data() + (size_t)clip * n_samples;
+        for (int f0 = 0; f0 < T; f0 += 4) {
+            auto fetch = [&](int tr, bool second, int n) -> float {
+                const int t = 2 * tr + (second ? 1 : 0);
+                if (f0 + t >= T) return 0.0f;
+                const int idx = (f0 + t) * kHearShift + n;
+                return idx < n_samples ? hear_scale(sc, x[idx]) : (idx < n_padded ? hear_scale(sc, 0.0f) : 0.0f);
+            };
+            for (int lane = 0; lane < 32; ++lane) hear_pass1(lane, win.data(), plane.data(), fetch, tile.data());
+            for (auto& e : ptile) e = xelem<f32x2>{};
+            for (int r = 0; r < 2; ++r) {
+                for (int lane = 0; lane < 25; ++lane) hear_pass2(lane, tile.data(), r, L[lane].zr, L[lane].zi);
+                for (int lane = 0; lane < 25; ++lane) {
+                    const int src = (25 - lane) % 25;
+                    for (int k2 = 0; k2 < 8; ++k2) {
+                        const int preg = hear_give_reg(src == 0, k2);
+                        const xelem<float> pw = frame_powers<float>(L[lane].zr[k2], L[lane].zi[k2], L[src].zr[preg], L[src].zi[preg]);
+                        const int k = lane + 25 * k2;
+                        pf[4 * k + r] = pw.a;
+                        pf[4 * k + 2 + r] = pw.b;
+                    }
+                }
+                const xelem<float> pw = frame_powers<float>(L[0].zr[8], L[0].zi[8], L[0].zr[8], L[0].zi[8]);
+                pf[4 * 200 + r] = pw.a;
+                pf[4 * 200 + 2 + r] = pw.b;
+            }
+            float* o = out_mel.data() + ((size_t)clip * T + f0) * n_mels;
+            for (int lane = 0; lane < 32; ++lane)
+                for (int s = 0; s < bm.n_slots; ++s) {
+                    f32x2 aa, ab;
+                    mel_slot<f32x2>(lane, ptile.data(), bm.w.data() + (size_t)bm.wbase[s] * 32, bm.start[s * 32 + lane], bm.trip[s],
+                                    aa, ab);
+                    const int row = bm.row[s * 32 + lane];
+                    if (row < 0) continue;
+                    if (f0 < T) o[row] = aa.x;
+                    if (f0 + 1 < T) o[n_mels + row] = ab.x;
+                    if (f0 + 2 < T) o[2 * n_mels + row] = aa.y;
+                    if (f0 + 3 < T) o[3 * n_mels + row] = ab.y;
+                }
+        }
+    }
+    PcenParams pp;
+    pp.alpha = 0.8f;
+    pp.c_in = 0.04f;
+    pp.c_state = (float)(1.0 - 0.04);
+    pp.delta = 2.0f;
+    pp.inv_root = 0.5f;
+    pp.floor = 1e-8f;
+    pp.delta_root = powf(2.0f, 0.5f);
+    out_pcen.assign((size_t)n_clips * out_rows * n_mels, 0.0f);
+    for (int clip = 0; clip < n_clips; ++clip)
+        for (int c = 0; c < n_mels; ++c) {
+            const float* xm = out_mel.data() + (size_t)clip * T * n_mels + c;
+            float* o = out_pcen.data() + (size_t)clip * out_rows * n_mels + c;
+            hear_pcen_column(pp, T, out_rows, [&](int t) { return xm[(size_t)t * n_mels]; },
+                             [&](int i, float v) { o[(size_t)i * n_mels] = v; });
+        }
+}
+
 static std::vector<float> read_f32(const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) {
@@ -297,6 +397,13 @@ int main(int argc, char** argv) {
         std::vector<float> out;
         run_fbank(x, atoi(argv[2]), out);
         write_f32(argv[4], out);
+        return 0;
+    }
+    if (argc >= 10 && !strcmp(argv[1], "hear")) {
+        std::vector<float> om, op;
+        run_hear(read_f32(argv[5]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), read_f32(argv[6]), read_f32(argv[7]), om, op);
+        write_f32(argv[8], om);
+        write_f32(argv[9], op);
         return 0;
     }
     fprintf(stderr, "usage: host_check logmel <scalar|packed|pair> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>\n");

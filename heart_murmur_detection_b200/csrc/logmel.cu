@@ -36,6 +36,7 @@ struct LogmelBatch {
     int64_t n_clips, n_items;
     int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
     int hop;
+    int reflect;     // 1: centre padding mirrors the clip (numpy 'reflect'), 0: zeros (librosa >= 0.10 default)
     int stagger_ns;  // start-up delay per warp index (HMFE_LOGMEL_STAGGER_NS overrides the default)
 };
 
@@ -109,7 +110,8 @@ HMFE_D ItemCtx locate_item(const LogmelBatch& b, int n_mels, int64_t item, int64
 
 // raw[t][h][n2] = sample (lane + 32*n2) of frame f0 + 2t + h (zero outside the clip / beyond T)
 template <int NV>
-HMFE_D void load_raw(const ItemCtx& c, int hop, int lane, float (&raw)[NV][2][32]) {
+HMFE_D void load_raw(const ItemCtx& c, const LogmelBatch& b, int lane, float (&raw)[NV][2][32]) {
+    const int hop = b.hop;
     int base[NV][2];
     bool interior = c.valid;
 #pragma unroll
@@ -137,8 +139,13 @@ HMFE_D void load_raw(const ItemCtx& c, int hop, int lane, float (&raw)[NV][2][32
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int n2 = 0; n2 < 32; ++n2) {
-                    const int i = base[t][h] + lane + 32 * n2;
-                    raw[t][h][n2] = (c.valid && i >= 0 && i < c.nsamp) ? __ldg(c.x + i) : 0.0f;
+                    int i = base[t][h] + lane + 32 * n2;
+                    if (b.reflect) {  // clips are longer than n_fft / 2 (checked on the host): one fold per side
+                        i = i < 0 ? -i : i;
+                        i = i >= c.nsamp ? 2 * (c.nsamp - 1) - i : i;
+                    }
+                    const bool ok = c.valid && c.f0 + 2 * t + h < c.T && i >= 0 && i < c.nsamp;
+                    raw[t][h][n2] = ok ? __ldg(c.x + i) : 0.0f;
                 }
     }
 }
@@ -212,7 +219,7 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     int64_t item = claim();
     blk_end = item + kItemBlock;
     ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
-    load_raw<NV>(cur, b.hop, lane, raw);
+    load_raw<NV>(cur, b, lane, raw);
 
     while (item < it_end) {
         V re[32], im[32];
@@ -258,7 +265,7 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
 
         item = next_item(item);
         const ItemCtx nxt = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
-        load_raw<NV>(nxt, b.hop, lane, raw);
+        load_raw<NV>(nxt, b, lane, raw);
 
         float vmax = 0.0f, vmin = INFINITY;
 #pragma unroll
@@ -362,7 +369,7 @@ logmel_power_pair_kernel(const LogmelBatch b, const LogmelTables tb, const MelMe
     int64_t item = claim();
     blk_end = item + kItemBlock;
     ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
-    load_raw<1>(cur, b.hop, lane, raw);
+    load_raw<1>(cur, b, lane, raw);
 
     while (item < it_end) {
         f32x2 re[16], im[16];
@@ -403,7 +410,7 @@ logmel_power_pair_kernel(const LogmelBatch b, const LogmelTables tb, const MelMe
 
         item = next_item(item);
         const ItemCtx nxt = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
-        load_raw<1>(nxt, b.hop, lane, raw);
+        load_raw<1>(nxt, b, lane, raw);
 
         float vmax = 0.0f, vmin = INFINITY;
 #pragma unroll
@@ -475,10 +482,12 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
             return r;
         };
-        const float ref_db = __fmul_rn(k10, lg2(fmaxf(amin, pmax)));
+        // HMFE_LOGMEL_OUT_DB_ABS: power_to_db(ref=1.0, top_db=None) = 10 log10(max(amin, S)), no clip-wide terms
+        const bool abs_db = out_mode == HMFE_LOGMEL_OUT_DB_ABS;
+        const float ref_db = abs_db ? 0.0f : __fmul_rn(k10, lg2(fmaxf(amin, pmax)));
         auto to_db = [&](float p) { return __fsub_rn(__fmul_rn(k10, lg2(fmaxf(amin, p))), ref_db); };
         const float smax = to_db(pmax);
-        const float floor_db = smax - top_db;
+        const float floor_db = abs_db ? -INFINITY : smax - top_db;
         const float smin = fmaxf(to_db(pmin), floor_db);
         const bool normalise = out_mode == HMFE_LOGMEL_OUT_NORMALISED && smax != smin;
         const float denom = normalise ? smax - smin : 1.0f;
@@ -523,6 +532,7 @@ using namespace hmfe;
 
 struct hmfe_logmel_plan {
     int sample_rate, n_fft, hop, n_mels, n_bins, variant;
+    int pad_mode = HMFE_PAD_CONSTANT;
     double f_min, f_max;
     std::vector<float> mel_dense;
     MelMeta meta;
@@ -663,6 +673,13 @@ void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
     delete p;
 }
 
+int hmfe_logmel_plan_set_pad_mode(hmfe_logmel_plan* p, int pad_mode) {
+    HMFE_REQUIRE(p, "NULL plan");
+    HMFE_REQUIRE(pad_mode == HMFE_PAD_CONSTANT || pad_mode == HMFE_PAD_REFLECT, "bad pad_mode %d", pad_mode);
+    p->pad_mode = pad_mode;
+    return HMFE_OK;
+}
+
 int64_t hmfe_logmel_num_frames(int64_t n_samples, int hop) { return hop > 0 && n_samples >= 0 ? 1 + n_samples / hop : -1; }
 
 int hmfe_logmel_mel_basis(const hmfe_logmel_plan* p, float* h_out) {
@@ -708,7 +725,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
                              const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream) {
     HMFE_REQUIRE(p && h_starts && h_lengths, "NULL argument");
     HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
-    HMFE_REQUIRE(out_mode >= 0 && out_mode <= 2, "bad out_mode %d", out_mode);
+    HMFE_REQUIRE(out_mode >= 0 && out_mode <= 3, "bad out_mode %d", out_mode);
     p->last_launches = 0;
     if (n_clips == 0) return HMFE_OK;
     HMFE_REQUIRE(d_wav && d_out, "NULL device pointer");
@@ -723,6 +740,9 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
         HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 30 && (h_starts[i] >= 0 || d_wav_alt != nullptr),
                      "clip %lld has invalid start/length %lld/%lld",
                      (long long)i, (long long)h_starts[i], (long long)n);
+        HMFE_REQUIRE(p->pad_mode != HMFE_PAD_REFLECT || n > p->n_fft / 2,
+                     "clip %lld: reflect padding needs more than n_fft/2 = %d samples, got %lld", (long long)i,
+                     p->n_fft / 2, (long long)n);
         uniform = uniform && n == n0 && h_starts[i] == i * n0;
     }
 
@@ -732,6 +752,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
     b.out = d_out;
     b.n_clips = n_clips;
     b.hop = p->hop;
+    b.reflect = p->pad_mode == HMFE_PAD_REFLECT ? 1 : 0;
     {
         const char* e = getenv("HMFE_LOGMEL_STAGGER_NS");
         b.stagger_ns = e ? atoi(e) : 500;  // measured on B200, c1: 0 -> 0.323 ms, 200 -> 0.308, 400..2000 -> 0.302-0.303

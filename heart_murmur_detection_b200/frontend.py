@@ -15,7 +15,8 @@ import torch
 from . import _lib
 from ._lib import check
 
-OUT_MODES = {"normalised": 0, "db": 1, "power": 2}
+OUT_MODES = {"normalised": 0, "db": 1, "power": 2, "db_abs": 3}
+PAD_MODES = {"constant": 0, "reflect": 1}
 VARIANTS = {"auto": 0, "scalar": 1, "packed": 2, "pair": 3}
 
 
@@ -40,7 +41,7 @@ class LogMelPlan:
     """Fused STFT-power + mel + dB/min-max for ragged batches (src/util.py:481-501)."""
 
     def __init__(self, sample_rate=16000, n_mels=64, f_min=50, f_max=2000, nfft=1024, hop=512, variant="auto",
-                 device=None):
+                 device=None, pad_mode="constant"):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.sample_rate, self.n_mels, self.nfft, self.hop = int(sample_rate), int(n_mels), int(nfft), int(hop)
         self.f_min, self.f_max = float(f_min), float(f_max)
@@ -51,6 +52,9 @@ class LogMelPlan:
                                              self.f_min, self.f_max, VARIANTS[variant]),
                 "hmfe_logmel_plan_create",
             )
+            self.pad_mode = pad_mode
+            if pad_mode != "constant":
+                check(_lib.hmfe_logmel_plan_set_pad_mode(self._h, PAD_MODES[pad_mode]), "hmfe_logmel_plan_set_pad_mode")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -109,13 +113,14 @@ _plans: dict = {}
 _plans_lock = threading.Lock()
 
 
-def logmel_plan(sample_rate=16000, n_mels=64, f_min=50, f_max=2000, nfft=1024, hop=512, variant="auto") -> LogMelPlan:
+def logmel_plan(sample_rate=16000, n_mels=64, f_min=50, f_max=2000, nfft=1024, hop=512, variant="auto",
+                pad_mode="constant") -> LogMelPlan:
     key = ("logmel", torch.cuda.current_device(), int(sample_rate), int(n_mels), float(f_min), float(f_max), int(nfft),
-           int(hop), variant)
+           int(hop), variant, pad_mode)
     with _plans_lock:
         p = _plans.get(key)
         if p is None:
-            p = _plans[key] = LogMelPlan(sample_rate, n_mels, f_min, f_max, nfft, hop, variant)
+            p = _plans[key] = LogMelPlan(sample_rate, n_mels, f_min, f_max, nfft, hop, variant, pad_mode=pad_mode)
         return p
 
 

@@ -44,6 +44,8 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 #define HMFE_LOGMEL_OUT_NORMALISED 0 /* reference output: dB min-max normalised to [0,1]   */
 #define HMFE_LOGMEL_OUT_DB 1         /* power_to_db(ref=max, top_db=80) before normalising  */
 #define HMFE_LOGMEL_OUT_POWER 2      /* mel power (linear)                                  */
+#define HMFE_LOGMEL_OUT_DB_ABS 3     /* 10 log10(max(1e-10, S)): power_to_db(ref=1.0, top_db=None), the torchlibrosa
+                                        LogmelFilterBank of the CLAP baseline (msclap/models/audio.py:146-175)    */
 
 #define HMFE_VARIANT_AUTO 0
 #define HMFE_VARIANT_SCALAR 1 /* one complex FFT (2 frames) per warp iteration            */
@@ -54,6 +56,12 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
                             double f_max, int variant);
 void hmfe_logmel_plan_destroy(hmfe_logmel_plan* plan);
+/* Centre padding of the STFT.  HMFE_PAD_CONSTANT (default): zeros, what librosa 0.10's melspectrogram does for
+ * src/util.py:484.  HMFE_PAD_REFLECT: numpy 'reflect' (torchlibrosa Spectrogram(pad_mode="reflect") of the CLAP
+ * baseline, msclap/models/audio.py:147,155-163); every clip must then be longer than n_fft / 2 samples. */
+#define HMFE_PAD_CONSTANT 0
+#define HMFE_PAD_REFLECT 1
+int hmfe_logmel_plan_set_pad_mode(hmfe_logmel_plan* plan, int pad_mode);
 /* frames librosa produces for a clip of n samples (centre=True): 1 + n / hop */
 int64_t hmfe_logmel_num_frames(int64_t n_samples, int hop);
 /* copies the float32 mel basis [n_mels][n_fft/2+1] the plan uses to host memory (tests) */
@@ -276,6 +284,32 @@ int hmfe_multicast_push(const float* d_src, float* mc_dst, int64_t n, int n_ctas
 int hmfe_htsat_input_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const int64_t* h_src_row,
                            const int32_t* h_n_rows, int64_t n_items, const float* h_scale, const float* h_shift,
                            int spec_size, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HeAR mel-PCEN front-end (sibling front-end of the thesis baselines): replaces preprocess_audio
+ * (src/benchmark/baseline/hear/python/data_processing/audio_utils.py:448-476): batch-wide min / max
+ * scaling to [-1, 1] (:361-365), 400-sample frames every 160 samples with a 400-POINT FFT and end
+ * padding (:367-378, _compute_stft :22-115), |X|^2 @ mel[201][n_mels] (:379-382), PCEN with its EMA
+ * smoother (:121-246), bilinear resize of the frame axis to out_rows (:386-445, :475).
+ * d_audio is [n_clips][n_samples] float32; clips shorter than n_padded (32000 in the reference,
+ * :466-468) are treated as zero padded BEFORE the scaling, as the reference does.
+ * h_window [400] and h_mel [201][n_mels] (the reference's torch.hann_window(400) and
+ * _linear_to_mel_weight_matrix(), :264-358) come from the caller; n_mels a multiple of 32, <= 128.
+ * The workspace holds the mel power [n_clips][frames][n_mels] (+16 bytes), frames = ceil(n_padded/160).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hmfe_hear_plan hmfe_hear_plan;
+int hmfe_hear_plan_create(hmfe_hear_plan** plan, const float* h_window, const float* h_mel, int n_mels, double alpha,
+                          double smooth_coef, double delta, double root, double floor);
+void hmfe_hear_plan_destroy(hmfe_hear_plan* plan);
+int hmfe_hear_num_frames(int n_padded);
+size_t hmfe_hear_workspace_bytes(const hmfe_hear_plan* plan, int64_t n_clips, int n_padded);
+/* d_out [n_clips][out_rows][n_mels] (the reference's [B, 1, 192, 128]) */
+int hmfe_hear_mel_pcen_batch(hmfe_hear_plan* plan, const float* d_audio, int64_t n_clips, int n_samples, int n_padded,
+                             int out_rows, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+/* mel power only: d_mel [n_clips][frames][n_mels]; the workspace needs 16 bytes */
+int hmfe_hear_mel_batch(hmfe_hear_plan* plan, const float* d_audio, int64_t n_clips, int n_samples, int n_padded,
+                        float* d_mel, void* d_workspace, size_t workspace_bytes, void* stream);
+int hmfe_hear_last_launches(const hmfe_hear_plan* plan);
 
 #ifdef __cplusplus
 }

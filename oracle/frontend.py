@@ -374,3 +374,111 @@ def htsat_input(x, bn_weight, bn_bias, bn_mean, bn_var, eps=1e-5, spec_size=256)
         x = x.reshape(1, 1, F_, ratio, target_T // ratio).permute(0, 1, 3, 2, 4).contiguous()
         x = x.reshape(1, 1, ratio * F_, target_T // ratio)
     return x[0, 0].numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# CLAP baseline front-end (sibling front-end).  torchlibrosa, which the reference
+# imports (msclap/models/audio.py:5), is not installed here: parity unpinned against torchlibrosa itself;
+# tests/test_oracle.py cross-checks this restatement against torchaudio's MelSpectrogram with the same
+# constants (reflect padding, Slaney mel, power 2).
+# ------------------------------------------------------------------------------------------------
+def clap_fixed_duration(x, audio_duration=5, sample_rate=44100):
+    """load_audio_into_tensor after read_audio (msclap/CLAPWrapper.py:279-299); draws from Python's global RNG."""
+    x = np.asarray(x).reshape(-1)
+    L = audio_duration * sample_rate
+    if L >= x.shape[0]:
+        repeat_factor = int(np.ceil(L / x.shape[0]))
+        return np.tile(x, repeat_factor)[0:L].astype(np.float32)
+    start_index = random.randrange(x.shape[0] - L)
+    return x[start_index : start_index + L].astype(np.float32)
+
+
+def clap_logmel(x, sample_rate=44100, window_size=1024, hop_size=320, mel_bins=64, fmin=50, fmax=14000, return_power=False):
+    """Cnn14 input stage (msclap/models/audio.py:146-175,190-192; configs/config_2022.yml:10-17):
+    torchlibrosa Spectrogram (Hann, centre, reflect, power 2) -> librosa mel -> 10 log10(max(1e-10, .)), [T, mel_bins]."""
+    x = np.asarray(x, dtype=np.float32)
+    D = lr.stft(x, n_fft=window_size, hop_length=hop_size, center=True, pad_mode="reflect")
+    S = (D.real.astype(np.float64) ** 2 + D.imag.astype(np.float64) ** 2).T
+    mel = S @ lr.mel_filterbank(sample_rate, window_size, n_mels=mel_bins, fmin=fmin, fmax=fmax).T.astype(np.float64)
+    mel = mel.astype(np.float32)
+    db = (10.0 * np.log10(np.maximum(np.float32(1e-10), mel))).astype(np.float32)
+    return (db, mel) if return_power else db
+
+
+# ------------------------------------------------------------------------------------------------
+# HeAR baseline front-end (sibling front-end, SURVEY 8f rank 4): restatement of
+# src/benchmark/baseline/hear/python/data_processing/audio_utils.py with the torch CPU ops the reference
+# calls.  Pinned: tests/golden/ref_hear.npz holds outputs of the reference's own preprocess_audio /
+# _linear_to_mel_weight_matrix (tests/golden/make_golden_hear.py executes them).
+# ------------------------------------------------------------------------------------------------
+def hear_mel_matrix(num_mel_bins=128, num_spectrogram_bins=201, sample_rate=16000.0, lower_edge_hertz=0.0,
+                    upper_edge_hertz=8000.0):
+    """_linear_to_mel_weight_matrix (audio_utils.py:264-358): [num_spectrogram_bins, num_mel_bins] float32, HTK mel,
+    triangles in the mel domain, DC row zero, all arithmetic in float32 torch ops as in the reference."""
+    import torch
+
+    dt = torch.float32
+    to_mel = lambda f: 2595.0 * torch.log10(1.0 + f / 700.0)  # noqa: E731  (:249-261)
+    nyquist = torch.tensor(sample_rate, dtype=dt) / 2.0
+    lin = torch.linspace(torch.tensor(0.0, dtype=dt), nyquist, num_spectrogram_bins, dtype=dt)[1:]
+    bins_mel = to_mel(lin).unsqueeze(1)
+    edges = torch.linspace(to_mel(torch.tensor(lower_edge_hertz, dtype=dt)), to_mel(torch.tensor(upper_edge_hertz, dtype=dt)),
+                           num_mel_bins + 2, dtype=dt).unfold(0, 3, 1)
+    lower, center, upper = (edges[:, i].unsqueeze(0) for i in range(3))
+    lower_slopes = (bins_mel - lower) / (center - lower)
+    upper_slopes = (upper - bins_mel) / (upper - center)
+    w = torch.maximum(torch.tensor(0.0, dtype=dt), torch.minimum(lower_slopes, upper_slopes))
+    return torch.nn.functional.pad(w, (0, 0, 1, 0)).numpy()
+
+
+def hear_mel_power(audio):
+    """Scaling + STFT + mel of _mel_pcen (audio_utils.py:357-382): [B, n] -> [B, ceil(n/160), 128] float32."""
+    import torch
+
+    x = torch.as_tensor(np.asarray(audio, dtype=np.float32)).clone()
+    x -= torch.min(x)
+    x = x / (torch.max(x) + 1e-8)
+    x = (x * 2) - 1
+    n = x.shape[-1]
+    n_frames = math.ceil(n / 160) if n > 0 else 0
+    padded = max(0, (n_frames - 1) * 160 + 400) if n_frames > 0 else 400
+    if padded > n:
+        x = torch.nn.functional.pad(x, (0, padded - n))
+    frames = x.unfold(-1, 400, 160) * torch.hann_window(400)
+    spec = torch.square(torch.abs(torch.fft.rfft(frames, n=400, dim=-1)))
+    return torch.matmul(spec, torch.as_tensor(hear_mel_matrix())).numpy()
+
+
+def hear_pcen(mel, alpha=0.8, smooth_coef=0.04, delta=2.0, root=2.0, floor=1e-8):
+    """_pcen_function with its _ema (audio_utils.py:121-246): [B, T, C] -> [B, T, C].  The reference's two matmuls
+    with diagonal kernels are two separately rounded float32 products."""
+    import torch
+
+    x = torch.as_tensor(np.asarray(mel, dtype=np.float32))
+    c_in = torch.tensor(smooth_coef, dtype=torch.float32)
+    c_state = torch.tensor(1.0 - smooth_coef, dtype=torch.float32)
+    state = x[:, 0]
+    ema = [state]
+    for t in range(1, x.shape[1]):
+        state = x[:, t] * c_in + state * c_state
+        ema.append(state)
+    ema = torch.stack(ema, dim=1)
+    a = torch.ones(x.shape[-1]) * min(alpha, 1.0)
+    r = 1.0 / (torch.ones(x.shape[-1]) * max(root, 1.0))
+    d = torch.ones(x.shape[-1]) * delta
+    return ((x / (floor + ema) ** a + d) ** r - d**r).numpy()
+
+
+def hear_preprocess_audio(audio):
+    """preprocess_audio (audio_utils.py:448-476): [B, n <= 32000] -> [B, 1, 192, 128] float32."""
+    import torch
+
+    audio = np.asarray(audio, dtype=np.float32)
+    if audio.ndim != 2:
+        raise ValueError(f"Input audio must have rank 2, got rank {audio.ndim}")
+    if audio.shape[1] > 32000:
+        raise ValueError(f"Input audio must have 32000 samples, got {audio.shape[1]}")
+    if audio.shape[1] < 32000:
+        audio = np.pad(audio, ((0, 0), (0, 32000 - audio.shape[1])))
+    img = torch.as_tensor(hear_pcen(hear_mel_power(audio))).unsqueeze(1)
+    return torch.nn.functional.interpolate(img, size=(192, 128), mode="bilinear", align_corners=False, antialias=False).numpy()

@@ -127,10 +127,10 @@ def stft(y, n_fft=2048, hop_length=None, center=True, pad_mode="constant"):
     y = np.asarray(y)
     if hop_length is None:
         hop_length = n_fft // 4
-    if pad_mode != "constant":
+    if pad_mode not in ("constant", "reflect"):
         raise NotImplementedError(pad_mode)
     if center:
-        y = np.pad(y, (n_fft // 2, n_fft // 2), mode="constant")
+        y = np.pad(y, (n_fft // 2, n_fft // 2), mode=pad_mode)
     fft_window = hann_periodic(n_fft).reshape(-1, 1)
     y_frames = frame(y, frame_length=n_fft, hop_length=hop_length)  # (n_fft, T)
     out_dtype = np.complex64 if y.dtype == np.float32 else np.complex128

@@ -97,3 +97,11 @@ def hash_spec(T: int, F: int, seed: int) -> np.ndarray:
         h ^= h >> np.uint64(32)
     v = (h >> np.uint64(44)).astype(np.float64) / float(1 << 20)
     return v.astype(np.float32).reshape(T, F)
+
+
+# HeAR front-end cases: name -> (samples per clip, golden_signal seeds); clips shorter than 32 000 are zero padded
+HEAR_CASES = {
+    "b3": (32000, (101, 102, 103)),
+    "single": (32000, (104,)),
+    "short": (20000, (105, 106)),
+}
