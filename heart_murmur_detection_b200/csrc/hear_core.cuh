@@ -174,6 +174,16 @@ HMFE_HD float sub_rn(float a, float b) { return a - b; }
 HMFE_HD float div_rn(float a, float b) { return a / b; }
 #endif
 
+// x^y for x > 0.  Device: exp2(y * log2 x) with the special-function log2 (relative error ~1e-6 for the PCEN operands,
+// i.e. <= 1e-5 absolute on outputs bounded by ~6; budget 1e-4); host emulation: powf.
+HMFE_HD float pow_pos(float x, float y) {
+#if defined(__CUDA_ARCH__)
+    return y == 0.5f ? sqrtf(x) : exp2f(y * __log2f(x));
+#else
+    return powf(x, y);
+#endif
+}
+
 // scaling of audio_utils.py:361-365: x -= min; x /= (max + 1e-8) [max taken after the shift]; x = 2 x - 1
 struct HearScale {
     float mn, den;
@@ -210,8 +220,8 @@ HMFE_HD void hear_pcen_column(const PcenParams& pp, int T, int out_rows, Load lo
             if (t_cur + 1 < T) x_next = load(t_cur + 1);
             ema = t_cur == 0 ? xv : add_rn(mul_rn(xv, pp.c_in), mul_rn(ema, pp.c_state));
             p_prev = p_cur;
-            const float g = powf(add_rn(pp.floor, ema), pp.alpha);
-            p_cur = sub_rn(powf(add_rn(div_rn(xv, g), pp.delta), pp.inv_root), pp.delta_root);
+            const float g = pow_pos(add_rn(pp.floor, ema), pp.alpha);
+            p_cur = sub_rn(pow_pos(add_rn(div_rn(xv, g), pp.delta), pp.inv_root), pp.delta_root);
         }
         const float a = r0 == t_cur ? p_cur : p_prev;
         store(i, add_rn(mul_rn(1.0f - lam, a), mul_rn(lam, p_cur)));

@@ -79,7 +79,7 @@ class HearPlan:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.hmfe_hear_plan_destroy(h)
             self._h = None
 
