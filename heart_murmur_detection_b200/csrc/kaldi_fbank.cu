@@ -116,6 +116,14 @@ HMFE_D FbItem fb_locate(const FbBatch& b, const FbMeta& mm, int64_t item, int64_
 // from those registers; the previous sample of the pre-emphasis comes from the neighbouring lane.
 constexpr int kFbSpanRegs = 28;
 
+constexpr float kLogFltEpsilon = -15.942384719848633f;  // float32(log(1.1920929e-7)), torch.log(eps) (kaldi.py: _get_log_energy / fbank floor)
+// ln(x) for normal positive x
+HMFE_D float fast_ln(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return 0.693147180559945309f * r;
+}
+
 HMFE_D void fb_load_span(const FbItem& c, int lane, float (&raw)[kFbSpanRegs]) {
     const int base = c.f0 * 160 + lane;
     if (c.valid && base - lane + 32 * kFbSpanRegs <= c.nsamp) {
@@ -372,8 +380,14 @@ fbank_kernel(const FbBatch b, const FbTables tb, const FbMeta mm) {
                 const float acc[4] = {a0, a1, a2, a3};
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (f0 + t < m)
-                        o[(int64_t)(f0 + t) * mm.n_mels + row] = logf(log_offset ? acc[t] + mm.log_offset : fmaxf(acc[t], FLT_EPSILON));
+                    if (f0 + t < m) {
+                        // natural log as ln2 * lg2.approx on the special-function unit (~1e-6 nat from the rounded value,
+                        // budget 2.3e-3 nat = 1e-2 dB; logf was 13 % of the kernel's instructions).  Entries at the floor
+                        // are written as the constant float32 log(FLT_EPSILON) the reference produces, bit for bit.
+                        const float x = log_offset ? acc[t] + mm.log_offset : acc[t];
+                        const float v = (!log_offset && x <= FLT_EPSILON) ? kLogFltEpsilon : fast_ln(x);
+                        o[(int64_t)(f0 + t) * mm.n_mels + row] = v;
+                    }
             }
         }
         __syncwarp();
