@@ -186,10 +186,22 @@ HMFE_HD float pow_pos(float x, float y) {
 
 // scaling of audio_utils.py:361-365: x -= min; x /= (max + 1e-8) [max taken after the shift]; x = 2 x - 1
 struct HearScale {
-    float mn, den;
+    float mn, den, inv;
 };
-HMFE_HD HearScale hear_make_scale(float mn, float mx) { return HearScale{mn, add_rn(sub_rn(mx, mn), 1e-8f)}; }
-HMFE_HD float hear_scale(const HearScale& s, float x) { return sub_rn(mul_rn(div_rn(sub_rn(x, s.mn), s.den), 2.0f), 1.0f); }
+HMFE_HD HearScale hear_make_scale(float mn, float mx) {
+    const float den = add_rn(sub_rn(mx, mn), 1e-8f);
+    return HearScale{mn, den, div_rn(1.0f, den)};
+}
+// The quotient (x - mn) / den is formed as q0 = t * (1 / den) plus one residual correction q0 + (t - q0 den) (1 / den):
+// with a correctly rounded reciprocal this is the correctly rounded quotient (Markstein), three FMA-pipe instructions
+// instead of the division sequence (0 <= t <= den, so no overflow; a constant batch, den = 1e-8, scales to -1 like the
+// reference's 0 / 1e-8).
+HMFE_HD float hear_scale(const HearScale& s, float x) {
+    const float t = sub_rn(x, s.mn);
+    const float q0 = mul_rn(t, s.inv);
+    const float q = fmaf(fmaf(-q0, s.den, t), s.inv, q0);
+    return sub_rn(mul_rn(q, 2.0f), 1.0f);
+}
 
 // ---- PCEN + row interpolation of one mel channel (audio_utils.py:121-246 and :386-445).
 struct PcenParams {

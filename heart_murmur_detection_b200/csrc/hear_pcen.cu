@@ -137,17 +137,36 @@ hear_mel_kernel(const HearBatch b, const HearTables tb, const HearMeta mm) {
     float* pf = reinterpret_cast<float*>(ptile);
     const int n_mels = mm.n_mels;
 
-    for (int64_t item = (int64_t)blockIdx.x * kHearWarps + warp; item < b.n_items; item += (int64_t)gridDim.x * kHearWarps) {
+    // The samples under an item (880 = 27.5 rows of 32) are fetched one item ahead into registers, so the global
+    // loads of item i+1 are in flight while item i is transformed.
+    constexpr int kRows = (kHearSpan + 31) / 32;
+    float raw[kRows];
+    auto load_raw = [&](int64_t it) {
+        const bool ok = it < b.n_items;
+        const int64_t cl = ok ? it / b.items_per_clip : 0;
+        const int s0n = ok ? (int)(it - cl * b.items_per_clip) * 4 * kHearShift : 0;
+        const float* xs = b.audio + cl * (int64_t)b.n_samples + s0n;
+        const int avail = ok ? b.n_samples - s0n : 0;  // samples of the clip from s0 on
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+            const int i = lane + 32 * j;
+            raw[j] = i < avail ? __ldg(xs + i) : 0.0f;
+        }
+    };
+    const int64_t item_stride = (int64_t)gridDim.x * kHearWarps;
+    int64_t item = (int64_t)blockIdx.x * kHearWarps + warp;
+    load_raw(item);
+    for (; item < b.n_items; item += item_stride) {
         const int64_t clip = item / b.items_per_clip;
         const int f0 = (int)(item - clip * b.items_per_clip) * 4;
-        const float* x = b.audio + clip * (int64_t)b.n_samples;
         const int s0 = f0 * kHearShift;
-        for (int i = lane; i < kHearSpan; i += 32) {
-            const int idx = s0 + i;
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+            const int i = lane + 32 * j, idx = s0 + i;
             // inside the clip: scaled sample; zero padding of preprocess_audio (:466-468): scaled zero;
             // zero padding of the STFT (:83-85, after the scaling): literal zero
-            const float v = idx < b.n_samples ? scale(__ldg(x + idx)) : (idx < b.n_padded ? scaled_zero : 0.0f);
-            span[hear_skew(i)] = v;
+            const float v = idx < b.n_samples ? scale(raw[j]) : (idx < b.n_padded ? scaled_zero : 0.0f);
+            if (i < kHearSpan) span[hear_skew(i)] = v;
         }
         __syncwarp();
         auto fetch = [&](int tr, bool second, int n) -> float {
@@ -156,6 +175,7 @@ hear_mel_kernel(const HearBatch b, const HearTables tb, const HearMeta mm) {
         };
         hear_pass1(lane, s_win, s_plane, fetch, tile);
         __syncwarp();
+        load_raw(item + item_stride);
         // power tile rows above bin 200 are read under zero weights and never written by the separation: clear
         // what the span (or another kernel) left there, so that 0 * x cannot be NaN
         for (int i = kHearBins + lane; i < kHearPRows; i += 32) ptile[i] = xelem<f32x2>{};

@@ -58,7 +58,7 @@ class LogMelPlan:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.hmfe_logmel_plan_destroy(h)
             self._h = None
 
@@ -192,7 +192,7 @@ class Context:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.hmfe_ctx_destroy(h)
             self._h = None
 
@@ -473,7 +473,7 @@ class FbankPlan:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.hmfe_fbank_plan_destroy(h)
             self._h = None
 
@@ -597,7 +597,7 @@ class ResamplePlan:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.hmfe_resample_plan_destroy(h)
             self._h = None
 
