@@ -157,7 +157,7 @@ static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float
     const float preemph = 0.97f;
     const int m = nsamp >= win ? 1 + (nsamp - win) / shift : 0;
     const std::vector<float> dense = mel_banks_kaldi(n_mels, 512, 16000.0, 20.0, 0.0);
-    const BandedMel bm = build_banded(dense, n_mels, 257, 16, 320);
+    const BandedMel bm = build_banded(dense, n_mels, 257, 8, 320);  // kFbMelGroup
     if (!verify_banded(bm, dense, 320)) {
         fprintf(stderr, "banded mel verification failed\n");
         exit(3);
