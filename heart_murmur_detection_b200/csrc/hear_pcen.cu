@@ -191,16 +191,12 @@ hear_mel_kernel(const HearBatch b, const HearTables tb, const HearMeta mm) {
                 const float gi = lane == 0 ? zi[hear_give_reg(true, k2)] : zi[hear_give_reg(false, k2)];
                 const float pr = __shfl_sync(0xffffffffu, gr, src), pi = __shfl_sync(0xffffffffu, gi, src);
                 const xelem<float> pw = frame_powers<float>(zr[k2], zi[k2], pr, pi);
-                if (lane < 25) {
-                    const int k = lane + 25 * k2;
-                    pf[4 * k + r] = pw.a;
-                    pf[4 * k + 2 + r] = pw.b;
-                }
+                // power tile element k = (frame f0, f0+1 | f0+2, f0+3): transform r owns one 8-byte half
+                if (lane < 25) *reinterpret_cast<float2*>(pf + 4 * (lane + 25 * k2) + 2 * r) = make_float2(pw.a, pw.b);
             }
             if (lane == 0) {
                 const xelem<float> pw = frame_powers<float>(zr[8], zi[8], zr[8], zi[8]);
-                pf[4 * 200 + r] = pw.a;
-                pf[4 * 200 + 2 + r] = pw.b;
+                *reinterpret_cast<float2*>(pf + 4 * 200 + 2 * r) = make_float2(pw.a, pw.b);
             }
         }
         __syncwarp();
@@ -211,8 +207,8 @@ hear_mel_kernel(const HearBatch b, const HearTables tb, const HearMeta mm) {
             const int row = s_row[s * 32 + lane];
             if (row >= 0) {
                 if (f0 < b.T) o[row] = aa.x;
-                if (f0 + 1 < b.T) o[n_mels + row] = ab.x;
-                if (f0 + 2 < b.T) o[2 * n_mels + row] = aa.y;
+                if (f0 + 1 < b.T) o[n_mels + row] = aa.y;
+                if (f0 + 2 < b.T) o[2 * n_mels + row] = ab.x;
                 if (f0 + 3 < b.T) o[3 * n_mels + row] = ab.y;
             }
         }

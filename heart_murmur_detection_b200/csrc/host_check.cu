@@ -157,7 +157,7 @@ static void run_fbank(const std::vector<float>& x, int n_mels, std::vector<float
     const float preemph = 0.97f;
     const int m = nsamp >= win ? 1 + (nsamp - win) / shift : 0;
     const std::vector<float> dense = mel_banks_kaldi(n_mels, 512, 16000.0, 20.0, 0.0);
-    const BandedMel bm = build_banded(dense, n_mels, 257, 8, 320);  // kFbMelGroup
+    const BandedMel bm = build_banded(dense, n_mels, 257, 8, 320, 16);  // kFbMelGroup, prefer 16 as in kaldi_fbank.cu
     if (!verify_banded(bm, dense, 320)) {
         fprintf(stderr, "banded mel verification failed\n");
         exit(3);
@@ -311,13 +311,13 @@ static void run_hear(const std::vector<float>& audio, int n_samples, int n_padde
                         const int preg = hear_give_reg(src == 0, k2);
                         const xelem<float> pw = frame_powers<float>(L[lane].zr[k2], L[lane].zi[k2], L[src].zr[preg], L[src].zi[preg]);
                         const int k = lane + 25 * k2;
-                        pf[4 * k + r] = pw.a;
-                        pf[4 * k + 2 + r] = pw.b;
+                        pf[4 * k + 2 * r] = pw.a;
+                        pf[4 * k + 2 * r + 1] = pw.b;
                     }
                 }
                 const xelem<float> pw = frame_powers<float>(L[0].zr[8], L[0].zi[8], L[0].zr[8], L[0].zi[8]);
-                pf[4 * 200 + r] = pw.a;
-                pf[4 * 200 + 2 + r] = pw.b;
+                pf[4 * 200 + 2 * r] = pw.a;
+                pf[4 * 200 + 2 * r + 1] = pw.b;
             }
             float* o = out_mel.data() + ((size_t)clip * T + f0) * n_mels;
             for (int lane = 0; lane < 32; ++lane)
@@ -328,8 +328,8 @@ static void run_hear(const std::vector<float>& audio, int n_samples, int n_padde
                     const int row = bm.row[s * 32 + lane];
                     if (row < 0) continue;
                     if (f0 < T) o[row] = aa.x;
-                    if (f0 + 1 < T) o[n_mels + row] = ab.x;
-                    if (f0 + 2 < T) o[2 * n_mels + row] = aa.y;
+                    if (f0 + 1 < T) o[n_mels + row] = aa.y;
+                    if (f0 + 2 < T) o[2 * n_mels + row] = ab.x;
                     if (f0 + 3 < T) o[3 * n_mels + row] = ab.y;
                 }
         }

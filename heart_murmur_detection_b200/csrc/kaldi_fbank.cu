@@ -482,7 +482,11 @@ static int fbank_plan_init(hmfe_fbank_plan** plan, int sample_rate, int win, int
         const int g = atoi(e);
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) group = g;
     }
-    const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1, group, kFbPStride);
+    // ... and the lanes are then re-assigned (minimum-cost assignment, tables.h) so that the windows are congruent to their
+    // lane modulo 16 wherever that fits the same trip counts: for the Kaldi bank all of them do (40 trips, conflict free).
+    int prefer = 16;
+    if (const char* e = getenv("HMFE_FBANK_MEL_PREFER")) prefer = atoi(e);
+    const BandedMel bm = build_banded(p->mel_dense, n_mels, kFbPad / 2 + 1, group, kFbPStride, prefer);
     if (!verify_banded(bm, p->mel_dense, kFbPStride)) {
         set_error("the mel matrix is not banded (every row must have one contiguous support that fits the tile)");
         delete p;

@@ -118,7 +118,61 @@ struct BandedMel {
 // per-iteration tile reads bank-conflict free; rows are placed on the lane that needs the
 // smallest downward shift of their window.  Trip counts are rounded up to a multiple of 8 (no
 // remainder loop) and every window must end at or before `cap` tile rows.
-inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n_bins, int group = 8, int cap = 576) {
+// Minimum-cost assignment of n rows to n columns (Hungarian algorithm with potentials, O(n^3)); cost[i][j] >= 0.
+// Returns col_of_row.
+inline std::vector<int> assign_min_cost(const std::vector<std::vector<int>>& cost) {
+    const int n = (int)cost.size();
+    const int INF = 1 << 29;
+    std::vector<int> u(n + 1, 0), v(n + 1, 0), p(n + 1, 0), way(n + 1, 0);
+    for (int i = 1; i <= n; ++i) {
+        p[0] = i;
+        int j0 = 0;
+        std::vector<int> minv(n + 1, INF);
+        std::vector<char> used(n + 1, 0);
+        do {
+            used[j0] = 1;
+            const int i0 = p[j0];
+            int delta = INF, j1 = 0;
+            for (int j = 1; j <= n; ++j)
+                if (!used[j]) {
+                    const int cur = cost[i0 - 1][j - 1] - u[i0] - v[j];
+                    if (cur < minv[j]) {
+                        minv[j] = cur;
+                        way[j] = j0;
+                    }
+                    if (minv[j] < delta) {
+                        delta = minv[j];
+                        j1 = j;
+                    }
+                }
+            for (int j = 0; j <= n; ++j)
+                if (used[j]) {
+                    u[p[j]] += delta;
+                    v[j] -= delta;
+                } else {
+                    minv[j] -= delta;
+                }
+            j0 = j1;
+        } while (p[j0] != 0);
+        do {
+            const int j1 = way[j0];
+            p[j0] = p[j1];
+            j0 = j1;
+        } while (j0);
+    }
+    std::vector<int> col(n, -1);
+    for (int j = 1; j <= n; ++j)
+        if (p[j] > 0) col[p[j] - 1] = j - 1;
+    return col;
+}
+
+// `prefer` (a multiple of `group`, 0 = off): after the trip counts are fixed by the modulo-`group` placement, the rows
+// of every slot are re-assigned to lanes so that as many windows as possible start congruent to their lane modulo
+// `prefer` WITHOUT lengthening the slot's trip count (minimum-cost assignment: 0 for a modulo-`prefer` fit, 1 for a
+// modulo-`group` fit).  For 8-byte tile elements (a shared-memory wavefront serves 16 lanes) group = 8 keeps the
+// windows short and prefer = 16 removes most of the two-way conflicts between lanes l and l + 8 that it would cost.
+inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n_bins, int group = 8, int cap = 576,
+                              int prefer = 0) {
     BandedMel b;
     b.n_mels = n_mels;
     b.n_bins = n_bins;
@@ -171,6 +225,34 @@ inline BandedMel build_banded(const std::vector<float>& dense, int n_mels, int n
         b.trip[s] = (need + 7) / 8 * 8;
         b.wbase[s] = b.total_trip;
         b.total_trip += b.trip[s];
+        if (prefer > group && prefer % group == 0) {
+            const int T = b.trip[s], BIG = 1000;
+            std::vector<int> rows;
+            for (int j = 0; j < 32 && s * 32 + j < n_mels; ++j) rows.push_back(order[s * 32 + j]);
+            std::vector<std::vector<int>> cost(32, std::vector<int>(32, 0));  // rows beyond rows.size() are dummies
+            auto shift_of = [&](int m, int l, int mod) { return ((first[m] - l) % mod + mod) % mod; };
+            auto fits = [&](int m, int sh) { return first[m] - sh >= 0 && len[m] + sh <= T; };
+            for (size_t j = 0; j < rows.size(); ++j)
+                for (int l = 0; l < 32; ++l) {
+                    const int m = rows[j];
+                    cost[j][l] = fits(m, shift_of(m, l, prefer)) ? 0 : (fits(m, shift_of(m, l, group)) ? 1 : BIG);
+                }
+            const std::vector<int> lane_of = assign_min_cost(cost);
+            int total = 0;
+            for (size_t j = 0; j < rows.size(); ++j) total += cost[j][lane_of[j]];
+            if (total < BIG) {  // otherwise keep the greedy placement (rows that start below `group`)
+                for (int l = 0; l < 32; ++l) {
+                    b.row[(size_t)s * 32 + l] = -1;
+                    b.start[(size_t)s * 32 + l] = 0;
+                }
+                for (size_t j = 0; j < rows.size(); ++j) {
+                    const int m = rows[j], l = lane_of[j];
+                    const int sh = cost[j][l] == 0 ? shift_of(m, l, prefer) : shift_of(m, l, group);
+                    b.row[(size_t)s * 32 + l] = m;
+                    b.start[(size_t)s * 32 + l] = first[m] - sh;
+                }
+            }
+        }
     }
     b.w.assign((size_t)b.total_trip * 32, 0.0f);
     for (int s = 0; s < b.n_slots; ++s)
