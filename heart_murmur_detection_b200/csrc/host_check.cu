@@ -9,6 +9,7 @@
 //
 // usage: host_check logmel <scalar|packed|pair> <hop> <n_mels> <fmin> <fmax> <in.f32> <out.f32>
 //        host_check fbank <n_mels> <in.f32> <out.f32>
+//        host_check banded
 //        host_check hear <n_samples> <n_padded> <out_rows> <audio.f32> <window.f32> <mel.f32> <out_mel.f32> <out_pcen.f32>
 #include <stdio.h>
 #include <stdlib.h>
@@ -352,6 +353,53 @@ static void run_hear(const std::vector<float>& audio, int n_samples, int n_padde
         }
 }
 
+// Shared-memory wavefronts of the banded mel tile reads for 8-byte tile elements (a wavefront serves 16 lanes whose
+// element indices are distinct modulo 16, or equal): the quantity the lane assignment of build_banded minimises.
+static long banded_wavefronts8(const BandedMel& bm) {
+    long wf = 0;
+    for (int s = 0; s < bm.n_slots; ++s)
+        for (int i = 0; i < bm.trip[s]; ++i)
+            for (int h = 0; h < 2; ++h) {
+                std::vector<int> seen[16];
+                for (int l = 16 * h; l < 16 * h + 16; ++l) {
+                    const int a = bm.start[s * 32 + l] + i;
+                    std::vector<int>& v = seen[a & 15];
+                    bool dup = false;
+                    for (int e : v) dup = dup || e == a;
+                    if (!dup) v.push_back(a);
+                }
+                size_t mx = 1;
+                for (int r = 0; r < 16; ++r) mx = seen[r].size() > mx ? seen[r].size() : mx;
+                wf += (long)mx;
+            }
+    return wf;
+}
+
+// host_check banded: the Kaldi mel bank (128 bands, 257 bins) under the three placements of kaldi_fbank.cu
+static int run_banded() {
+    const std::vector<float> dense = mel_banks_kaldi(128, 512, 16000.0, 20.0, 0.0);
+    const int cfg[3][2] = {{16, 0}, {8, 0}, {8, 16}};
+    for (const auto& c : cfg) {
+        const BandedMel bm = build_banded(dense, 128, 257, c[0], 320, c[1]);
+        printf("group %d prefer %d total_trip %d wavefronts %ld ideal %d verify %d\n", c[0], c[1], bm.total_trip,
+               banded_wavefronts8(bm), 2 * bm.total_trip, (int)verify_banded(bm, dense, 320));
+    }
+    // the assignment solver on a matrix with a known optimum (a permutation of zeros in a field of ones)
+    std::vector<std::vector<int>> cost(32, std::vector<int>(32, 1));
+    for (int i = 0; i < 32; ++i) cost[i][(7 * i + 3) % 32] = 0;
+    const std::vector<int> col = assign_min_cost(cost);
+    int total = 0;
+    std::vector<char> used(32, 0);
+    for (int i = 0; i < 32; ++i) {
+        total += cost[i][col[i]];
+        used[col[i]] = 1;
+    }
+    int distinct = 0;
+    for (char u : used) distinct += u;
+    printf("assign total %d distinct %d\n", total, distinct);
+    return 0;
+}
+
 static std::vector<float> read_f32(const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) {
@@ -399,6 +447,7 @@ int main(int argc, char** argv) {
         write_f32(argv[4], out);
         return 0;
     }
+    if (argc >= 2 && !strcmp(argv[1], "banded")) return run_banded();
     if (argc >= 10 && !strcmp(argv[1], "hear")) {
         std::vector<float> om, op;
         run_hear(read_f32(argv[5]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), read_f32(argv[6]), read_f32(argv[7]), om, op);

@@ -32,3 +32,19 @@ def test_logmel_power_emulation(host_check, variant, tmp_path):
         dbp = 10 * np.log10(np.maximum(1e-10, P)) - 10 * np.log10(max(1e-10, P.max()))
         dbp = np.maximum(dbp, dbp.max() - 80)
         assert np.abs(dbp - db).max() <= 1e-2
+
+
+def test_banded_mel_lane_assignment(host_check):
+    """tables.h build_banded for the Kaldi bank (kaldi_fbank.cu): aligning the windows modulo 8 cuts the loop trips from 72
+    to 40, and the minimum-cost lane re-assignment (prefer = 16) makes those 40 trips bank-conflict free again; every
+    placement must reproduce the dense mel matrix exactly (verify_banded), which is what plan creation enforces."""
+    out = subprocess.check_output([host_check, "banded"], text=True).strip().splitlines()
+    rows = {}
+    for line in out[:3]:
+        f = line.split()
+        rows[(int(f[1]), int(f[3]))] = dict(trip=int(f[5]), wf=int(f[7]), ideal=int(f[9]), verify=int(f[11]))
+    assert all(r["verify"] == 1 for r in rows.values())
+    assert rows[(16, 0)]["trip"] == 72 and rows[(16, 0)]["wf"] == rows[(16, 0)]["ideal"]
+    assert rows[(8, 0)]["trip"] == 40 and rows[(8, 0)]["wf"] > rows[(8, 0)]["ideal"]
+    assert rows[(8, 16)]["trip"] == 40 and rows[(8, 16)]["wf"] == rows[(8, 16)]["ideal"] == 80
+    assert out[3].split() == ["assign", "total", "0", "distinct", "32"]
