@@ -18,7 +18,10 @@ METRICS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
     "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",  # load/store data pipe: shared + global wavefronts
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg",
     "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
 ]
