@@ -95,7 +95,7 @@ def _one(x: torch.Tensor, sr: int, resample: bool) -> torch.Tensor:
     if x.dim() == 2:  # the reference resamples every channel, then flattens channel after channel (:270-271,278)
         if resample and sr != SAMPLING_RATE:
             n = x.shape[1]
-            y, no = fe.resample_plan(sr, SAMPLING_RATE)(x.reshape(-1), np.arange(x.shape[0] + 1, dtype=np.int64) * n)
+            y, _ = fe.resample_plan(sr, SAMPLING_RATE)(x.reshape(-1), np.arange(x.shape[0] + 1, dtype=np.int64) * n)
             x, sr = y, SAMPLING_RATE
         else:
             x = x.reshape(-1)

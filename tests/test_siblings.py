@@ -43,9 +43,8 @@ def test_clap_oracle_vs_torchaudio():
 
 def test_clap_fixed_duration_plan_matches_oracle():
     from heart_murmur_detection_b200 import clap_input as ci
-    from heart_murmur_detection_b200 import frontend as fe
 
-    def apply(ch, x):
+    def apply(ch, x):  # what the gather kernel does with a plan record (include/hmfe.h: hmfe_gather_desc)
         if ch[0] == "view":
             return x[ch[1] : ch[1] + ch[2]]
         _, length, src_start, period, a_end, a_phase, b_end, b_start = ch
@@ -53,7 +52,6 @@ def test_clap_fixed_duration_plan_matches_oracle():
         out = np.where(i < a_end, x[src_start + (a_phase + i) % period], 0.0)
         return out.astype(np.float32)
 
-    assert fe  # the plan records are the gather records of the main path
     for n in (1, 7, 1000, 110249, 110250, 220499, 220500, 220501, 300000, 1000000):
         x = (np.arange(n) % 977).astype(np.float32)
         random.seed(n)
