@@ -38,7 +38,7 @@ lengths = st.one_of(st.integers(1, 400_000), st.sampled_from([15999, 16000, 1600
 secs = st.sampled_from([1, 2, 4.09, 8, 8.18])
 
 
-@settings(max_examples=120, deadline=None)
+@settings(max_examples=120, deadline=None, derandomize=True)
 @given(n=lengths, sec=secs, types=st.sampled_from(["repeat", "zero"]))
 def test_plan_split_pad_equals_reference_layout(n, sec, types):
     """split_pad_sample / _duplicate_padding / _equally_slice_pad_sample / _zero_padding (src/util.py:504-620)."""
@@ -51,7 +51,7 @@ def test_plan_split_pad_equals_reference_layout(n, sec, types):
         assert got.shape == r.shape and np.array_equal(got, r)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(n=lengths, sec=st.sampled_from([2, 10]))
 def test_plan_split_sample_equals_reference(n, sec):
     """split_sample (extract_feature.py:250-259)."""
@@ -63,7 +63,7 @@ def test_plan_split_sample_equals_reference(n, sec):
         assert np.array_equal(apply_chunk(x, ch), r)
 
 
-@settings(max_examples=120, deadline=None)
+@settings(max_examples=120, deadline=None, derandomize=True)
 @given(n=st.integers(0, 700_000), pad=st.booleans(), types=st.sampled_from(["repeat", "zero"]),
        max_sec=st.sampled_from([None, 32, 10]))
 def test_entire_signal_chunker_equals_reference_control_flow(n, pad, types, max_sec):
@@ -88,7 +88,7 @@ def test_entire_signal_chunker_equals_reference_control_flow(n, pad, types, max_
         assert np.array_equal(apply_chunk(x, chunks[0]), ref)
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=80, deadline=None, derandomize=True)
 @given(n=st.integers(1, 600_000), sec=st.sampled_from([2, 4.09, 8.18, 10]), trim_tail=st.booleans())
 def test_split_signal_chunker_drop_last(n, sec, trim_tail):
     """get_split_signal_librosa's chunk list incl. decide_droplast (src/util.py:348-354, 369-371)."""
