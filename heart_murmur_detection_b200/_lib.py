@@ -158,6 +158,20 @@ hmfe_spec_crop_batch = _sig(
 )
 
 
+class RectDesc(C.Structure):
+    """struct hmfe_rect_desc (include/hmfe.h)."""
+
+    _fields_ = [("item", C.c_int64), ("row0", C.c_int32), ("n_rows", C.c_int32), ("col0", C.c_int32), ("n_cols", C.c_int32)]
+
+
+hmfe_spec_zero_rects = _sig(
+    "hmfe_spec_zero_rects", C.c_int, c_voidp, c_voidp, C.c_int, C.c_int, C.c_int64, c_voidp, C.c_int64, c_voidp
+)
+hmfe_cola_draws = _sig(
+    "hmfe_cola_draws", C.c_int64, c_voidp, C.c_int64, c_voidp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+    c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp,
+)
+
 hmfe_htsat_input_batch = _sig(
     "hmfe_htsat_input_batch", C.c_int, c_voidp, c_voidp, C.c_int, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp, C.c_int,
     c_voidp, c_voidp,

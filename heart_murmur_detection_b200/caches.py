@@ -22,18 +22,40 @@ from . import pipeline as pl
 
 
 def _batches(paths, sample_rate, batch_bytes, workers):
-    """Yield (indices, pinned float32 samples, offsets) for consecutive groups of files."""
+    """Yield (indices, clips at ``sample_rate``) for consecutive groups of files.
+
+    The worker threads only DECODE (host work, native rate).  Rate conversion runs on the GPU from the calling thread,
+    one ``ResamplePlan`` call per native rate and batch: an ``hmfe`` plan / context belongs to one host thread
+    (include/hmfe.h) and worker threads would all default to CUDA device 0."""
     with ThreadPoolExecutor(max_workers=workers) as ex:
         pending, idx, size = [], [], 0
-        for i, clip in enumerate(ex.map(lambda p: audio_io.load(p, sr=sample_rate)[0], paths)):
-            pending.append(clip)
+        for i, (clip, native) in enumerate(ex.map(lambda p: audio_io.load(p, sr=None), paths)):
+            pending.append((clip, native))
             idx.append(i)
-            size += clip.size * 4
+            size += int(clip.size * 4 * (sample_rate / native if native != sample_rate else 1))
             if size >= batch_bytes:
-                yield idx, pending
+                yield idx, _resample_group(pending, sample_rate)
                 pending, idx, size = [], [], 0
         if pending:
-            yield idx, pending
+            yield idx, _resample_group(pending, sample_rate)
+
+
+def _resample_group(decoded, sample_rate):
+    """[(clip, native rate)] -> [clip at sample_rate]; one ragged GPU call per distinct native rate."""
+    out = [None] * len(decoded)
+    by_rate = {}
+    for k, (clip, native) in enumerate(decoded):
+        if native == sample_rate:
+            out[k] = clip
+        else:
+            by_rate.setdefault(native, []).append(k)
+    for native, ks in by_rate.items():
+        wav, off = _to_device([decoded[k][0] for k in ks])
+        y, no = audio_io.fe.resample_plan(native, sample_rate)(wav, off)
+        y = y.cpu().numpy()
+        for j, k in enumerate(ks):
+            out[k] = y[int(no[j]) : int(no[j + 1])]
+    return out
 
 
 def _to_device(clips):

@@ -56,6 +56,18 @@ spec_crop_kernel(const float* __restrict__ spec, float* __restrict__ out, const 
     }
 }
 
+// SpecAugmentation stripes (finetuning.py:104-116): zero a rectangle of an output item
+__global__ void __launch_bounds__(256)
+spec_zero_rects_kernel(float* __restrict__ out, const hmfe_rect_desc* __restrict__ rects, int out_rows, int n_cols) {
+    const hmfe_rect_desc r = rects[blockIdx.x];
+    float* o = out + r.item * (int64_t)out_rows * n_cols;
+    const int n = r.n_rows * r.n_cols;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int rr = i / r.n_cols, cc = i - rr * r.n_cols;
+        o[(int64_t)(r.row0 + rr) * n_cols + r.col0 + cc] = 0.0f;
+    }
+}
+
 }  // namespace hmfe
 
 using namespace hmfe;
@@ -112,6 +124,33 @@ int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const h
                                                                     d_row_mask, d_mean, n_cols, out_rows, tiles);
     HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->prof_end(st);
+    ctx->last_launches = 1;
+    return ctx->ring.release(slot, st);
+}
+
+int hmfe_spec_zero_rects(hmfe_ctx* ctx, float* d_out, int out_rows, int n_cols, int64_t n_items, const hmfe_rect_desc* h_rects,
+                         int64_t n_rects, void* stream) {
+    HMFE_REQUIRE(ctx && (h_rects || n_rects == 0), "NULL argument");
+    HMFE_REQUIRE(n_rects >= 0 && n_rects < (int64_t)INT32_MAX && out_rows > 0 && n_cols > 0, "bad arguments");
+    ctx->last_launches = 0;
+    if (n_rects == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_out, "NULL device pointer");
+    for (int64_t i = 0; i < n_rects; ++i) {
+        const hmfe_rect_desc& r = h_rects[i];
+        HMFE_REQUIRE(r.item >= 0 && r.item < n_items && r.row0 >= 0 && r.n_rows >= 0 && r.row0 + r.n_rows <= out_rows &&
+                         r.col0 >= 0 && r.n_cols >= 0 && r.col0 + r.n_cols <= n_cols,
+                     "rectangle %lld lies outside its item", (long long)i);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)n_rects * sizeof(hmfe_rect_desc);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = ctx->ring.acquire(bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    memcpy(hbuf, h_rects, bytes);
+    int rc = ctx->ring.upload(slot, bytes, st);
+    if (rc != HMFE_OK) return rc;
+    spec_zero_rects_kernel<<<(unsigned)n_rects, 256, 0, st>>>(d_out, static_cast<hmfe_rect_desc*>(dbuf), out_rows, n_cols);
+    HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->last_launches = 1;
     return ctx->ring.release(slot, st);
 }

@@ -167,21 +167,28 @@ class PeerAllGather:
                 self.done[i].record(self.comm)
             self.used[i] = True
             return self.buffers[i]
+        # Rendezvous BEFORE the push (as the multicast path does): a rank that runs ahead must not overwrite buffer i
+        # of a peer that has not finished with the previous contents - a peer joins this barrier only after its own
+        # ready[i], i.e. after everything it enqueued on its producing stream (including reads of the old buffer i).
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[i])
+            self.handles[i].barrier(channel=0)
+            go = torch.cuda.Event()
+            go.record(self.comm)
         evs = []
         for k in range(self.world - 1):
             r = (self.rank + 1 + k) % self.world  # stagger the targets: rank r sends to r+1, r+2, ...
             cs = self.copy_streams[k]
-            cs.wait_event(self.ready[i])
+            cs.wait_event(go)
             with torch.cuda.stream(cs):
                 self.peer[i][r][lo:hi].copy_(src, non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(cs)
                 evs.append(e)
         with torch.cuda.stream(self.comm):
-            self.comm.wait_event(self.ready[i])
             for e in evs:
                 self.comm.wait_event(e)
-            self.handles[i].barrier(channel=0)
+            self.handles[i].barrier(channel=1)  # every rank's copies have landed
             self.done[i].record(self.comm)
         self.used[i] = True
         return self.buffers[i]

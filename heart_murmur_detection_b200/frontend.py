@@ -825,11 +825,13 @@ def plan_split_sample(n, desired_length, sample_rate):
     return [_view(L * i, min(L, n - L * i)) for i in range(int(np.ceil(n / L)))]
 
 
-def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, ctx: Context | None = None, stream=None):
+def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, ctx: Context | None = None, stream=None,
+                       owned: bool = True):
     """Turn per-clip chunk plans into (starts, lengths, clip_ids) views into ``work``.
 
     ``work[:used]`` holds the signal; gather chunks are written behind it (the buffer is
-    re-allocated with the signal copied if its spare capacity is too small).
+    re-allocated with the signal copied if its spare capacity is too small, or if ``owned`` is False:
+    ``work`` is then the caller's tensor and whatever lies behind ``used`` in it is the caller's).
     Returns (work, starts, lengths, clip_ids, is_view).
     """
     starts, lengths, clip_ids, recs, is_view = [], [], [], [], []
@@ -848,7 +850,7 @@ def materialise_chunks(work: torch.Tensor, used: int, clip_starts, chunk_lists, 
             clip_ids.append(cid)
             is_view.append(ch[0] == "view")
     if recs:
-        if tail > work.numel():
+        if tail > work.numel() or not owned:
             bigger = torch.empty(tail, dtype=torch.float32, device=work.device)
             bigger[:used].copy_(work[:used])
             work = bigger

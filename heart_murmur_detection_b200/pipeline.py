@@ -109,7 +109,8 @@ def prepare_chunks(wav: torch.Tensor, offsets, chunker, *, sample_rate=16000, bu
         chunk_lists.append(chunks)
     dup = bool(getattr(chunker, "dup_called", False))
     clip_starts = o[:-1] + se[:, 0]
-    work, starts, lengths, clip_ids, is_view = fe.materialise_chunks(work, total, clip_starts, chunk_lists, ctx=ctx)
+    work, starts, lengths, clip_ids, is_view = fe.materialise_chunks(work, total, clip_starts, chunk_lists, ctx=ctx,
+                                                                     owned=sos is not None)
     if not is_view.all():
         launches += ctx.last_launches
     return ChunkBatch(work, starts, lengths, clip_ids, n, valid, se, dup, launches, is_view, sos is not None)
@@ -163,6 +164,9 @@ def split_signal_chunker(input_sec=8, sample_rate=16000, trim_tail=False, types=
 
 def log_mel_features(cb: ChunkBatch, f_max=8000, n_mels=64, f_min=50, nfft=1024, hop=512, sample_rate=16000,
                      mode="normalised", out: torch.Tensor | None = None) -> FeatureBatch:
+    """``sample_rate`` is the rate of the MEL BASIS.  The reference's callers never forward their own ``sample_rate``
+    to pre_process_audio_mel_t (src/util.py:198,261-263,358-360): the basis is always built for 16 kHz, whatever rate
+    the audio was loaded at; the batch entry points below do the same."""
     plan = fe.logmel_plan(sample_rate, n_mels, f_min, f_max, nfft, hop)
     if len(cb.starts) == 0:
         return FeatureBatch(torch.empty((0, n_mels), device=cb.work.device), np.zeros(1, np.int64), cb, cb.launches)
@@ -251,7 +255,8 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
             d["b_end"] = L
             dup = True
         need = total + L * padded.size
-        if need <= work.numel():  # spare capacity behind the signal (band-passed copy or a caller's roomy buffer)
+        if sos is not None and need <= work.numel():  # spare capacity behind the band-passed copy (a buffer of ours or
+            # the caller's explicit ``work=``); the caller's SIGNAL tensor is never written, however roomy it is
             fe.gather(work, work, d, ctx=ctx)
             starts[padded] = d["dst_off"]
         else:  # read-only signal without room: padded copies go to their own buffer, addressed by negative starts
@@ -284,7 +289,7 @@ def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterwort
         cb = prepare_chunks(wav, offsets, entire_signal_chunker(input_sec, sample_rate, pad, types, max_sec),
                             sample_rate=sample_rate, butterworth_filter=butterworth_filter, lowcut=lowcut,
                             highcut=highcut, pad_hint=L if pad else 0)
-    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate, out=out) if spectrogram else cb
+    return log_mel_features(cb, f_max=f_max, out=out) if spectrogram else cb
 
 
 def split_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
@@ -294,7 +299,7 @@ def split_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth
                         sample_rate=sample_rate,
                         butterworth_filter=butterworth_filter, lowcut=lowcut, highcut=highcut,
                         pad_hint=int(input_sec * sample_rate))
-    return log_mel_features(cb, f_max=f_max, sample_rate=sample_rate) if spectrogram else cb
+    return log_mel_features(cb, f_max=f_max) if spectrogram else cb
 
 
 def split_signal_fbank_pad_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None,
@@ -349,7 +354,7 @@ def individual_segments_batch(wav, offsets, input_sec=8, sample_rate=16000, hop_
 
     cb = prepare_chunks(wav, offsets, chunker, sample_rate=sample_rate, butterworth_filter=butterworth_filter,
                         lowcut=200, highcut=1800, pad_hint=8 * sample_rate)
-    return log_mel_features(cb, f_max=2000, sample_rate=sample_rate) if spectrogram else cb
+    return log_mel_features(cb, f_max=2000) if spectrogram else cb
 
 
 # ----------------------------------------------------------------------------------------------

@@ -176,7 +176,7 @@ def get_entire_signal_librosa(
         work, starts, lengths, _, is_view = fe.materialise_chunks(work, n, [0], [chunks])
         cb = pl.ChunkBatch(work, starts, lengths, np.zeros(1, np.int64), 1, np.ones(1, bool), np.array([[0, n]]),
                            chunker.dup_called, 0, is_view, np.asarray(yt).dtype == np.float64)
-        res = pl.log_mel_features(cb, f_max=8000, sample_rate=sample_rate) if spectrogram else cb
+        res = pl.log_mel_features(cb, f_max=8000) if spectrogram else cb  # mel basis at the 16 kHz default (src/util.py:261-263)
     else:
         data, _ = _load(data_folder, filename, sample_rate)
         wav, off = _one(data)

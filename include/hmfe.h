@@ -264,6 +264,27 @@ int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_ro
 int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const hmfe_crop_desc* h_descs, int64_t n_items,
                          const uint8_t* d_row_mask, const float* d_mean, float* d_out, int out_rows, void* stream);
 
+/* SpecAugmentation (torchlibrosa DropStripes as called from finetuning.py:64-69,104-116): zero rectangles
+ * [row0, row0 + n_rows) x [col0, col0 + n_cols) of output item `item` of d_out[n_items][out_rows][n_cols].
+ * The stripe positions are drawn on the host (torch.randint, the generator the reference consumes). */
+typedef struct hmfe_rect_desc {
+    int64_t item;
+    int32_t row0, n_rows, col0, n_cols;
+} hmfe_rect_desc;
+int hmfe_spec_zero_rects(hmfe_ctx* ctx, float* d_out, int out_rows, int n_cols, int64_t n_items, const hmfe_rect_desc* h_rects,
+                         int64_t n_rects, void* stream);
+
+/* Host planner (no device work): the random draws of AudioDataset.__getitem__, method "cola"
+ * (cola_training.py:56-80; mae_training.py:64-79 adds `windowing`) for n_items items of h_rows[i] frames each, from
+ * the stream of uniforms h_u[n_u] in the reference's order: [window crop start] -> random_mask rows (second draw only
+ * after a masked frame) -> two crop starts -> two gains.  Outputs: h_mask (concatenated per-item row masks, item i at
+ * h_mask_off[i], rows counted inside the window), window / crop starts (Python int() truncation) and float32 gains.
+ * Returns the number of uniforms consumed, -100 when h_u is too short (nothing is consumed then: call again with
+ * more), HMFE_ERR_INVALID on bad arguments. */
+int64_t hmfe_cola_draws(const double* h_u, int64_t n_u, const int64_t* h_rows, int64_t n_items, int max_len, int windowing,
+                        int augment, double rate_start, double rate_seq, uint8_t* h_mask, int64_t* h_mask_off,
+                        int64_t* h_win_start, int64_t* h_start1, int64_t* h_start2, float* h_gain1, float* h_gain2);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: push `n` floats from local memory into the same offset of a buffer on EVERY GPU of the
  * node with NVLink-switch multicast stores (multimem.st).  `mc_dst` is the multicast mapping of a

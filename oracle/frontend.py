@@ -482,3 +482,76 @@ def hear_preprocess_audio(audio):
         audio = np.pad(audio, ((0, 0), (0, 32000 - audio.shape[1])))
     img = torch.as_tensor(hear_pcen(hear_mel_power(audio))).unsqueeze(1)
     return torch.nn.functional.interpolate(img, size=(192, 128), mode="bilinear", align_corners=False, antialias=False).numpy()
+
+
+class SpecAugmentation:
+    """torchlibrosa.augmentation.SpecAugmentation (torchlibrosa 0.1.0, un-vendored dependency of
+    src/benchmark/other_eval/finetuning.py:14,64-69,104-116; restated from its published source - parity unpinned
+    for the library itself, torchlibrosa is not installable here).  Training-mode DropStripes on a 4-D tensor
+    (batch, channels, time, freq), in place: per batch element and stripe ``distance = torch.randint(0, drop_width)``,
+    ``bgn = torch.randint(0, total - distance)``, time stripes (dim 2) first, then frequency stripes (dim 3); the
+    draws come from torch's global generator."""
+
+    def __init__(self, time_drop_width, time_stripes_num, freq_drop_width, freq_stripes_num):
+        self.cfg = ((2, time_drop_width, time_stripes_num), (3, freq_drop_width, freq_stripes_num))
+        self.training = True
+
+    def __call__(self, x):
+        import torch
+
+        assert x.ndimension() == 4
+        if not self.training:
+            return x
+        for dim, width, num in self.cfg:
+            total = x.shape[dim]
+            for n in range(x.shape[0]):
+                e = x[n]
+                for _ in range(num):
+                    distance = torch.randint(low=0, high=width, size=(1,))[0]
+                    bgn = torch.randint(low=0, high=total - distance, size=(1,))[0]
+                    if dim == 2:
+                        e[:, bgn : bgn + distance, :] = 0
+                    else:
+                        e[:, :, bgn : bgn + distance] = 0
+        return x
+
+
+def dataset_cola_item(x, max_len=251, augment=True, windowing=False):
+    """AudioDataset.__getitem__, method 'cola' (src/pretrain/cola_training.py:56-80; src/pretrain/mae_training.py:64-79
+    adds the ``windowing`` pre-crop to 3 * max_len)."""
+    if windowing and x.shape[0] > max_len * 3:
+        x = random_crop(x, crop_size=max_len * 3)
+    if augment:
+        x = random_mask(x)
+    x1 = random_crop(x, crop_size=max_len)
+    x2 = random_crop(x, crop_size=max_len)
+    if augment:
+        x1, x2 = random_multiply(x1), random_multiply(x2)
+    return np.asarray(x1, dtype=np.float32), np.asarray(x2, dtype=np.float32)
+
+
+def dataset_mae_item(x, max_len):
+    """AudioDataset.__getitem__, methods 'mae' / 'audiomae' (src/pretrain/mae_training.py:82-109)."""
+    p = max_len - x.shape[0]
+    if p < 0:
+        x = random_crop(x, crop_size=max_len)
+    elif p > 0:
+        x = np.pad(x, ((0, p), (0, 0)), mode="constant")
+    return x.astype(np.float32)
+
+
+def dataset_finetune_item(x, max_len=256, augment=True, crop_mode="first", spec_augment=False, time_drop_width=100,
+                          time_stripes_num=2, freq_drop_width=20, freq_stripes_num=2):
+    """AudioDataset.__getitem__ of src/benchmark/other_eval/finetuning.py:74-123 (spectrogram branch)."""
+    import torch
+
+    if max_len:
+        x = random_crop(x, crop_size=max_len) if crop_mode == "random" else crop_first(x, crop_size=max_len)
+    if augment:
+        x = random_mask(x)
+        x = random_multiply(x)
+    x = torch.tensor(x, dtype=torch.float)
+    if spec_augment:
+        aug = SpecAugmentation(time_drop_width, time_stripes_num, freq_drop_width, freq_stripes_num)
+        x = aug(x.unsqueeze(0).unsqueeze(0)).squeeze(0).squeeze(0)
+    return x.numpy()

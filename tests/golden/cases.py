@@ -105,3 +105,11 @@ HEAR_CASES = {
     "single": (32000, (104,)),
     "short": (20000, (105, 106)),
 }
+
+
+# Dataset __getitem__ fixtures (make_golden_datasets.py): pseudo-spectrogram lengths and the item order of a batch
+DATASET_SPECS = {
+    "rows64": [251, 400, 1001, 2500, 760, 300],     # >= max_len = 251; 1001 and 2500 exceed the 3 * max_len window
+    "rows128": [998, 1022, 1024, 1500, 2048, 16],   # audiomae: padded and cropped to 1024
+    "order": [3, 0, 4, 1, 2, 0, 5],
+}

@@ -326,6 +326,35 @@ def test_cache_writers_match_per_file_entry_points(wav_dir, tmp_path):
         assert np.array_equal(fb[i], ref.numpy()), n
 
 
+def test_cache_writers_resample_native_rate_files(tmp_path):
+    """CirCor recordings are 4 kHz PCM16: every file takes the resampler.  The cache writers decode
+    in worker threads but resample whole batches on the calling thread (one plan per thread, include/hmfe.h);
+    the result must equal the per-file drop-in, which resamples one file at a time."""
+    from heart_murmur_detection_b200 import audio_io, caches
+    from heart_murmur_detection_b200 import util as U
+
+    d = tmp_path / "wav4k"
+    d.mkdir()
+    names = []
+    for i, (sec, native) in enumerate([(9.0, 4000), (12.5, 4000), (3.0, 4000), (10.0, 8000), (9.5, 16000), (20.0, 4000),
+                                       (8.7, 2000), (11.0, 4000)]):
+        n = int(sec * native)
+        x = golden_signal(n * (SR // native), 900 + i, SR, 0.2, 0.3)[:: SR // native]  # decimated test tone
+        audio_io.write_wav_pcm16(str(d / f"r{i}.wav"), x, native)
+        names.append(f"r{i}")
+    files = [str(d / (n + ".wav")) for n in names]
+    for workers in (1, 8):
+        feature_dir = str(tmp_path / f"feat{workers}")
+        os.makedirs(feature_dir)
+        written, invalid = caches.write_entire_spec_cache(files, feature_dir, input_sec=8, batch_bytes=1 << 19, workers=workers)
+        per_file = {n: U.get_entire_signal_librosa(str(d), n, spectrogram=True, input_sec=8) for n in names}
+        assert invalid == sum(v is None for v in per_file.values()) == 1
+        assert [os.path.basename(w) for w in written] == [n for n in names if per_file[n] is not None]
+        for w in written:
+            got, ref = np.load(w + ".npy"), per_file[os.path.basename(w)]
+            assert got.shape == ref.shape and np.array_equal(got, ref), w
+
+
 def test_c2_full_size_properties():
     """BASELINE config 2 at full size (5 272 ragged clips, 1.78 G samples) through size-independent
     properties: the one-pass overlap band-pass equals the exact chunked scan on every sample; trim

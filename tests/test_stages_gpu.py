@@ -489,3 +489,97 @@ def test_vggish_examples_match_reference():
         check_digest(ex, g["digest"], rtol=1e-4, atol=1e-4)
     assert np.abs(V.waveform_to_examples(rec["r_short"], 16000) - arr["vggish/r_short"]).max() <= 1e-4
     assert V.waveform_to_examples(rec["r_short"][:15000], 16000).shape == (0, 96, 64)  # shorter than one example
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Dataset __getitem__ over batches (a18): fixtures from the executed reference classes (make_golden_datasets.py)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def _dataset_fixture():
+    import json as _json
+
+    from cases import DATASET_SPECS
+
+    g = _json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_datasets.json")))["cases"]
+    specs64 = [hash_spec(T, 64, seed=300 + T) for T in DATASET_SPECS["rows64"]]
+    specs128 = [hash_spec(T, 128, seed=500 + T) for T in DATASET_SPECS["rows128"]]
+    return g, specs64, specs128, DATASET_SPECS["order"]
+
+
+def _close_masked(got, ref):
+    """unmasked rows bit exact; rows replaced by the mean within one float32 rounding of the mean"""
+    same = (got == ref).all(axis=1)
+    assert np.abs(got - ref).max() <= 2e-7
+    assert same.sum() >= 0.7 * len(ref)
+
+
+@pytest.mark.gpu
+def test_cola_batch_with_windowing_matches_executed_reference():
+    """datasets.cola_batch (native draw planner + crop kernel) against mae_training.py's AudioDataset, method 'cola',
+    with and without the 3 * max_len window and augmentation: same Python RNG stream, same crops, same gains."""
+    from heart_murmur_detection_b200 import datasets as D
+    from oracle import frontend as F
+
+    g, specs64, _, order = _dataset_fixture()
+    store = D.SpecStore(specs64)
+    for windowing in (False, True):
+        for augment in (False, True):
+            fx = g[f"mae_training/cola/w{int(windowing)}a{int(augment)}"]
+            random.seed(4242)
+            x1, x2 = D.cola_batch(store, order, max_len=251, augment=augment, windowing=windowing)
+            assert rng_fingerprint() == fx["rng_after"]
+            random.seed(4242)
+            refs = [F.dataset_cola_item(specs64[i], 251, augment, windowing) for i in order]
+            assert [sha(a) for a, _ in refs] == fx["x1"]
+            for k, (r1, r2) in enumerate(refs):
+                for got, ref in ((x1[k], r1), (x2[k], r2)):
+                    got = got.cpu().numpy()
+                    if augment:
+                        _close_masked(got, ref)
+                    else:
+                        np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_mae_batch_matches_executed_reference():
+    """datasets.mae_batch against AudioDataset methods 'mae' (max_len 256, 64 mel) and 'audiomae' (1024, 128 mel):
+    random_crop draws only for the items that are too long, zero padding for the short ones; bit exact."""
+    from heart_murmur_detection_b200 import datasets as D
+
+    g, specs64, specs128, order = _dataset_fixture()
+    random.seed(77)
+    out = D.mae_batch(D.SpecStore(specs64), order, max_len=256).cpu().numpy()
+    assert [sha(np.ascontiguousarray(x)) for x in out] == g["mae_training/mae/256"]["x"]
+    assert rng_fingerprint() == g["mae_training/mae/256"]["rng_after"]
+    random.seed(78)
+    out = D.mae_batch(D.SpecStore(specs128), list(range(len(specs128))), max_len=1024).cpu().numpy()
+    assert [sha(np.ascontiguousarray(x)) for x in out] == g["mae_training/audiomae/1024"]["x"]
+    assert rng_fingerprint() == g["mae_training/audiomae/1024"]["rng_after"]
+
+
+@pytest.mark.gpu
+def test_finetune_batch_matches_executed_reference():
+    """datasets.finetune_batch against finetuning.py's AudioDataset: crop -> random_mask (mean of the CROPPED item) ->
+    random_multiply -> SpecAugmentation stripes; Python and torch generators end in the reference's states."""
+    from heart_murmur_detection_b200 import datasets as D
+    from oracle import frontend as F
+
+    g, specs64, _, order = _dataset_fixture()
+    store = D.SpecStore(specs64)
+    for name in ("first", "random_aug", "specaug", "specaug_only"):
+        fx = g[f"finetuning/{name}"]
+        random.seed(990)
+        torch.manual_seed(991)
+        out = D.finetune_batch(store, order, **fx["kw"]).cpu().numpy()
+        assert rng_fingerprint() == fx["rng_after"], name
+        assert sha(torch.get_rng_state().numpy()) == fx["torch_rng_after"], name
+        random.seed(990)
+        torch.manual_seed(991)
+        for k, i in enumerate(order):
+            ref = F.dataset_finetune_item(specs64[i], **fx["kw"])
+            assert list(out[k].shape) == fx["shape"][k]
+            assert [int(r) for r in np.flatnonzero((out[k] == 0).all(axis=1))] == fx["zero_rows"][k]
+            assert [int(c) for c in np.flatnonzero((out[k] == 0).all(axis=0))] == fx["zero_cols"][k]
+            assert np.abs(out[k] - ref).max() <= 2e-7, name
+            assert abs(float(np.asarray(out[k], np.float64).sum()) - fx["sum"][k]) <= 1e-6 * max(1.0, abs(fx["sum"][k]))

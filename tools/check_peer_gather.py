@@ -30,6 +30,25 @@ for mode in modes:
     ref = torch.empty((world * rows, cols), device=dev)
     dist.all_gather_into_tensor(ref, ref_in)
     ok = ok and torch.equal(out, ref)
+  # skewed ranks, delayed consumer, no host synchronisation between steps: rank 0 reads each gathered buffer late
+  # (a long spin kernel in front of the read) while the other ranks run two steps ahead.  Without the rendezvous
+  # before the push a fast rank would overwrite buffer i of the slow rank before it was read.
+  steps = 8
+  sums = torch.zeros((steps, world), device=dev, dtype=torch.float64)
+  for step in range(steps):
+    i = step % 2
+    ag.wait_reusable(i)
+    ag.slot(i).fill_(float(100 * step + rank + 1))
+    out = ag.gather(i)
+    ag.finish()
+    if rank == 0:
+        torch.cuda._sleep(200_000_000)  # ~0.1 s
+    sums[step] = out.view(world, rows * cols)[:, ::4097].double().mean(dim=1)
+  torch.cuda.synchronize()
+  want = torch.tensor([[100 * s_ + r + 1 for r in range(world)] for s_ in range(steps)], device=dev, dtype=torch.float64)
+  skew_ok = bool(torch.equal(sums, want))
+  if not skew_ok and rank == 0: print("mode", mode, "skewed-consumer check FAILED:", sums.tolist())
+  ok = ok and skew_ok
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
