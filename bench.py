@@ -44,8 +44,16 @@ WORKLOADS = {
 WORKLOADS["c2nf"] = ("OPERA-CT linear-probe front-end exactly as the reference's callers invoke it (no band-pass, SURVEY F4): "
                      "silence trim + zero/tile pad to >=8 s + cut at 32 s + 64-mel log-spectrogram over 5272 ragged clips "
                      "(model_util.py:161-163)")
-DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000, "c2nf": 5272}
-CPU_SAMPLE = {"c1": 2048, "c2": 768, "c3": 2048, "c2nf": 1024}
+WORKLOADS["c4"] = ("COLA continued-pretraining input: 100000 synthetic multi-site recordings of 8-60 s -> silence trim + "
+                   "whole-recording 64-mel log-spectrogram (heart_pressl.py:58-99) -> AudioDataset items: random_mask, two "
+                   "random_crops of 251 frames, two random_multiplies (cola_training.py:56-80), batch 64")
+WORKLOADS["c5"] = ("Throughput sweep: 1000000 CirCor-shaped clips (8 s @16 kHz -> [251,64]) sharded over the GPUs in chunks "
+                   "dealt round-robin, one in-place NCCL all-gather of the features per round, every rank ends with the "
+                   "[1000000,251,64] tensor in global clip order")
+DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000, "c2nf": 5272, "c4": 100000, "c5": 1000000}
+CPU_SAMPLE = {"c1": 1000, "c2": 768, "c3": 1000, "c2nf": 1024}
+LENS_SEED = 1234          # clip lengths of rank r: synth.clip_lengths(seed=LENS_SEED + r)
+SEED_STRIDE = 10_000_000  # clip i of rank r: synth.make_clip(seed = SEED_STRIDE * r + i)
 C2_KW = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
 C2NF_KW = dict(input_sec=8, butterworth_filter=None, pad=True, types="zero", max_sec=32)
 
@@ -61,7 +69,7 @@ def _cpu_process(workload, x, F):
     return 0 if fb is None else int(F.pad_to_model(fb.numpy()).shape[0])
 
 
-def _cpu_worker(rank, cores, workload, lens, repeats, barrier, queue):
+def _cpu_worker(rank, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs):
     """One host core: generate its share of the sample (untimed), then run the oracle port clip by clip."""
     try:
         from threadpoolctl import threadpool_limits
@@ -75,7 +83,12 @@ def _cpu_worker(rank, cores, workload, lens, repeats, barrier, queue):
     from heart_murmur_detection_b200 import synth
     from oracle import frontend as F
 
-    mine = [synth.make_clip(int(lens[i]), 1000 + i).numpy() for i in range(rank, len(lens), cores)]
+    mine = []
+    for i in range(rank, len(lens), cores):
+        x = synth.make_clip(int(lens[i]), seed_base + i).numpy()
+        if shared is not None:  # hand the clip to the parent: the GPU arm times the very same samples
+            np.frombuffer(shared, dtype=np.float32)[offs[i] : offs[i + 1]] = x
+        mine.append(x)
     if mine:
         _cpu_process(workload, mine[0], F)  # warm-up: imports, table construction, page-in
     spans = []
@@ -87,20 +100,33 @@ def _cpu_worker(rank, cores, workload, lens, repeats, barrier, queue):
     queue.put((rank, spans))
 
 
-def cpu_reference(workload: str, n_clips: int, repeats: int = 1):
+def sample_spec(workload, n_batch, rank=0):
+    """(lengths, seed base) of the first K clips of rank `rank`'s batch: the sample both arms share."""
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c2" if workload == "c2nf" else workload, n_batch, seed=LENS_SEED + rank)
+    k = min(n_batch, CPU_SAMPLE[workload])
+    return lens[:k], SEED_STRIDE * rank
+
+
+def cpu_reference(workload: str, lens, seed_base: int, repeats: int = 1, keep_clips: bool = False):
     """Oracle port (numpy restatement of the librosa path + live scipy / torchaudio), one clip at a
     time on every host core - mirrors the reference's one-file-at-a-time loop (model_util.py:138)
     run as `cores` independent processes, clip i on core i mod cores.  Time = first start to last
-    finish (CLOCK_MONOTONIC is shared by the processes)."""
+    finish (CLOCK_MONOTONIC is shared by the processes).  The clips are the FIRST K CLIPS OF THE GPU ARM'S BATCH
+    (same lengths, same per-clip generator seeds); with ``keep_clips`` they are returned (shared memory) so that
+    the GPU arm can place exactly these samples in its batch."""
     import multiprocessing as mp
 
-    from heart_murmur_detection_b200 import synth
-
     cores = os.cpu_count() or 1
-    lens = synth.clip_lengths("c2" if workload == "c2nf" else workload, n_clips, seed=4321)
+    n_clips = len(lens)
     ctx = mp.get_context("fork")
+    offs = np.zeros(n_clips + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    shared = ctx.RawArray("f", int(offs[-1])) if keep_clips else None
     barrier, queue = ctx.Barrier(cores), ctx.Queue()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, cores, workload, lens, repeats, barrier, queue)) for r in range(cores)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs))
+             for r in range(cores)]
     for p in procs:
         p.start()
     results = [queue.get() for _ in procs]
@@ -112,10 +138,19 @@ def cpu_reference(workload: str, n_clips: int, repeats: int = 1):
         t1 = max(sp[k][1] for _, sp in results)
         if best is None or t1 - t0 < best:
             best, frames = t1 - t0, sum(sp[k][2] for _, sp in results)
-    return {"clips_per_s": n_clips / best, "frames_per_s": frames / best, "cores": cores, "seconds": best,
-            "sample": f"{n_clips} clips of workload {workload} ({float(lens.sum()) / SR:.0f} s of audio, "
-                      f"{best * cores:.0f} core-seconds), clip i on core i mod {cores}, one process per core, "
-                      f"1 BLAS thread each"}
+    return {"clips_per_s": n_clips / best, "frames_per_s": frames / best, "cores": cores, "seconds": best, "repeats": repeats,
+            "clips": np.frombuffer(shared, dtype=np.float32) if keep_clips else None, "offsets": offs,
+            "sample": f"the first {n_clips} clips of the GPU arm's own batch of workload {workload} (same lengths, same "
+                      f"per-clip seeds; {float(np.sum(lens)) / SR:.0f} s of audio, {best * cores:.0f} core-seconds per "
+                      f"repeat, best of {repeats}), clip i on core i mod {cores}, one process per core, 1 BLAS thread each"}
+
+
+def shared_config(wl, n_clips):
+    """`config` of the JSON line: identical in the GPU arm and the reference arm (what both arms were asked to run)."""
+    return {"workload": WORKLOADS[wl], "workload_id": wl, "clips_per_gpu_per_step": n_clips,
+            "clip_lengths": f"synth.clip_lengths(seed={LENS_SEED} + rank)", "clip_seeds": f"{SEED_STRIDE} * rank + clip index",
+            "cpu_sample": f"clips 0..{min(n_clips, CPU_SAMPLE.get(wl, 0)) - 1} of rank 0's batch, generated by the host "
+                          "generator in both arms"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -169,7 +204,277 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(power) if power else None,
-                "window": "timed region + end-to-end loop (the timed region alone is shorter than nvidia-smi's period)"}
+                "window": "timed region + end-to-end loop + sub-workloads (the timed region alone is shorter than nvidia-smi's period)"}
+
+
+
+# ----------------------------------------------------------------------------- sub-workloads (embedded records)
+
+
+def _event_ms(fn, steps, warmup):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_fixed(wl, dev, steps, warmup, variant="auto"):
+    """c1 (CirCor log-mel) / c3 (Audio-MAE fbank): one kernel family on a fixed-length batch, device resident."""
+    import torch
+
+    from heart_murmur_detection_b200 import frontend, synth
+
+    hbm_peak, _ = peaks()
+    n = DEFAULT_CLIPS[wl]
+    lens = synth.clip_lengths(wl, n, seed=LENS_SEED)
+    wav, off = synth.make_batch(lens, base_seed=0, device=dev)
+    total = int(off[-1])
+    if wl == "c1":
+        plan = frontend.logmel_plan(16000, 64, 50, 8000, 1024, 512, variant)
+        rows, cols = int(plan.frame_offsets(off)[-1]), 64
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        fn = lambda: plan(wav, off, out=out)  # noqa: E731
+        frames = rows
+    else:
+        plan = frontend.fbank_plan(sample_rate=16000)
+        rows, cols = n * 1024, 128
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        fn = lambda: plan(wav, off, rows_per_clip=1024, out=out)  # noqa: E731
+        frames = int(plan.num_frames(np.diff(off)).sum())
+    _event_ms(fn, 0, warmup)
+    plan.set_profile(True)
+    ms = _event_ms(fn, steps, 0)
+    if wl == "c1":
+        p_ms, f_ms, calls = plan.profile_ms()
+        kern = {"logmel_power": p_ms / calls, "logmel_finalize": f_ms / calls}
+        alg = {"logmel_power": 4 * total + rows * cols * 4, "logmel_finalize": 2 * rows * cols * 4}
+        dom = "logmel_power"
+    else:
+        k_ms, calls = plan.profile_ms()
+        kern = {"fbank": k_ms / calls}
+        alg = {"fbank": 4 * total + rows * cols * 4}
+        dom = "fbank"
+    plan.set_profile(False)
+    ach = alg[dom] / (kern[dom] * 1e-3) / 1e9
+    return {"workload": WORKLOADS[wl], "value": n / (ms * 1e-3), "unit": "clips/s", "frames_per_s": frames / (ms * 1e-3),
+            "ms_per_step": ms, "steps": steps, "clips_per_step": n, "launches_per_step": int(plan.last_launches),
+            "kernels_ms_per_launch": {k: round(v, 4) for k, v in kern.items()},
+            "roofline": {"bound": "hbm", "kernel": dom, "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg[dom],
+                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak},
+            "l2_policy": f"inputs larger than L2 ({total * 4 / 1e6:.0f} MB of samples per step)"}
+
+
+def bench_c4(dev, rank, n_total=100000, pool=2048, max_len=251, batch=64):
+    """BASELINE config 4: producer (heart_pressl.py:58-99: trim + whole-recording log-mel, recordings shorter than
+    8 s dropped) + COLA Dataset items (cola_training.py:56-80) on the fly.  The 100 000 recordings are streamed as
+    ceil(100000 / pool) passes over a resident pool of `pool` distinct recordings (100 000 x 34 s would be 218 GB);
+    every pass re-runs the full path: kernels, host planning and the Python-RNG-exact draws."""
+    import random
+
+    import torch
+
+    from heart_murmur_detection_b200 import datasets, pipeline, synth
+
+    lens = synth.clip_lengths("c4", pool, seed=4000 + rank)
+    wav, off = synth.make_batch(lens, base_seed=SEED_STRIDE * rank + 5_000_000, device=dev)
+    total = int(off[-1])
+    rows_ub = int((1 + np.diff(off) // 512).sum())
+    out = torch.empty((rows_ub, 64), dtype=torch.float32, device=dev)
+    passes = -(-n_total // pool)
+    t_prod = t_data = 0.0
+    items = pairs_checksum = 0
+
+    def one_pass(timed):
+        nonlocal t_prod, t_data, items, pairs_checksum
+        t0 = time.perf_counter()
+        fb = pipeline.entire_signal_batch(wav, off, input_sec=8, spectrogram=True, out=out)
+        store = datasets.SpecStore.from_features(fb.features, fb.row_offsets)
+        if timed:
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        n_items = len(fb.row_offsets) - 1
+        x1, x2 = datasets.cola_batch(store, np.arange(n_items), max_len=max_len, augment=True)
+        if timed:
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            t_prod += t1 - t0
+            t_data += t2 - t1
+            items += n_items
+        return x1, x2, fb
+
+    random.seed(2024 + rank)
+    one_pass(False)
+    torch.cuda.synchronize()
+    t_begin = time.perf_counter()
+    for _ in range(passes):
+        x1, x2, fb = one_pass(True)
+    wall = time.perf_counter() - t_begin
+    n_rec = passes * pool
+    frames = int(fb.row_offsets[-1]) * passes
+    return {"workload": WORKLOADS["c4"], "value": n_rec / wall, "unit": "recordings/s", "recordings": n_rec,
+            "seconds": wall, "passes": passes, "pool_recordings": pool, "audio_seconds_per_s": passes * total / SR / wall,
+            "frames_per_s": frames / wall, "items_per_s": items / wall, "pairs_shape": [int(v) for v in x1.shape],
+            "batches_of_64_per_pass": -(-int(x1.shape[0]) // batch),
+            "producer_ms_per_pass": 1e3 * t_prod / passes, "dataset_ms_per_pass": 1e3 * t_data / passes,
+            "note": "wall clock with a device synchronise after each stage (host planning and the Python-RNG-exact "
+                    "draws are part of the path); one cola_batch call per pass = the pass's items in DataLoader order, "
+                    "i.e. consecutive batches of 64"}
+
+
+def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=1250, pool_chunks=4, passes=2):
+    """BASELINE config 5, STRONG scaling: the job is fixed (1 M clips); chunks of `chunk` clips are dealt round-robin
+    (dist.chunk_rounds), every rank writes its features in place into the global-order tensor and each round is
+    completed by one in-place NCCL all-gather on a side stream, overlapped with the next round's kernels.  Input
+    clips come from a resident pool (1 M x 512 KB = 512 GB does not fit): global clip g is pool clip g mod pool."""
+    import torch
+    import torch.distributed as dist
+
+    from heart_murmur_detection_b200 import dist as hd
+    from heart_murmur_detection_b200 import frontend, synth
+
+    n_samp, T = 8 * SR, 251
+    pool = chunk * pool_chunks
+    wav, _ = synth.make_batch(np.full(pool, n_samp, dtype=np.int64), base_seed=77_000_000, device=dev)  # same on every rank
+    off = np.arange(chunk + 1, dtype=np.int64) * n_samp
+    plan = frontend.logmel_plan(16000, 64, 50, 8000, 1024, 512, variant)
+    rounds = hd.chunk_rounds(n_total, chunk, world)
+    final = torch.empty((n_total * T, 64), dtype=torch.float32, device=dev)
+    rows_chunk = chunk * T
+    comm = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+
+    def job(gather):
+        for j in range(rounds):
+            c = j * world + rank
+            pc = c % pool_chunks
+            plan(wav[pc * chunk * n_samp : (pc + 1) * chunk * n_samp], off, out=final[c * rows_chunk : (c + 1) * rows_chunk])
+            if gather and world > 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    hd.all_gather_round_inplace(final, j, rows_chunk)
+        main.wait_stream(comm)
+
+    def timed(gather):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        job(gather)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    final.zero_()
+    timed(True)  # warm-up pass (also the pass the identity check reads)
+    # in-run identity check: sampled clips of the gathered tensor == the same clip computed alone on this rank (P = 1)
+    rng = np.random.default_rng(5)
+    sample = np.unique(np.concatenate([rng.integers(0, n_total, size=24), [0, n_total - 1, chunk * world - 1, chunk * world]]))
+    one = np.array([0, n_samp], dtype=np.int64)
+    same = True
+    for g in sample:
+        pc, i = (int(g) // chunk) % pool_chunks, int(g) % chunk
+        ref, _ = plan(wav[(pc * chunk + i) * n_samp : (pc * chunk + i + 1) * n_samp], one)
+        same = same and bool(torch.equal(final[int(g) * T : (int(g) + 1) * T], ref))
+    flag = torch.tensor([1 if same else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ms = min(timed(True) for _ in range(passes))
+    ms_compute = timed(False) if world > 1 else ms
+    del final
+    torch.cuda.empty_cache()
+    return {"workload": WORKLOADS["c5"], "value": n_total / (ms * 1e-3), "unit": "clips/s", "scaling": "strong",
+            "n_gpus": world, "clips_total": n_total, "frames_per_s": n_total * T / (ms * 1e-3), "ms_per_job": ms,
+            "ms_per_job_compute_only": ms_compute, "value_compute_only": n_total / (ms_compute * 1e-3),
+            "rounds": rounds, "chunk_clips": chunk, "pool_clips": pool,
+            "gathered_bytes_per_rank": (world - 1) * (n_total // world) * T * 64 * 4,
+            "nvlink_rx_gbs_per_gpu": ((world - 1) * (n_total // world) * T * 64 * 4) / (ms * 1e-3) / 1e9 if world > 1 else 0.0,
+            "collective": "none" if world == 1 else "in-place NCCL all_gather_into_tensor per round on a side stream",
+            "identity_check": {"sampled_clips": int(sample.size), "bit_identical_to_p1_on_every_rank": bool(flag.item()),
+                               "how": "gathered rows of sampled global clips == the same clip run alone through the same plan"},
+            "passes_timed": passes, "timing": "CUDA events around one whole job, barrier + synchronise both sides, max over ranks, best pass"}
+
+
+def check_all_gather_features(dev, rank, world):
+    """The ragged product path on NCCL, outside the timed region: one global ragged batch (identical on every rank),
+    dist.shard_by_length -> local pipeline -> dist.all_gather_features (metadata gathers + order-restoring index_select)
+    must equal the single-GPU result computed locally, bit for bit."""
+    import torch
+    import torch.distributed as dist
+
+    from heart_murmur_detection_b200 import dist as hd
+    from heart_murmur_detection_b200 import pipeline, synth
+
+    n = 256
+    lens = synth.clip_lengths("c2", n, seed=99)
+    wav, off = synth.make_batch(lens, base_seed=123_000_000, device=dev)
+    kw = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32, spectrogram=True)
+    full = pipeline.entire_signal_batch(wav, off, **kw)
+    shard = hd.shard_by_length(lens, world)[rank]
+    lo = np.zeros(len(shard) + 1, dtype=np.int64)
+    np.cumsum(lens[shard], out=lo[1:])
+    lw = torch.cat([wav[int(off[i]) : int(off[i + 1])] for i in shard])
+    res = pipeline.entire_signal_batch(lw, lo, **kw)
+    rows = np.zeros(len(shard), dtype=np.int64)
+    rows[res.chunks.clip_ids] = np.diff(res.row_offsets)
+    out, ro = hd.all_gather_features(res.features[: int(res.row_offsets[-1])], rows, shard, n)
+    ref = full.features[: int(full.row_offsets[-1])]
+    ok = out.shape == ref.shape and bool(torch.equal(out, ref))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"api": "dist.shard_by_length + pipeline.entire_signal_batch + dist.all_gather_features", "clips": n,
+            "rows": int(ref.shape[0]), "bit_identical_to_p1_on_every_rank": bool(flag.item())}
+
+
+def run_sub_as_main(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_begin = time.perf_counter()
+    if wl == "c5":
+        rec = bench_c5(dev, rank, world, args.variant, n_total=args.clips or DEFAULT_CLIPS["c5"])
+        scaling = "strong"
+    else:
+        rec = bench_c4(dev, rank, n_total=args.clips or DEFAULT_CLIPS["c4"])
+        if world > 1:
+            t = torch.tensor([rec["value"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            rec["value"] = float(t.item())
+        scaling = "weak"
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+    if rank == 0:
+        line = {"metric": "front-end clips/s", "value": rec["value"], "unit": rec["unit"], "n_gpus": world,
+                "steps": rec.get("passes_timed", rec.get("passes", 1)), "warmup": 1,
+                "ms_per_step": rec.get("ms_per_job", 1e3 * rec.get("seconds", 0.0)), "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": shared_config(wl, args.clips or DEFAULT_CLIPS[wl]), "e2e": None,
+                "e2e_note": "inputs are generated on the device (c5: 512 GB of samples would not fit the host); the "
+                            "end-to-end figure of the path is the default workload's",
+                "workloads": {wl: rec}, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------- main
@@ -202,13 +507,17 @@ def measured_traffic(workload, kernel, n_clips):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = CPU_SAMPLE[args.workload]
-    r = cpu_reference(args.workload, n, repeats=max(1, min(args.steps, 3)))
+    wl = args.workload
+    n_batch = args.clips or DEFAULT_CLIPS[wl]
+    lens, seed_base = sample_spec(wl, n_batch)
+    # every "step" of this arm is one pass over the bounded sample; the run is sized to end within minutes
+    repeats = max(1, min(args.steps, 3))
+    r = cpu_reference(wl, lens, seed_base, repeats=repeats)
     line = {
         "impl": "reference", "metric": "front-end clips/s", "value": r["clips_per_s"], "unit": "clips/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3,
+        "n_gpus": args.gpus, "steps": repeats, "steps_requested": args.steps, "warmup": 1, "ms_per_step": r["seconds"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT + f64 IIR / f32 mel (numpy, scipy)",
-        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload], "sample_clips": n},
+        "data": "synthetic", "config": shared_config(wl, n_batch),
         "frames_per_s": r["frames_per_s"],
         "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
@@ -228,6 +537,7 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (0 = the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the embedded c1 / c3 / c4 / c5 sub-records")
     ap.add_argument("--gather", default="auto", choices=["auto", "copy", "multicast", "nccl"],
                     help="N > 1: all-gather through peer memory (dist.PeerAllGather: copy engines or NVLink multicast "
                          "push) or NCCL.  auto = copy engines up to 4 GPUs, NCCL beyond (measured, DESIGN.md section 8)")
@@ -244,9 +554,14 @@ def main():
         return
 
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork safety)
-    cpu = None
+    if wl in ("c4", "c5"):
+        return run_sub_as_main(args, rank, world, local_rank)
+    cpu, host_clips = None, None
+    n_clips = args.clips or DEFAULT_CLIPS[wl]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(wl, CPU_SAMPLE[wl], repeats=2)
+        k_lens, k_seed = sample_spec(wl, n_clips)
+        r = cpu_reference(wl, k_lens, k_seed, repeats=2, keep_clips=True)
+        host_clips = (r["clips"], r["offsets"])
         cpu = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "frames_per_s": r["frames_per_s"]}
 
@@ -260,10 +575,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_clips = args.clips or DEFAULT_CLIPS[wl]
-    lens = synth.clip_lengths("c2" if wl == "c2nf" else wl, n_clips, seed=1234 + rank)
+    lens = synth.clip_lengths("c2" if wl == "c2nf" else wl, n_clips, seed=LENS_SEED + rank)
     kw2 = C2NF_KW if wl == "c2nf" else C2_KW
-    wav, off = synth.make_batch(lens, base_seed=10_000_000 * rank, device=dev)
+    wav, off = synth.make_batch(lens, base_seed=SEED_STRIDE * rank, device=dev)
+    if host_clips is not None:  # the clips the CPU arm timed ARE the first K clips of this batch, bit for bit
+        wav[: host_clips[0].size].copy_(torch.from_numpy(host_clips[0]))
+        assert np.array_equal(host_clips[1], off[: host_clips[1].size])
+        host_clips = None
     total_samples = int(off[-1])
     ctx = frontend.default_ctx()
     lm_plan = frontend.logmel_plan(16000, 64, 50, 8000, 1024, 512, args.variant)
@@ -465,16 +783,32 @@ def main():
                                        "h2d_bytes_per_step": total_samples * 2, "ms_per_step": float(t.item()) * 1e3,
                                        "note": "same API, host buffer = 16-bit PCM WAV payload (quantised copy of the "
                                                "synthetic clips), int16 -> float32 / 32768 on the device"}
+    # ---- the other BASELINE configs as sub-records of the same line (c1, c3, c4 at N = 1; the c5 sweep at every N)
+    chunk_samples = int(state["res"].chunks.lengths.sum()) if wl in ("c2", "c2nf") else total_samples
+    launches_per_step = int(state["launches"])
+    subs = {}
+    if not args.no_sub and wl == "c2":
+        state.clear()
+        h_wav = h_out = h_pcm = h_out16 = None  # noqa: F841
+        del wav, work_buf, send, out
+        if world > 1 and peer_ag is None:
+            del gathered
+        peer_ag = None if peer_ag is None else peer_ag  # symmetric buffers stay (freed at exit)
+        pipeline._host_pipes.clear()
+        torch.cuda.empty_cache()
+        if world == 1:
+            subs["c1"] = bench_fixed("c1", dev, args.steps, args.warmup, args.variant)
+            subs["c3"] = bench_fixed("c3", dev, args.steps, args.warmup)
+            subs["c4"] = bench_c4(dev, rank)
+        else:
+            subs["gather_check"] = check_all_gather_features(dev, rank, world)
+        subs["c5"] = bench_c5(dev, rank, world, args.variant)
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
         # algorithmic bytes per launch of each kernel
         out_bytes = rows * n_cols * 4
-        if wl in ("c2", "c2nf"):
-            chunk_samples = int(state["res"].chunks.lengths.sum())
-        else:
-            chunk_samples = total_samples
         alg = {
             "logmel_power": 4 * chunk_samples + out_bytes,
             "logmel_finalize": 2 * out_bytes,
@@ -503,18 +837,19 @@ def main():
             "metric": "front-end clips/s", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (FFT, mel) + f64 (IIR)", "data": "synthetic",
-            "config": {"workload": WORKLOADS[wl], "workload_id": wl, "clips_per_gpu_per_step": n_clips,
-                       "audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
-                       "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
-                       "collective": ("none" if world == 1 else f"peer-memory all-gather of the row-padded features (symmetric memory, {peer_ag.mode}, device barrier), overlapped with the next step's kernels" if peer_ag is not None else "NCCL all_gather_into_tensor(row-padded features), overlapped with the next step's kernels"),
-                       **({"iir_plan": iir_plan} if iir_plan else {})},
+            "config": shared_config(wl, n_clips),
+            "run": {"audio_seconds_per_gpu_per_step": total_samples / SR, "variant": args.variant,
+                    "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB of samples per step)",
+                    "collective": ("none" if world == 1 else f"peer-memory all-gather of the row-padded features (symmetric memory, {peer_ag.mode}, device barrier), overlapped with the next step's kernels" if peer_ag is not None else "NCCL all_gather_into_tensor(row-padded features), overlapped with the next step's kernels"),
+                    **({"iir_plan": iir_plan} if iir_plan else {})},
             "frames_per_s": world * n_frames_valid / (ms_step * 1e-3),
             "audio_seconds_per_s": world * total_samples / SR / (ms_step * 1e-3),
             "e2e": e2e,
-            "gpu_launches": int(state["launches"]) * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "workloads": subs,
         }
         print(json.dumps(line))
     if world > 1:

@@ -57,6 +57,7 @@ hmfe_logmel_batch_views2 = _sig(
     "hmfe_logmel_batch_views2", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
 )
 hmfe_logmel_last_launches = _sig("hmfe_logmel_last_launches", C.c_int, c_voidp)
+hmfe_logmel_tc_status = _sig("hmfe_logmel_tc_status", C.c_int, c_voidp, C.POINTER(C.c_uint32))
 hmfe_logmel_set_profile = _sig("hmfe_logmel_set_profile", C.c_int, c_voidp, C.c_int)
 hmfe_logmel_profile_ms = _sig(
     "hmfe_logmel_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)

@@ -10,102 +10,10 @@
 #include <vector>
 
 #include "api_common.h"
-#include "logmel_core.cuh"
+#include "logmel_batch.cuh"
 #include "tables.h"
 
 namespace hmfe {
-
-constexpr int kMaxSlots = 8;
-constexpr int kTileElems = 32 * kXStride;  // 1056 >= kBinsPad
-
-struct MelMeta {
-    int n_slots, total_trip, n_mels;
-    int trip[kMaxSlots], wbase[kMaxSlots];
-};
-
-struct LogmelBatch {
-    const float* wav;
-    const float* wav_alt;        // second sample buffer: clips with a negative start s live at wav_alt[-s - 1]
-    float* out;
-    const int64_t* clip_start;   // [n_clips] ragged only: first sample of each clip in wav
-    const int64_t* clip_len;     // [n_clips] ragged only
-    const int64_t* frame_off;    // [n_clips+1] ragged only
-    const int64_t* item_prefix;  // [n_clips+1] ragged only
-    unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
-    unsigned long long* queue;   // next unclaimed work item (dynamic distribution over the warps)
-    int64_t n_clips, n_items;
-    int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
-    int hop;
-    int stagger_ns;  // start-up delay per warp index (HMFE_LOGMEL_STAGGER_NS overrides the default)
-};
-
-struct LogmelTables {
-    const float* win;   // 1024, 0.5 * Hann
-    const float2* tw;   // [32][32]
-    const float* melw;  // [total_trip][32]
-    const int* start;   // [n_slots][32]
-    const int* row;     // [n_slots][32]
-};
-
-HMFE_D float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-HMFE_D f32x2 shfl(f32x2 v, int src) {
-    return f32x2{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
-}
-
-// Work item descriptor: 2*NV consecutive frames of one clip.
-struct ItemCtx {
-    const float* x;  // clip samples
-    float* o;        // clip output rows
-    int64_t clip;
-    int nsamp, T, f0;
-    bool valid;
-};
-
-template <int FR>
-HMFE_D ItemCtx locate_item(const LogmelBatch& b, int n_mels, int64_t item, int64_t it_end, int64_t& clip) {
-    ItemCtx c;
-    c.valid = item < it_end;
-    if (!c.valid) {
-        c.x = b.wav;
-        c.o = b.out;
-        c.clip = 0;
-        c.nsamp = c.T = c.f0 = 0;
-        return c;
-    }
-    int64_t q;
-    if (b.uniform_items > 0) {
-        clip = item / b.uniform_items;
-        q = item - clip * b.uniform_items;
-        c.nsamp = b.uniform_n;
-        c.T = b.uniform_T;
-        c.x = b.wav + clip * (int64_t)c.nsamp;
-        c.o = b.out + clip * (int64_t)c.T * n_mels;
-    } else {
-        if (clip < 0 || item >= b.item_prefix[min(clip + 4, b.n_clips)]) {
-            // first item of this warp, or a jump to a far block: binary search, largest c with prefix[c] <= item
-            int64_t lo = max(clip, (int64_t)0), hi = b.n_clips;
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (b.item_prefix[mid] <= item)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            clip = lo;
-        }
-        while (item >= b.item_prefix[clip + 1]) ++clip;
-        q = item - b.item_prefix[clip];
-        c.nsamp = (int)b.clip_len[clip];
-        const int64_t f0g = b.frame_off[clip];
-        c.T = (int)(b.frame_off[clip + 1] - f0g);
-        const int64_t s0 = b.clip_start[clip];
-        c.x = s0 >= 0 ? b.wav + s0 : b.wav_alt + (-s0 - 1);
-        c.o = b.out + f0g * n_mels;
-    }
-    c.clip = clip;
-    c.f0 = (int)q * FR;
-    return c;
-}
 
 // raw[t][h][n2] = sample (lane + 32*n2) of frame f0 + 2t + h (zero outside the clip / beyond T)
 template <int NV, bool REFLECT = false>
@@ -533,23 +441,11 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
 
 using namespace hmfe;
 
-struct hmfe_logmel_plan {
-    int sample_rate, n_fft, hop, n_mels, n_bins, variant;
-    int pad_mode = HMFE_PAD_CONSTANT;
-    double f_min, f_max;
-    std::vector<float> mel_dense;
-    MelMeta meta;
-    float *d_win = nullptr, *d_melw = nullptr;
-    float2* d_tw = nullptr;
-    int *d_start = nullptr, *d_row = nullptr;
-    size_t table_smem = 0;
-    DescRing ring;
-    int last_launches = 0;
-    int sm_count = 148;
-    // optional per-kernel timing (bench.py roofline): events recorded on the launch stream
-    bool profile = false;
-    std::vector<cudaEvent_t> prof_events;  // triples: before power, after power, after finalize
-};
+namespace hmfe {  // logmel_tc.cu
+std::vector<uint32_t> tc_build_a_words(const std::vector<float>& mel_dense, int n_mels, int n_bins);
+bool tc_shape_ok(const hmfe_logmel_plan* p);
+int launch_logmel_tc(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st);
+}  // namespace hmfe
 
 template <typename T>
 static int upload_vec(const std::vector<T>& v, T** dptr) {
@@ -629,7 +525,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
                  n_mels, 32 * kMaxSlots);
     HMFE_REQUIRE(sample_rate > 0 && f_min >= 0 && f_max > f_min && f_max <= 0.5 * sample_rate + 1e-9,
                  "bad frequency range [%g, %g] for sr=%d", f_min, f_max, sample_rate);
-    HMFE_REQUIRE(variant >= 0 && variant <= 3, "bad variant %d", variant);
+    HMFE_REQUIRE(variant >= 0 && variant <= 4, "bad variant %d", variant);
     hmfe_logmel_plan* p = new (std::nothrow) hmfe_logmel_plan();
     HMFE_REQUIRE(p != nullptr, "out of host memory");
     p->sample_rate = sample_rate;
@@ -642,7 +538,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
     p->variant = variant == HMFE_VARIANT_AUTO ? HMFE_VARIANT_PACKED : variant;
     p->sm_count = device_sm_count();
     p->mel_dense = mel_filterbank_slaney(sample_rate, n_fft, n_mels, f_min, f_max);
-    const int group = p->variant == HMFE_VARIANT_PACKED ? 8 : 16;  // lanes per shared-memory phase (16 B / 8 B elements)
+    const int group = (p->variant == HMFE_VARIANT_PACKED || p->variant == HMFE_VARIANT_TC) ? 8 : 16;  // lanes per shared-memory phase (16 B / 8 B elements)
     const BandedMel bm = build_banded(p->mel_dense, n_mels, p->n_bins, group, kBinsPad);
     if (!verify_banded(bm, p->mel_dense, kBinsPad)) {
         set_error("internal error: banded mel tables do not reproduce the mel basis");
@@ -663,6 +559,18 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
     if (rc == HMFE_OK) rc = upload_vec(bm.w, &p->d_melw);
     if (rc == HMFE_OK) rc = upload_vec(bm.start, &p->d_start);
     if (rc == HMFE_OK) rc = upload_vec(bm.row, &p->d_row);
+    p->tc_ok = tc_shape_ok(p);
+    if (p->variant == HMFE_VARIANT_TC && !p->tc_ok) {
+        set_error("the tensor-core variant needs n_mels <= 64, hop <= 512 and a zero Nyquist weight; use HMFE_VARIANT_PACKED");
+        hmfe_logmel_plan_destroy(p);
+        return HMFE_ERR_UNSUPPORTED;
+    }
+    if (rc == HMFE_OK && p->tc_ok) {
+        rc = upload_vec(tc_build_a_words(p->mel_dense, n_mels, p->n_bins), &p->d_tc_a);
+        if (rc == HMFE_OK) rc = upload_vec(std::vector<uint32_t>(4, 0u), &p->d_tc_status);
+        const char* e = getenv("HMFE_TC_FFT_WARPS");
+        if (e) p->tc_fft_warps = atoi(e) <= 8 ? 8 : 11;
+    }
     if (rc != HMFE_OK) {
         hmfe_logmel_plan_destroy(p);
         return rc;
@@ -680,6 +588,8 @@ void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
     cudaFree(p->d_melw);
     cudaFree(p->d_start);
     cudaFree(p->d_row);
+    cudaFree(p->d_tc_a);
+    cudaFree(p->d_tc_status);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     delete p;
 }
@@ -687,6 +597,7 @@ void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
 int hmfe_logmel_plan_set_pad_mode(hmfe_logmel_plan* p, int pad_mode) {
     HMFE_REQUIRE(p, "NULL plan");
     HMFE_REQUIRE(pad_mode == HMFE_PAD_CONSTANT || pad_mode == HMFE_PAD_REFLECT, "bad pad_mode %d", pad_mode);
+    if (pad_mode == HMFE_PAD_REFLECT && p->variant == HMFE_VARIANT_TC) p->variant = HMFE_VARIANT_PACKED;  // same tables
     if (pad_mode == HMFE_PAD_REFLECT && p->variant != HMFE_VARIANT_PACKED) {
         set_error("reflect padding is built for the default (packed) variant only");
         return HMFE_ERR_UNSUPPORTED;
@@ -704,6 +615,14 @@ int hmfe_logmel_mel_basis(const hmfe_logmel_plan* p, float* h_out) {
 }
 
 int hmfe_logmel_last_launches(const hmfe_logmel_plan* p) { return p ? p->last_launches : 0; }
+
+int hmfe_logmel_tc_status(hmfe_logmel_plan* p, uint32_t* h_status) {
+    HMFE_REQUIRE(p && h_status, "NULL argument");
+    *h_status = 0;
+    if (!p->d_tc_status) return HMFE_OK;
+    HMFE_CHECK_CUDA(cudaMemcpy(h_status, p->d_tc_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return HMFE_OK;
+}
 
 int hmfe_logmel_set_profile(hmfe_logmel_plan* p, int enable) {
     HMFE_REQUIRE(p, "NULL plan");
@@ -746,7 +665,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
     HMFE_REQUIRE(d_wav && d_out, "NULL device pointer");
     HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "d_out must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int FR = p->variant == HMFE_VARIANT_PACKED ? 4 : 2;
+    const int FR = (p->variant == HMFE_VARIANT_PACKED || p->variant == HMFE_VARIANT_TC) ? 4 : 2;
 
     bool uniform = true;
     const int64_t n0 = h_lengths[0];
@@ -767,6 +686,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
     b.out = d_out;
     b.n_clips = n_clips;
     b.hop = p->hop;
+    b.status = p->d_tc_status;
     {
         const char* e = getenv("HMFE_LOGMEL_STAGGER_NS");
         b.stagger_ns = e ? atoi(e) : 500;  // measured on B200, c1: 0 -> 0.323 ms, 200 -> 0.308, 400..2000 -> 0.302-0.303
@@ -818,7 +738,8 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
         }
         HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
     }
-    int rc = p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
+    int rc = p->variant == HMFE_VARIANT_TC       ? launch_logmel_tc(p, b, st)
+             : p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
              : p->variant == HMFE_VARIANT_PAIR ? launch_pair(p, b, st)
                                                : launch_power<float, 8, 2>(p, b, st);
     if (rc != HMFE_OK) return rc;

@@ -1,0 +1,547 @@
+// Log-mel power kernel with the mel projection on the 5th-generation tensor cores (sm_100a): replaces
+// librosa.feature.melspectrogram inside pre_process_audio_mel_t (/root/reference/src/util.py:481-492) like
+// logmel.cu, with the `einsum('ft,mf->mt', S, mel_basis)` of that call as tcgen05.mma instead of shared-memory FMAs.
+//
+// One CTA per SM, 16 warps in 4 warpgroups with re-allocated registers (setmaxnreg):
+//   warps 0-3    "epilogue": tensor-memory lane quarter q = warp; read the accumulators (tcgen05.ld), add the four
+//                partial products, store the mel rows, clip max / min
+//   warps 4..    NF "FFT" warps, each autonomous as in logmel.cu: claim 4-frame items, window + 1024-point FFT of two
+//                packed transforms, power -> bf16 (hi, lo) pairs -> the warp's B tile in shared memory
+//   warp 15      "MMA": one thread issues the 32 tcgen05.mma (K = 16 each) of every ready tile and commits them
+// Frames reach shared memory by 1-D bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) issued one item ahead and
+// completed on an mbarrier; no thread waits for global memory.
+//
+// The contraction D[128 x 16] = A[128 x 512] * B[16 x 512]^T per item:
+//   A (tensor memory, loaded once per CTA): row 32q + i = mel 16q + i as bf16 "hi" (i < 16) or "lo" (i >= 16) part of
+//     the float32 Slaney weight, w = hi + lo to 2^-17; K is the FFT bin PERMUTED so that a lane's 16 bins
+//     (lane + 32 k1) are two 16-byte chunks: kappa = 8 lane + 256 (k1 / 8) + k1 % 8
+//   B (shared memory, K-major, 128-byte swizzle, 8 rows stored): rows 0-3 = bf16 hi part of the power of frames 0-3,
+//     rows 4-7 = lo part; rows 8-15 of the N = 16 instruction alias the next K atom, their D columns are never read
+//   mel[m][frame j] = D[hi row m][j] + D[hi row m][4 + j] + D[lo row m][j] + D[lo row m][4 + j]
+// i.e. all four products of (w_hi + w_lo)(p_hi + p_lo): relative error ~1e-5, inside the 1e-4 max|S| budget.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "api_common.h"
+#include "logmel_batch.cuh"
+#include "tables.h"
+#include "tc_ptx.cuh"
+
+namespace hmfe {
+
+using namespace tc;
+
+constexpr int kTcThreads = 512;
+constexpr int kRegionBytes = 19456;                        // per FFT warp: [B tile 8192 | frame staging 11264]
+constexpr int kPowerBytes = 8192;                          //   the 16 896-byte FFT exchange tile overlays both
+constexpr int kTmemCols = 512, kTmemD = 256, kDCols = 16;  // A: columns 0-255, accumulator of FFT warp w: 256 + 16 w
+constexpr int kMmaWarp = 15;
+static_assert(32 * kXStride * 16 <= kRegionBytes, "exchange tile must fit its region");
+
+enum : uint32_t {
+    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrMmaSpin = 16u,
+};
+
+struct __align__(16) TcMeta {
+    float* out;     // first output row of the item
+    int64_t clip;
+    int nvalid;     // frames of the item that exist (1..4)
+    int pad_[3];
+};
+
+struct TcTables {
+    const float* win;
+    const float2* tw;
+    const uint32_t* a_words;  // [128][256]
+};
+
+struct TcSmem {  // pointers into the dynamic shared memory of the CTA
+    uint8_t* regions;
+    float2* tw;
+    float* win;
+    uint64_t *full, *ready, *dfree, *raw;
+    TcMeta* meta;
+    uint32_t *tmem, *done;
+};
+
+template <int NF>
+HMFE_TC_D TcSmem carve(uint8_t* base) {
+    TcSmem s;
+    s.regions = base;
+    uint8_t* p = base + NF * kRegionBytes;
+    s.tw = reinterpret_cast<float2*>(p);
+    p += 1024 * sizeof(float2);
+    s.win = reinterpret_cast<float*>(p);
+    p += 1024 * sizeof(float);
+    s.full = reinterpret_cast<uint64_t*>(p);
+    s.ready = s.full + NF;
+    s.dfree = s.ready + NF;
+    s.raw = s.dfree + NF;
+    p += 4 * NF * sizeof(uint64_t);
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    s.meta = reinterpret_cast<TcMeta*>(p);
+    p += NF * sizeof(TcMeta);
+    s.tmem = reinterpret_cast<uint32_t*>(p);
+    s.done = s.tmem + 1;
+    return s;
+}
+template <int NF>
+constexpr size_t tc_smem_bytes() {
+    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + 4 * NF * 8 + 16 + NF * sizeof(TcMeta) + 16;
+}
+
+// Frame span of an item in its clip, and where it sits in the staging buffer.
+struct Span {
+    const float* src;  // 16-byte aligned global address
+    uint32_t bytes;    // multiple of 16 (0: nothing to copy)
+    int soff;          // staging index of clip sample i is i + soff
+    bool interior;     // all four frames exist and none needs zero padding
+};
+HMFE_TC_D Span item_span(const ItemCtx& c, int hop) {
+    Span s;
+    s.src = c.x;
+    s.bytes = 0;
+    s.soff = 0;
+    s.interior = false;
+    if (!c.valid) return s;
+    const int last_frame = min(c.f0 + 3, c.T - 1);
+    const int first = max(0, c.f0 * hop - kNfft / 2);
+    const int end = min(c.nsamp, last_frame * hop + kNfft / 2);
+    if (end > first) {
+        const float* g = c.x + first;
+        const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
+        s.src = g - skip;
+        s.bytes = (uint32_t)(((end - first + skip) * 4 + 15) & ~15);
+        s.soff = skip - first;
+    }
+    s.interior = c.f0 + 3 < c.T && c.f0 * hop - kNfft / 2 >= 0 && (c.f0 + 3) * hop + kNfft / 2 <= c.nsamp;
+    return s;
+}
+
+// bf16 (hi, lo) split of eight powers -> one 16-byte chunk each
+HMFE_TC_D void split8(const float (&p)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float p0 = p[2 * e], p1 = p[2 * e + 1];
+        h[e] = pack_bf16x2(p0, p1);
+        const float h0 = __uint_as_float(h[e] << 16), h1 = __uint_as_float(h[e] & 0xffff0000u);
+        l[e] = pack_bf16x2(p0 - h0, p1 - h1);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+HMFE_TC_D void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ FFT warps
+template <int NF, bool HOP512>
+HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane, int n_mels) {
+    using V = f32x2;
+    constexpr int FR = 4;
+    uint8_t* region = sm.regions + w * kRegionBytes;
+    xelem<V>* tile = reinterpret_cast<xelem<V>*>(region);
+    const float* stage = reinterpret_cast<const float*>(region + kPowerBytes);
+    const uint32_t tile_addr = smem_u32(region), stage_addr = tile_addr + kPowerBytes;
+    const uint32_t bar_full = smem_u32(sm.full + w), bar_ready = smem_u32(sm.ready + w), bar_free = smem_u32(sm.dfree + w),
+                   bar_raw = smem_u32(sm.raw + w);
+    const int hop = HOP512 ? 512 : b.hop;
+
+    constexpr int kItemBlock = 8;
+    const int64_t it_end = b.n_items;
+    auto claim = [&]() -> int64_t {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
+        return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+    };
+    int64_t blk_end = 0;
+    auto next_item = [&](int64_t item) -> int64_t {
+        if (item + 1 < blk_end) return item + 1;
+        if (item >= it_end) return item;
+        const int64_t nb = claim();
+        blk_end = nb + kItemBlock;
+        return nb;
+    };
+    auto issue_raw = [&](const Span& s) {  // lane 0
+        if (s.bytes) {
+            mbar_expect_tx(bar_raw, s.bytes);
+            bulk_g2s(stage_addr, s.src, s.bytes, bar_raw);
+        } else {
+            mbar_arrive(bar_raw);
+        }
+    };
+    int64_t clip_cursor = -1;
+    if (b.stagger_ns > 0) __nanosleep((unsigned)(w * b.stagger_ns));
+    int64_t item = claim();
+    blk_end = item + kItemBlock;
+    ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
+    Span span = item_span(cur, hop);
+    if (lane == 0 && item < it_end) issue_raw(span);
+    uint32_t n_done = 0;
+    bool ok = true;
+
+    while (item < it_end && ok) {
+        if (!mbar_wait(bar_raw, n_done & 1)) {
+            if (lane == 0) atomicOr(b.status, kErrRawWait);
+            ok = false;
+            break;
+        }
+        V re[32], im[32];
+        {
+            const float* sp = stage + span.soff + cur.f0 * hop - kNfft / 2 + lane;  // sample `lane` of frame f0
+            if (HOP512 && span.interior) {
+                // 50 % overlap: frame j = half-frames (j, j + 1) of the span, every staged sample is read once
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    float h5[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) h5[q] = sp[512 * q + 32 * m];
+                    const float w0 = sm.win[lane + 32 * m], w1 = sm.win[lane + 32 * (m + 16)];
+                    re[brev(m, 5)] = vmuls(V{h5[0], h5[2]}, w0);
+                    im[brev(m, 5)] = vmuls(V{h5[1], h5[3]}, w0);
+                    re[brev(m + 16, 5)] = vmuls(V{h5[1], h5[3]}, w1);
+                    im[brev(m + 16, 5)] = vmuls(V{h5[2], h5[4]}, w1);
+                }
+            } else if (span.interior) {
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) {
+                    const float wv = sm.win[lane + 32 * n2];
+                    const float* q = sp + 32 * n2;
+                    re[brev(n2, 5)] = vmuls(V{q[0], q[2 * hop]}, wv);
+                    im[brev(n2, 5)] = vmuls(V{q[hop], q[3 * hop]}, wv);
+                }
+            } else {
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) {
+                    const float wv = sm.win[lane + 32 * n2];
+                    float x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = (cur.f0 + j) * hop - kNfft / 2 + lane + 32 * n2;
+                        x[j] = (cur.f0 + j < cur.T && i >= 0 && i < cur.nsamp) ? stage[i + span.soff] : 0.0f;
+                    }
+                    re[brev(n2, 5)] = vmuls(V{x[0], x[2]}, wv);
+                    im[brev(n2, 5)] = vmuls(V{x[1], x[3]}, wv);
+                }
+            }
+        }
+        __syncwarp();
+        int64_t nitem = item;
+        ItemCtx nxt = cur;
+        Span nspan = span;
+        // both 32-point passes run the same unrolled butterfly code (one copy in the instruction cache)
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            fft_dit<32, V>(re, im);
+            if (pass == 0) {
+                apply_twiddle<V>(lane, sm.tw, re, im);
+                // the tensor core must be done with the previous B tile before the exchange overwrites it
+                if (n_done > 0 && !mbar_wait(bar_full, (n_done - 1) & 1)) {
+                    if (lane == 0) atomicOr(b.status, kErrFullWait);
+                    ok = false;
+                }
+                exchange_store<V>(lane, tile, re, im);
+                __syncwarp();
+                exchange_load<V>(lane, tile, re, im);
+                __syncwarp();
+                // the staging area is free again: claim the next item and start the copy of its frames
+                nitem = next_item(item);
+                nxt = locate_item<FR>(b, n_mels, nitem, it_end, clip_cursor);
+                nspan = item_span(nxt, hop);
+                if (lane == 0 && nitem < it_end) {
+                    fence_proxy_async();
+                    issue_raw(nspan);
+                }
+            }
+        }
+        {   // separation of the packed frames, power, bf16 (hi, lo) split, B tile rows
+            const int src = (32 - lane) & 31;
+            const uint32_t row_chunk = (uint32_t)(lane >> 3) * 1024u;
+#pragma unroll
+            for (int j8 = 0; j8 < 2; ++j8) {
+                float f0p[8], f1p[8], f2p[8], f3p[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k1 = 8 * j8 + e;
+                    const V give_r = lane == 0 ? re[(32 - k1) & 31] : re[31 - k1];
+                    const V give_i = lane == 0 ? im[(32 - k1) & 31] : im[31 - k1];
+                    const V pr = shfl(give_r, src), pi = shfl(give_i, src);
+                    const xelem<V> pw = frame_powers<V>(re[k1], im[k1], pr, pi);
+                    f0p[e] = pw.a.x;
+                    f2p[e] = pw.a.y;
+                    f1p[e] = pw.b.x;
+                    f3p[e] = pw.b.y;
+                }
+                const uint32_t atom = tile_addr + row_chunk + (uint32_t)j8 * 4096u;
+                uint4 hi, lo;
+#define HMFE_TC_STORE_ROW(J, P)                                                        \
+    split8(P, hi, lo);                                                                 \
+    sts128(atom + (J) * 128u + (uint32_t)(((lane & 7) ^ (J)) << 4), hi);               \
+    sts128(atom + ((J) + 4) * 128u + (uint32_t)(((lane & 7) ^ ((J) + 4)) << 4), lo);
+                HMFE_TC_STORE_ROW(0, f0p)
+                HMFE_TC_STORE_ROW(1, f1p)
+                HMFE_TC_STORE_ROW(2, f2p)
+                HMFE_TC_STORE_ROW(3, f3p)
+#undef HMFE_TC_STORE_ROW
+            }
+        }
+        // the epilogue must have consumed the previous item's accumulator and meta record
+        if (n_done > 0 && !mbar_wait(bar_free, (n_done - 1) & 1)) {
+            if (lane == 0) atomicOr(b.status, kErrFreeWait);
+            ok = false;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            TcMeta m;
+            m.out = cur.o + (int64_t)cur.f0 * n_mels;
+            m.clip = cur.clip;
+            m.nvalid = min(4, cur.T - cur.f0);
+            m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
+            sm.meta[w] = m;
+            mbar_arrive(bar_ready);
+        }
+        ++n_done;
+        item = nitem;
+        cur = nxt;
+        span = nspan;
+    }
+    // all of this warp's accumulators have been produced before it reports completion
+    if (n_done > 0 && ok) mbar_wait(bar_full, (n_done - 1) & 1);
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(sm.done, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ MMA warp
+template <int NF>
+HMFE_TC_D void mma_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tmem) {
+    constexpr uint64_t desc_hi = smem_desc(0, 0, 1024, kSwizzle128B);
+    constexpr uint32_t idesc = idesc_bf16_f32(128, kDCols);
+    uint32_t parity = 0, started = 0;  // bit w: parity of the number of tiles of FFT warp w issued so far / any issued
+    volatile uint32_t* done = sm.done;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        bool progress = false;
+        const bool all_done = *done == (uint32_t)NF;
+#pragma unroll 1
+        for (int w = 0; w < NF; ++w) {
+            const uint32_t par = (parity >> w) & 1u;
+            if (!mbar_test_wait(smem_u32(sm.ready + w), par)) continue;
+            // the accumulator of this warp's previous item must have been read
+            if (((started >> w) & 1u) && !mbar_test_wait(smem_u32(sm.dfree + w), par ^ 1u)) continue;
+            tc_fence_after();
+            const uint32_t tile = smem_u32(sm.regions + w * kRegionBytes);
+            const uint32_t d = tmem + kTmemD + kDCols * w;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const uint32_t addr = tile + (k >> 2) * 1024 + (k & 3) * 32;
+                mma_ts_f16(d, tmem + 8 * k, desc_hi | (uint64_t)((addr >> 4) & 0x3fffu), idesc, k > 0);
+            }
+            mma_commit(smem_u32(sm.full + w));
+            parity ^= 1u << w;
+            started |= 1u << w;
+            progress = true;
+        }
+        if (!progress) {
+            if (all_done) return;
+            __nanosleep(40);
+        }
+    }
+    atomicOr(b.status, kErrMmaSpin);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue warps
+template <int NF>
+HMFE_TC_D void epilogue_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tmem, int q, int lane, int n_mels) {
+    uint32_t parity = 0;  // bit w: parity of the number of items of FFT warp w consumed so far
+    volatile uint32_t* done = sm.done;
+    const int col = 16 * q + (lane & 15);
+    const int fsel = lane >> 4;  // lanes 0-15 store frames 0 and 1, lanes 16-31 frames 2 and 3
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        bool progress = false;
+        const bool all_done = *done == (uint32_t)NF;
+#pragma unroll 1
+        for (int w = 0; w < NF; ++w) {
+            if (!mbar_test_wait(smem_u32(sm.full + w), (parity >> w) & 1u)) continue;
+            tc_fence_after();
+            const TcMeta m = sm.meta[w];
+            uint32_t v[8];
+            tmem_ld8(tmem + kTmemD + kDCols * w + ((uint32_t)(32 * q) << 16), v);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(sm.dfree + w));
+            parity ^= 1u << w;
+            progress = true;
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[j] = __uint_as_float(v[j]) + __uint_as_float(v[4 + j]);
+                d[j] += __shfl_xor_sync(0xffffffffu, d[j], 16);
+                d[j] = fmaxf(d[j], 0.0f);
+            }
+            const float va = fsel ? d[2] : d[0], vb = fsel ? d[3] : d[1];
+            const int fa = 2 * fsel, fb = fa + 1;
+            const bool oka = col < n_mels && fa < m.nvalid, okb = col < n_mels && fb < m.nvalid;
+            if (oka) m.out[(int64_t)fa * n_mels + col] = va;
+            if (okb) m.out[(int64_t)fb * n_mels + col] = vb;
+            uint32_t hi = 0u, lo = 0x7f800000u;
+            if (oka) {
+                hi = __float_as_uint(va) & 0x7fffffffu;
+                lo = hi;
+            }
+            if (okb) {
+                const uint32_t bb = __float_as_uint(vb) & 0x7fffffffu;
+                hi = max(hi, bb);
+                lo = min(lo, bb);
+            }
+            hi = __reduce_max_sync(0xffffffffu, hi);  // non-negative floats order like their bit patterns
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            if (lane == 0) {
+                atomicMax(b.stats + 2 * m.clip, hi);
+                atomicMin(b.stats + 2 * m.clip + 1, lo);
+            }
+        }
+        if (!progress) {
+            if (all_done) return;
+            __nanosleep(64);
+        }
+    }
+    if (lane == 0) atomicOr(b.status, kErrEpiSpin);
+}
+
+// NF FFT warps.  Registers per thread after re-allocation (65 536 per SM):
+//   NF = 11: epilogue warpgroup 32, the three other warpgroups 160      (128*32 + 384*160 = 65 536)
+//   NF = 8 : epilogue 40, two FFT warpgroups 216, last warpgroup 40     (256*40 + 256*216 = 65 536)
+template <int NF, bool HOP512>
+__global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBatch b, const TcTables tb, int n_mels) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    const TcSmem sm = carve<NF>(base);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < 1024; i += kTcThreads) {
+        sm.tw[i] = tb.tw[i];
+        sm.win[i] = tb.win[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < NF; ++w) {
+            mbar_init(smem_u32(sm.full + w), 1);
+            mbar_init(smem_u32(sm.ready + w), 1);
+            mbar_init(smem_u32(sm.dfree + w), 4);
+            mbar_init(smem_u32(sm.raw + w), 1);
+        }
+        *sm.done = 0;
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(sm.tmem), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem;
+    if (warp < 4) {  // the mel weights: row 32 warp + lane of A, 256 words
+        const uint32_t* row = tb.a_words + (32 * warp + lane) * 256;
+        for (int c = 0; c < 256; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(row + c + j);
+            tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + c, v);
+        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 4) {
+        if constexpr (NF > 8) setmaxnreg_dec<32>(); else setmaxnreg_dec<40>();
+        epilogue_role<NF>(b, sm, tmem, warp, lane, n_mels);
+    } else {
+        if constexpr (NF > 8) {
+            setmaxnreg_inc<160>();
+        } else {
+            if (warp < 12) setmaxnreg_inc<216>(); else setmaxnreg_dec<40>();
+        }
+        if (warp - 4 < NF) {
+            fft_role<NF, HOP512>(b, sm, warp - 4, lane, n_mels);
+        } else if (warp == kMmaWarp) {
+            if (lane == 0) mma_role<NF>(b, sm, tmem);
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_f32(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// A operand: [128 rows][256 words]; row 32q + i = mel 16q + (i % 16), hi part for i < 16, lo part for i >= 16;
+// word c of a row = K positions (2c, 2c + 1), position kappa <-> FFT bin (kappa % 256) / 8 + 32 (8 (kappa / 256) + kappa % 8)
+std::vector<uint32_t> tc_build_a_words(const std::vector<float>& mel_dense, int n_mels, int n_bins) {
+    std::vector<uint32_t> a(128 * 256, 0u);
+    for (int r = 0; r < 128; ++r) {
+        const int q = r / 32, i = r % 32, mel = 16 * q + (i % 16);
+        if (mel >= n_mels) continue;
+        for (int kappa = 0; kappa < 512; ++kappa) {
+            const int lane = (kappa % 256) / 8, k1 = 8 * (kappa / 256) + kappa % 8;
+            const int bin = lane + 32 * k1;
+            const float wv = mel_dense[(size_t)mel * n_bins + bin];
+            const uint16_t hi = f32_to_bf16_rn(wv);
+            const uint16_t part = i < 16 ? hi : f32_to_bf16_rn(wv - bf16_to_f32(hi));
+            a[r * 256 + kappa / 2] |= (uint32_t)part << (16 * (kappa & 1));
+        }
+    }
+    return a;
+}
+
+bool tc_shape_ok(const hmfe_logmel_plan* p) {
+    if (p->n_fft != kNfft || p->n_mels > 64 || p->hop > 512 || p->hop < 1) return false;
+    for (int m = 0; m < p->n_mels; ++m)  // the Nyquist bin is outside K = 512: its weight must be zero
+        if (p->mel_dense[(size_t)m * p->n_bins + 512] != 0.0f) return false;
+    return true;
+}
+
+template <int NF, bool HOP512>
+static int launch_tc_n(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    const size_t smem = tc_smem_bytes<NF>();
+    auto kern = logmel_tc_kernel<NF, HOP512>;
+    HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (b.n_items + NF - 1) / NF;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count));
+    TcTables tb{p->d_win, p->d_tw, p->d_tc_a};
+    kern<<<grid, kTcThreads, smem, st>>>(b, tb, p->n_mels);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
+int launch_logmel_tc(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
+    HMFE_REQUIRE(p->tc_ok && p->d_tc_a && p->pad_mode == HMFE_PAD_CONSTANT,
+                 "the tensor-core log-mel variant needs n_mels <= 64, hop <= 512 and constant padding");
+    const bool h512 = p->hop == 512;
+    if (p->tc_fft_warps <= 8) return h512 ? launch_tc_n<8, true>(p, b, st) : launch_tc_n<8, false>(p, b, st);
+    return h512 ? launch_tc_n<11, true>(p, b, st) : launch_tc_n<11, false>(p, b, st);
+}
+
+}  // namespace hmfe

@@ -33,6 +33,64 @@ def shard_by_length(lengths, world: int):
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
 
 
+def chunk_rounds(n_clips: int, chunk: int, world: int):
+    """Deal chunks of ``chunk`` consecutive clips round-robin over the ranks: in round j rank r owns the clips
+    ``[(j * world + r) * chunk, (j * world + r + 1) * chunk)``.  The blocks a round's all-gather collects are then
+    contiguous AND in global clip order, so every rank can produce its features in place inside the global-order
+    tensor and the collective needs neither a staging buffer nor an order-restoring pass afterwards (contrast
+    ``all_gather_features``, which restores the order of length-balanced ragged shards with an index_select).
+    Returns the number of rounds; ``n_clips`` must be a multiple of ``chunk * world``."""
+    if chunk <= 0 or world <= 0 or n_clips % (chunk * world):
+        raise ValueError(f"n_clips={n_clips} is not a multiple of chunk * world = {chunk} * {world}")
+    return n_clips // (chunk * world)
+
+
+def all_gather_round_inplace(final: torch.Tensor, round_index: int, rows_per_chunk: int, group=None):
+    """In-place all-gather of one round of ``chunk_rounds``: ``final`` is the global-order feature tensor
+    ``[n_clips * rows_per_clip, C]``; this rank has already written its chunk of the round into it.  One
+    ``all_gather_into_tensor`` whose input is this rank's slice of its output (NCCL's in-place form)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo = round_index * world * rows_per_chunk
+    block = final[lo : lo + world * rows_per_chunk]
+    mine = block[rank * rows_per_chunk : (rank + 1) * rows_per_chunk]
+    if final.device.type == "cuda":
+        dist.all_gather_into_tensor(block, mine, group=group)
+    else:  # gloo (CPU tests)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.clone(), group=group)
+        for r, p in enumerate(parts):
+            block[r * rows_per_chunk : (r + 1) * rows_per_chunk].copy_(p)
+    return block
+
+
+def bind_to_gpu_numa_node(device_index: int | None = None) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host buffers are allocated
+    (first touch decides where they live): with one process per GPU on a two-socket box, host<->device copies of
+    ranks whose staging memory sits on the far socket cross the inter-socket link and contend with each other.
+    Returns {"numa_node", "cpus"}; a no-op (node -1) when the topology cannot be read."""
+    import os
+
+    idx = torch.cuda.current_device() if device_index is None else int(device_index)
+    try:
+        bus = torch.cuda.get_device_properties(idx).pci_bus_id
+        dom = torch.cuda.get_device_properties(idx).pci_domain_id
+        dev = torch.cuda.get_device_properties(idx).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa_node": -1, "cpus": 0}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:  # no sysfs / no permission: leave the affinity alone
+        return {"numa_node": -1, "cpus": 0}
+
+
 def local_batch(wav_host: np.ndarray, offsets, shard):
     """Concatenate this rank's clips: returns (float32 array, offsets)."""
     offsets = np.asarray(offsets, dtype=np.int64)

@@ -17,7 +17,7 @@ from ._lib import check
 
 OUT_MODES = {"normalised": 0, "db": 1, "power": 2, "db_abs": 3}
 PAD_MODES = {"constant": 0, "reflect": 1}
-VARIANTS = {"auto": 0, "scalar": 1, "packed": 2, "pair": 3}
+VARIANTS = {"auto": 0, "scalar": 1, "packed": 2, "pair": 3, "tc": 4}
 
 
 def _stream_ptr(stream=None):
@@ -80,6 +80,12 @@ class LogMelPlan:
 
     def set_profile(self, enable: bool):
         check(_lib.hmfe_logmel_set_profile(self._h, int(bool(enable))))
+
+    def tc_status(self) -> int:
+        """Protocol-error word of the tensor-core variant's bounded waits (0 = fine); synchronises."""
+        w = C.c_uint32()
+        check(_lib.hmfe_logmel_tc_status(self._h, C.byref(w)), "hmfe_logmel_tc_status")
+        return int(w.value)
 
     def profile_ms(self):
         """(stft+mel kernel ms, dB/min-max kernel ms, calls) since the last query."""

@@ -51,6 +51,9 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 #define HMFE_VARIANT_SCALAR 1 /* one complex FFT (2 frames) per warp iteration            */
 #define HMFE_VARIANT_PACKED 2 /* two complex FFTs (4 frames), packed FP32 (FFMA2)          */
 #define HMFE_VARIANT_PAIR 3   /* one complex FFT, FFMA2 across element pairs, 20 warps / SM */
+#define HMFE_VARIANT_TC 4     /* FFT as PACKED; mel projection on the tensor cores (tcgen05.mma, accumulators in tensor
+                                 memory, bf16 hi/lo split of weights and powers), frames staged by bulk asynchronous
+                                 copies; warp-specialised (FFT / MMA / epilogue warps).  n_mels <= 64, hop <= 512 */
 
 /* n_fft must be 1024 (the only value the reference uses); n_mels a multiple of 32, <= 256. */
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
@@ -76,6 +79,8 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* plan, const float* d_wav, const in
  * d_wav_alt[-s - 1 : -s - 1 + length] (padded copies kept apart from a read-only signal buffer) */
 int hmfe_logmel_batch_views2(hmfe_logmel_plan* plan, const float* d_wav, const float* d_wav_alt, const int64_t* h_starts,
                              const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream);
+/* HMFE_VARIANT_TC only: protocol-error word of the kernel's bounded mbarrier waits (0 = no error); synchronises. */
+int hmfe_logmel_tc_status(hmfe_logmel_plan* plan, uint32_t* h_status);
 /* number of kernel launches the last hmfe_logmel_batch call on this plan issued */
 int hmfe_logmel_last_launches(const hmfe_logmel_plan* plan);
 /* Measurement hook: when enabled, every hmfe_logmel_batch call records CUDA events on its

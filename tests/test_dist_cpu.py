@@ -91,3 +91,42 @@ def test_shard_by_length_balances_samples():
         assert loads.max() / loads.mean() < 1.001
     c = D.shard_contiguous(1000, 8)
     assert [len(x) for x in c] == [125] * 8 and np.concatenate(c).tolist() == list(range(1000))
+
+
+def _rr_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from heart_murmur_detection_b200 import dist as D
+
+    n_clips, chunk, rows, cols = 24, 3, 5, 4
+    rounds = D.chunk_rounds(n_clips, chunk, world)
+    final = torch.full((n_clips * rows, cols), -1.0)
+    for j in range(rounds):
+        c0 = (j * world + rank) * chunk  # first global clip of this rank's chunk in round j
+        for i in range(chunk):
+            final[(c0 + i) * rows : (c0 + i + 1) * rows] = float(c0 + i) + torch.arange(rows * cols).view(rows, cols) / 100.0
+        D.all_gather_round_inplace(final, j, chunk * rows)
+    q.put((rank, final.numpy()))
+    dist.destroy_process_group()
+
+
+def test_round_robin_chunks_gather_in_place_in_global_order():
+    """c5's sharding: chunks dealt round-robin, features produced in place, one in-place all-gather per round; every
+    rank ends with the single-process tensor, no order-restoring pass."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = np.concatenate([c + np.arange(20, dtype=np.float32).reshape(5, 4) / 100.0 for c in range(24)]).astype(np.float32)
+    for _, out in results:
+        np.testing.assert_array_equal(out, ref)
+    from heart_murmur_detection_b200 import dist as D
+
+    with pytest.raises(ValueError):
+        D.chunk_rounds(25, 3, 2)

@@ -47,7 +47,7 @@ def _check(plan, clips, f_max=8000, hop=512):
         assert np.abs(n - norm).max() <= NORM_TOL
 
 
-@pytest.mark.parametrize("variant", ["scalar", "packed", "pair"])
+@pytest.mark.parametrize("variant", ["scalar", "packed", "pair", "tc"])
 def test_ragged_batch_matches_oracle(variant):
     from heart_murmur_detection_b200.frontend import LogMelPlan
 
@@ -57,7 +57,7 @@ def test_ragged_batch_matches_oracle(variant):
     _check(plan, clips)
 
 
-@pytest.mark.parametrize("variant", ["scalar", "packed", "pair"])
+@pytest.mark.parametrize("variant", ["scalar", "packed", "pair", "tc"])
 def test_uniform_batch_matches_oracle(variant):
     from heart_murmur_detection_b200.frontend import LogMelPlan
 
@@ -66,6 +66,8 @@ def test_uniform_batch_matches_oracle(variant):
     _check(plan, clips)
     # CirCor-shaped: 8 s -> [251, 64]
     assert _run(plan, clips[:1], "normalised")[0].shape == (251, 64)
+    if variant == "tc":
+        assert plan.tc_status() == 0
 
 
 def test_default_fmax_2000_and_other_hop():
@@ -135,3 +137,41 @@ def test_size_independent_properties_at_full_size():
     # scale invariance of the normalised output (dB re max): x -> 4x only shifts the floor
     out4, _ = plan(wav[: off[8]] * 4.0, off[:9])
     assert (out4.view(8, 251, 64) - out[:8]).abs().max() <= 1e-5
+
+
+@pytest.mark.parametrize("fft_warps", [11, 8])
+def test_tensor_core_variant_full_size_and_other_shapes(fft_warps, monkeypatch):
+    """HMFE_VARIANT_TC (mel projection as tcgen05.mma on bf16 hi/lo pairs, frames staged by bulk copies): same
+    tolerances as the FP32 kernels on other hops / f_max / fewer mels, mel power within 3e-5 relative of the packed
+    FP32 kernel on c1 at full size, per-clip results independent of the batch, no protocol error reported."""
+    from heart_murmur_detection_b200 import synth
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    monkeypatch.setenv("HMFE_TC_FFT_WARPS", str(fft_warps))
+    clips = [golden_signal(n, seed=3 + n % 11) for n in (48000, 7777, 128000, 1, 600, 1500)]
+    for kw in (dict(f_max=2000), dict(f_max=8000, hop=256), dict(f_max=8000, hop=320, n_mels=32), dict(f_max=4000, hop=500)):
+        plan = LogMelPlan(variant="tc", **kw)
+        _check(plan, clips, f_max=kw["f_max"], hop=kw.get("hop", 512))
+        assert plan.tc_status() == 0
+    tc, ref = LogMelPlan(f_max=8000, variant="tc"), LogMelPlan(f_max=8000, variant="packed")
+    lens = synth.clip_lengths("c1", 1000)
+    wav, off = synth.make_batch(lens, base_seed=11, device="cuda")
+    p_tc, _ = tc(wav, off, mode="power")
+    p_ref, _ = ref(wav, off, mode="power")
+    rel = ((p_tc - p_ref).abs() / p_ref.clamp_min(1e-30)).max().item()
+    assert rel <= 3e-5, rel
+    out, _ = tc(wav, off)
+    out = out.view(1000, 251, 64)
+    assert torch.all(out.amax(dim=(1, 2)) == 1.0) and torch.all(out.amin(dim=(1, 2)) == 0.0)
+    for i in (0, 499, 999):
+        single, _ = tc(wav[off[i] : off[i + 1]].clone(), np.array([0, lens[i]]))
+        assert torch.equal(single, out[i])
+    # misaligned clip starts (the bulk copies align their source down to 16 bytes)
+    for shift in (1, 2, 3):
+        o = np.array([shift, shift + 128000, shift + 128000 + 70001])
+        a, _ = tc(wav, o, mode="power")
+        b_, _ = ref(wav, o, mode="power")
+        assert ((a - b_).abs() / b_.clamp_min(1e-30)).max().item() <= 3e-5
+    assert tc.tc_status() == 0
+    with pytest.raises(Exception):
+        LogMelPlan(f_max=8000, n_mels=128, variant="tc")
