@@ -223,7 +223,7 @@ def _event_ms(fn, steps, warmup):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    return e0.elapsed_time(e1) / max(steps, 1)
 
 
 def bench_fixed(wl, dev, steps, warmup, variant="auto"):

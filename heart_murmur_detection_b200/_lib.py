@@ -153,6 +153,9 @@ hmfe_resample_last_launches = _sig("hmfe_resample_last_launches", C.c_int, c_voi
 hmfe_spec_mean_batch = _sig(
     "hmfe_spec_mean_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp, c_voidp
 )
+hmfe_spec_mean_ranges = _sig(
+    "hmfe_spec_mean_ranges", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp, c_voidp
+)
 hmfe_spec_crop_batch = _sig(
     "hmfe_spec_crop_batch", C.c_int, c_voidp, c_voidp, C.c_int, c_voidp, C.c_int64, c_voidp, c_voidp, c_voidp, C.c_int,
     c_voidp,

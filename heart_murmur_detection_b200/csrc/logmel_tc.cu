@@ -44,7 +44,7 @@ constexpr int kMmaWarp = 15;
 static_assert(32 * kXStride * 16 <= kRegionBytes, "exchange tile must fit its region");
 
 enum : uint32_t {
-    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrMmaSpin = 16u,
+    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrMmaSpin = 16u, kErrTmemBase = 32u,
 };
 
 struct __align__(16) TcMeta {
@@ -60,13 +60,23 @@ struct TcTables {
     const uint32_t* a_words;  // [128][256]
 };
 
+constexpr int kRing = 16;          // > NF: at most one tile per FFT warp is in flight
+constexpr uint32_t kSentinel = 0xffu;
+
 struct TcSmem {  // pointers into the dynamic shared memory of the CTA
     uint8_t* regions;
     float2* tw;
     float* win;
-    uint64_t *full, *ready, *dfree, *raw;
+    // per FFT warp: full (its MMAs are complete: the B tile may be overwritten), dfree (all four epilogue warps have
+    // read its accumulator and meta record), raw (its frame copy has landed)
+    uint64_t *full, *dfree, *raw;
+    // two in-order rings replace polling of per-warp barriers (an mbarrier test costs ~150 cycles: sweeping 11 of
+    // them took longer than an item): FFT warps append their index to the "ready" ring, the MMA warp issues the
+    // tiles in that order and appends them to the "done" ring, whose barriers the tensor core completes in order
+    uint64_t *ready_seq, *done_seq;
+    uint32_t *ready_who, *done_who;
     TcMeta* meta;
-    uint32_t *tmem, *done;
+    uint32_t *tmem, *done, *tail;
 };
 
 template <int NF>
@@ -79,20 +89,26 @@ HMFE_TC_D TcSmem carve(uint8_t* base) {
     s.win = reinterpret_cast<float*>(p);
     p += 1024 * sizeof(float);
     s.full = reinterpret_cast<uint64_t*>(p);
-    s.ready = s.full + NF;
-    s.dfree = s.ready + NF;
+    s.dfree = s.full + NF;
     s.raw = s.dfree + NF;
-    p += 4 * NF * sizeof(uint64_t);
+    s.ready_seq = s.raw + NF;
+    s.done_seq = s.ready_seq + kRing;
+    p += (3 * NF + 2 * kRing) * sizeof(uint64_t);
+    s.ready_who = reinterpret_cast<uint32_t*>(p);
+    s.done_who = s.ready_who + kRing;
+    p += 2 * kRing * sizeof(uint32_t);
     p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
     s.meta = reinterpret_cast<TcMeta*>(p);
     p += NF * sizeof(TcMeta);
     s.tmem = reinterpret_cast<uint32_t*>(p);
     s.done = s.tmem + 1;
+    s.tail = s.tmem + 2;
     return s;
 }
 template <int NF>
 constexpr size_t tc_smem_bytes() {
-    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + 4 * NF * 8 + 16 + NF * sizeof(TcMeta) + 16;
+    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + (3 * NF + 2 * kRing) * 8 +
+           2 * kRing * 4 + 16 + NF * sizeof(TcMeta) + 16;
 }
 
 // Frame span of an item in its clip, and where it sits in the staging buffer.
@@ -149,8 +165,7 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
     xelem<V>* tile = reinterpret_cast<xelem<V>*>(region);
     const float* stage = reinterpret_cast<const float*>(region + kPowerBytes);
     const uint32_t tile_addr = smem_u32(region), stage_addr = tile_addr + kPowerBytes;
-    const uint32_t bar_full = smem_u32(sm.full + w), bar_ready = smem_u32(sm.ready + w), bar_free = smem_u32(sm.dfree + w),
-                   bar_raw = smem_u32(sm.raw + w);
+    const uint32_t bar_full = smem_u32(sm.full + w), bar_free = smem_u32(sm.dfree + w), bar_raw = smem_u32(sm.raw + w);
     const int hop = HOP512 ? 512 : b.hop;
 
     constexpr int kItemBlock = 8;
@@ -305,7 +320,9 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
             m.nvalid = min(4, cur.T - cur.f0);
             m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
             sm.meta[w] = m;
-            mbar_arrive(bar_ready);
+            const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
+            sm.ready_who[slot] = (uint32_t)w;
+            mbar_arrive(smem_u32(sm.ready_seq + slot));  // release: the tile, the meta record and the ring entry
         }
         ++n_done;
         item = nitem;
@@ -317,102 +334,104 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();
-        atomicAdd(sm.done, 1u);
+        if (atomicAdd(sm.done, 1u) == (uint32_t)NF - 1) {  // the last FFT warp closes the ready ring
+            const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
+            sm.ready_who[slot] = kSentinel;
+            mbar_arrive(smem_u32(sm.ready_seq + slot));
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ MMA warp
+// The whole warp runs this loop with warp-uniform values (loop counters, kernel parameters, shared-memory window
+// base, tensor-memory base 0): the descriptors and tensor-memory addresses then live in uniform registers and every
+// tcgen05.mma is ONE issue slot of the elected lane.  (With a single active lane and operands in vector registers
+// the compiler wraps every instruction in an elect / broadcast loop: 12 instructions per MMA, measured 3x slower
+// than the FP32 kernel because this warp could not keep up with the FFT warps.)
 template <int NF>
-HMFE_TC_D void mma_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tmem) {
+HMFE_TC_D void mma_role(const LogmelBatch& b, const TcSmem& sm, uint32_t regions_addr) {
     constexpr uint64_t desc_hi = smem_desc(0, 0, 1024, kSwizzle128B);
     constexpr uint32_t idesc = idesc_bf16_f32(128, kDCols);
     uint32_t parity = 0, started = 0;  // bit w: parity of the number of tiles of FFT warp w issued so far / any issued
-    volatile uint32_t* done = sm.done;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        bool progress = false;
-        const bool all_done = *done == (uint32_t)NF;
-#pragma unroll 1
-        for (int w = 0; w < NF; ++w) {
-            const uint32_t par = (parity >> w) & 1u;
-            if (!mbar_test_wait(smem_u32(sm.ready + w), par)) continue;
-            // the accumulator of this warp's previous item must have been read
-            if (((started >> w) & 1u) && !mbar_test_wait(smem_u32(sm.dfree + w), par ^ 1u)) continue;
-            tc_fence_after();
-            const uint32_t tile = smem_u32(sm.regions + w * kRegionBytes);
-            const uint32_t d = tmem + kTmemD + kDCols * w;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const uint32_t addr = tile + (k >> 2) * 1024 + (k & 3) * 32;
-                mma_ts_f16(d, tmem + 8 * k, desc_hi | (uint64_t)((addr >> 4) & 0x3fffu), idesc, k > 0);
+    const uint32_t ready_seq = smem_u32(sm.ready_seq), done_seq = smem_u32(sm.done_seq);
+    for (uint32_t seq = 0; seq < (1u << 30); ++seq) {
+        const uint32_t slot = seq % kRing, ring_par = (seq / kRing) & 1u;
+        if (!mbar_wait(ready_seq + 8u * slot, ring_par)) break;
+        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sm.ready_who + slot);
+        if (w == kSentinel) {  // every FFT warp has finished: pass the sentinel on to the epilogue warps
+            if (elect_one()) {
+                *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot) = kSentinel;
+                mbar_arrive(done_seq + 8u * slot);
             }
-            mma_commit(smem_u32(sm.full + w));
-            parity ^= 1u << w;
-            started |= 1u << w;
-            progress = true;
+            __syncwarp();
+            return;
         }
-        if (!progress) {
-            if (all_done) return;
-            __nanosleep(40);
+        // the accumulator of this warp's previous item must have been read
+        if (((started >> w) & 1u) && !mbar_wait(smem_u32(sm.dfree + w), ((parity >> w) & 1u) ^ 1u)) break;
+        tc_fence_after();
+        const uint32_t lo0 = (regions_addr + w * kRegionBytes) >> 4;
+        const uint32_t d = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
+        if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                mma_ts_f16(d, 8 * k, desc_hi | (uint64_t)(lo0 + (k >> 2) * 64 + (k & 3) * 2), idesc, k > 0);
+            *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot) = w;
+            mma_commit(done_seq + 8u * slot);        // -> epilogue warps, in issue order
+            mma_commit(smem_u32(sm.full + w));       // -> the FFT warp: its B tile is free
         }
+        __syncwarp();
+        parity ^= 1u << w;
+        started |= 1u << w;
     }
-    atomicOr(b.status, kErrMmaSpin);
+    if ((threadIdx.x & 31) == 0) atomicOr(b.status, kErrMmaSpin);
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue warps
 template <int NF>
 HMFE_TC_D void epilogue_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tmem, int q, int lane, int n_mels) {
-    uint32_t parity = 0;  // bit w: parity of the number of items of FFT warp w consumed so far
-    volatile uint32_t* done = sm.done;
     const int col = 16 * q + (lane & 15);
     const int fsel = lane >> 4;  // lanes 0-15 store frames 0 and 1, lanes 16-31 frames 2 and 3
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        bool progress = false;
-        const bool all_done = *done == (uint32_t)NF;
-#pragma unroll 1
-        for (int w = 0; w < NF; ++w) {
-            if (!mbar_test_wait(smem_u32(sm.full + w), (parity >> w) & 1u)) continue;
-            tc_fence_after();
-            const TcMeta m = sm.meta[w];
-            uint32_t v[8];
-            tmem_ld8(tmem + kTmemD + kDCols * w + ((uint32_t)(32 * q) << 16), v);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(sm.dfree + w));
-            parity ^= 1u << w;
-            progress = true;
-            float d[4];
+    const uint32_t done_seq = smem_u32(sm.done_seq);
+    for (uint32_t seq = 0; seq < (1u << 30); ++seq) {
+        const uint32_t slot = seq % kRing;
+        if (!mbar_wait(done_seq + 8u * slot, (seq / kRing) & 1u)) break;
+        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot);
+        if (w == kSentinel) return;
+        tc_fence_after();
+        const TcMeta m = sm.meta[w];
+        uint32_t v[8];
+        tmem_ld8(tmem + kTmemD + kDCols * w + ((uint32_t)(32 * q) << 16), v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(sm.dfree + w));
+        float d[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                d[j] = __uint_as_float(v[j]) + __uint_as_float(v[4 + j]);
-                d[j] += __shfl_xor_sync(0xffffffffu, d[j], 16);
-                d[j] = fmaxf(d[j], 0.0f);
-            }
-            const float va = fsel ? d[2] : d[0], vb = fsel ? d[3] : d[1];
-            const int fa = 2 * fsel, fb = fa + 1;
-            const bool oka = col < n_mels && fa < m.nvalid, okb = col < n_mels && fb < m.nvalid;
-            if (oka) m.out[(int64_t)fa * n_mels + col] = va;
-            if (okb) m.out[(int64_t)fb * n_mels + col] = vb;
-            uint32_t hi = 0u, lo = 0x7f800000u;
-            if (oka) {
-                hi = __float_as_uint(va) & 0x7fffffffu;
-                lo = hi;
-            }
-            if (okb) {
-                const uint32_t bb = __float_as_uint(vb) & 0x7fffffffu;
-                hi = max(hi, bb);
-                lo = min(lo, bb);
-            }
-            hi = __reduce_max_sync(0xffffffffu, hi);  // non-negative floats order like their bit patterns
-            lo = __reduce_min_sync(0xffffffffu, lo);
-            if (lane == 0) {
-                atomicMax(b.stats + 2 * m.clip, hi);
-                atomicMin(b.stats + 2 * m.clip + 1, lo);
-            }
+        for (int j = 0; j < 4; ++j) {
+            d[j] = __uint_as_float(v[j]) + __uint_as_float(v[4 + j]);
+            d[j] += __shfl_xor_sync(0xffffffffu, d[j], 16);
+            d[j] = fmaxf(d[j], 0.0f);
         }
-        if (!progress) {
-            if (all_done) return;
-            __nanosleep(64);
+        const float va = fsel ? d[2] : d[0], vb = fsel ? d[3] : d[1];
+        const int fa = 2 * fsel, fb = fa + 1;
+        const bool oka = col < n_mels && fa < m.nvalid, okb = col < n_mels && fb < m.nvalid;
+        if (oka) m.out[(int64_t)fa * n_mels + col] = va;
+        if (okb) m.out[(int64_t)fb * n_mels + col] = vb;
+        uint32_t hi = 0u, lo = 0x7f800000u;
+        if (oka) {
+            hi = __float_as_uint(va) & 0x7fffffffu;
+            lo = hi;
+        }
+        if (okb) {
+            const uint32_t bb = __float_as_uint(vb) & 0x7fffffffu;
+            hi = max(hi, bb);
+            lo = min(lo, bb);
+        }
+        hi = __reduce_max_sync(0xffffffffu, hi);  // non-negative floats order like their bit patterns
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        if (lane == 0) {
+            atomicMax(b.stats + 2 * m.clip, hi);
+            atomicMin(b.stats + 2 * m.clip + 1, lo);
         }
     }
     if (lane == 0) atomicOr(b.status, kErrEpiSpin);
@@ -436,11 +455,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBa
     if (threadIdx.x == 0) {
         for (int w = 0; w < NF; ++w) {
             mbar_init(smem_u32(sm.full + w), 1);
-            mbar_init(smem_u32(sm.ready + w), 1);
             mbar_init(smem_u32(sm.dfree + w), 4);
             mbar_init(smem_u32(sm.raw + w), 1);
         }
+        for (int i = 0; i < kRing; ++i) {
+            mbar_init(smem_u32(sm.ready_seq + i), 1);
+            mbar_init(smem_u32(sm.done_seq + i), 1);
+        }
         *sm.done = 0;
+        *sm.tail = 0;
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(sm.tmem), kTmemCols);
@@ -474,8 +497,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBa
         if (warp - 4 < NF) {
             fft_role<NF, HOP512>(b, sm, warp - 4, lane, n_mels);
         } else if (warp == kMmaWarp) {
-            if (lane == 0) mma_role<NF>(b, sm, tmem);
-            __syncwarp();
+            if (tmem != 0) {  // cannot happen while the CTA owns all 512 columns; the MMA role assumes base 0
+                if (lane == 0) atomicOr(b.status, kErrTmemBase);
+            } else {
+                mma_role<NF>(b, sm, (raw_addr + 1023u) & ~1023u);
+            }
         }
     }
     tc_fence_before();

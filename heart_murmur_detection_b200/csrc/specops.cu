@@ -13,11 +13,13 @@
 namespace hmfe {
 
 // mean over all elements of each ragged spectrogram (float64 accumulation, float32 result)
-__global__ void __launch_bounds__(256) spec_mean_kernel(const float* __restrict__ spec, const int64_t* __restrict__ row_off,
-                                                        int n_cols, float* __restrict__ mean) {
+// rows [row_lo[s], row_hi[s]) of spectrogram s (row_hi = row_lo + 1 for a packed ragged batch)
+__global__ void __launch_bounds__(256) spec_mean_kernel(const float* __restrict__ spec, const int64_t* __restrict__ row_lo,
+                                                        const int64_t* __restrict__ row_hi, int n_cols,
+                                                        float* __restrict__ mean) {
     __shared__ double s_acc[8];
     const int64_t s = blockIdx.x;
-    const int64_t e0 = row_off[s] * n_cols, e1 = row_off[s + 1] * n_cols;
+    const int64_t e0 = row_lo[s] * n_cols, e1 = row_hi[s] * n_cols;
     double acc = 0.0;
     for (int64_t i = e0 + threadIdx.x; i < e1; i += 256) acc += (double)spec[i];
 #pragma unroll
@@ -90,7 +92,35 @@ int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_ro
     int rc = ctx->ring.upload(slot, bytes, st);
     if (rc != HMFE_OK) return rc;
     ctx->prof_begin(HMFE_K_SPEC_MEAN, st);
-    spec_mean_kernel<<<(unsigned)n_specs, 256, 0, st>>>(d_spec, static_cast<int64_t*>(dbuf), n_cols, d_mean);
+    spec_mean_kernel<<<(unsigned)n_specs, 256, 0, st>>>(d_spec, static_cast<int64_t*>(dbuf), static_cast<int64_t*>(dbuf) + 1,
+                                                         n_cols, d_mean);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
+    ctx->last_launches = 1;
+    return ctx->ring.release(slot, st);
+}
+
+int hmfe_spec_mean_ranges(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_row_lo, const int64_t* h_row_hi, int64_t n,
+                          int n_cols, float* d_mean, void* stream) {
+    HMFE_REQUIRE(ctx && h_row_lo && h_row_hi, "NULL argument");
+    HMFE_REQUIRE(n >= 0 && n_cols > 0, "bad arguments");
+    ctx->last_launches = 0;
+    if (n == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_spec && d_mean, "NULL device pointer");
+    for (int64_t i = 0; i < n; ++i)
+        HMFE_REQUIRE(h_row_lo[i] >= 0 && h_row_hi[i] >= h_row_lo[i], "row range %lld is inverted", (long long)i);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)(2 * n) * sizeof(int64_t);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = ctx->ring.acquire(bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    memcpy(hbuf, h_row_lo, (size_t)n * sizeof(int64_t));
+    memcpy(static_cast<int64_t*>(hbuf) + n, h_row_hi, (size_t)n * sizeof(int64_t));
+    int rc = ctx->ring.upload(slot, bytes, st);
+    if (rc != HMFE_OK) return rc;
+    ctx->prof_begin(HMFE_K_SPEC_MEAN, st);
+    spec_mean_kernel<<<(unsigned)n, 256, 0, st>>>(d_spec, static_cast<int64_t*>(dbuf), static_cast<int64_t*>(dbuf) + n, n_cols,
+                                                  d_mean);
     HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->prof_end(st);
     ctx->last_launches = 1;

@@ -130,6 +130,17 @@ HMFE_TC_D void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// true in exactly one (converged) lane of the warp
+HMFE_TC_D bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- registers per warpgroup
 template <int N>
 HMFE_TC_D void setmaxnreg_inc() {

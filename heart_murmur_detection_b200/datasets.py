@@ -119,18 +119,22 @@ def cola_batch(store: SpecStore, indices, max_len=251, augment=True, windowing=F
     dr = cola_draws(T, max_len, augment, windowing)
     Te, w0 = dr["rows_eff"], dr["win_start"]
 
+    windowed = bool(windowing) and bool((T > Te).any())
+
     def descs(start, gain):
         s = np.maximum(start, 0)
         d = np.zeros(idx.size, dtype=fe.CROP_DTYPE)
         d["src_row"] = r0 + w0 + s
         d["n_rows"] = np.minimum(np.minimum(max_len, Te), Te - s)
-        d["spec_id"] = idx
+        d["spec_id"] = np.arange(idx.size) if windowed else idx
         d["gain"] = gain
         d["mask_off"] = dr["mask_off"] + s if augment else 0
         return d
 
     dmask = torch.from_numpy(dr["mask"]).to(store.data.device, non_blocking=True) if augment and dr["mask"].size else None
     means = store.means if augment else None
+    if augment and windowed:  # random_mask runs on the WINDOW: its fill value is the window's mean, per item
+        means = fe.spec_mean_ranges(store.data, r0 + w0, r0 + w0 + Te)
     x1 = fe.spec_crop(store.data, descs(dr["start1"], dr["gain1"]), max_len, dmask, means)
     x2 = fe.spec_crop(store.data, descs(dr["start2"], dr["gain2"]), max_len, dmask, means)
     return x1, x2
@@ -173,8 +177,8 @@ def mae_batch(store: SpecStore, indices, max_len=256):
     return pad_or_crop_batch(store, indices, max_len, starts)
 
 
-def finetune_batch(store: SpecStore, indices, max_len=None, crop_mode="first", augment=True, spec_augment=False,
-                   time_drop_width=64, time_stripes_num=2, freq_drop_width=8, freq_stripes_num=2):
+def finetune_batch(store: SpecStore, indices, max_len=256, crop_mode="first", augment=True, spec_augment=False,
+                   time_drop_width=100, time_stripes_num=2, freq_drop_width=20, freq_stripes_num=2):
     """AudioDataset.__getitem__ of the fine-tuning script (finetuning.py:74-123) over a batch, per item and in the
     reference's order: crop (``random_crop`` draws from Python's ``random``; ``crop_first`` draws nothing) ->
     ``random_mask`` on the CROPPED item (its mean is the crop's mean) -> ``random_multiply`` -> SpecAugmentation
@@ -215,15 +219,7 @@ def finetune_batch(store: SpecStore, indices, max_len=None, crop_mode="first", a
         d["mask_off"] = np.concatenate([[0], np.cumsum(n_eff)[:-1]]) if B else 0
         dmask = torch.from_numpy(np.concatenate(masks) if masks else np.zeros(0, np.uint8)).to(store.data.device)
         # random_mask runs AFTER the crop: the fill value is the mean of the cropped item, not of the recording
-        crop_store_off = np.zeros(B + 1, np.int64)
-        np.cumsum(n_eff, out=crop_store_off[1:])
-        plain = np.zeros(B, dtype=fe.CROP_DTYPE)
-        plain["src_row"], plain["n_rows"], plain["spec_id"], plain["gain"] = r0 + starts, n_eff, 0, 1.0
-        cropped = fe.spec_crop(store.data, plain, rows)
-        if (n_eff == rows).all():
-            means = fe.spec_means(cropped.view(-1, store.n_cols), np.arange(B + 1, dtype=np.int64) * rows)
-        else:
-            means = torch.stack([cropped[k, : int(n_eff[k])].double().mean().float() for k in range(B)])
+        means = fe.spec_mean_ranges(store.data, r0 + starts, r0 + starts + n_eff)
     out = fe.spec_crop(store.data, d, rows, dmask, means)
     if rects:
         ctx = fe.default_ctx()

@@ -700,6 +700,23 @@ def spec_means(spec: torch.Tensor, row_offsets, ctx: Context | None = None, stre
     return mean
 
 
+def spec_mean_ranges(spec: torch.Tensor, row_lo, row_hi, ctx: Context | None = None, stream=None) -> torch.Tensor:
+    """Mean of rows [row_lo[i], row_hi[i]) of ``spec`` for every i (float64 accumulation, float32 result)."""
+    _require_cuda_f32(spec, "spec")
+    lo = np.ascontiguousarray(row_lo, dtype=np.int64)
+    hi = np.ascontiguousarray(row_hi, dtype=np.int64)
+    ctx = ctx or default_ctx()
+    mean = torch.empty(lo.size, dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        check(
+            _lib.hmfe_spec_mean_ranges(ctx._h, C.c_void_p(spec.data_ptr()), lo.ctypes.data_as(C.c_void_p),
+                                       hi.ctypes.data_as(C.c_void_p), lo.size, int(spec.shape[-1]), C.c_void_p(mean.data_ptr()),
+                                       _stream_ptr(stream)),
+            "hmfe_spec_mean_ranges",
+        )
+    return mean
+
+
 def spec_crop(spec: torch.Tensor, descs: np.ndarray, out_rows: int, row_mask: torch.Tensor | None = None,
               means: torch.Tensor | None = None, ctx: Context | None = None, stream=None) -> torch.Tensor:
     """Apply ``hmfe_crop_desc`` records: returns [n_items, out_rows, n_cols]."""

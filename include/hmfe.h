@@ -266,6 +266,10 @@ typedef struct hmfe_crop_desc {
 } hmfe_crop_desc;
 int hmfe_spec_mean_batch(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_row_offsets, int64_t n_specs, int n_cols,
                          float* d_mean, void* stream);
+/* means over arbitrary row ranges [h_row_lo[i], h_row_hi[i]) of d_spec: the fill value of random_mask when it runs on a
+ * window or a crop of a recording (mae_training.py:64-69, finetuning.py:96-102) */
+int hmfe_spec_mean_ranges(hmfe_ctx* ctx, const float* d_spec, const int64_t* h_row_lo, const int64_t* h_row_hi, int64_t n,
+                          int n_cols, float* d_mean, void* stream);
 int hmfe_spec_crop_batch(hmfe_ctx* ctx, const float* d_spec, int n_cols, const hmfe_crop_desc* h_descs, int64_t n_items,
                          const uint8_t* d_row_mask, const float* d_mean, float* d_out, int out_rows, void* stream);
 

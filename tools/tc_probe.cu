@@ -118,6 +118,53 @@ __global__ void __launch_bounds__(160, 1) probe_mma(const ProbeParams p) {
     if (threadIdx.x == 0) p.status[3] = 0xd0e5u;
 }
 
+// ---- 6. tensor-pipe time of small-N instructions: REPS back-to-back tcgen05.mma (M = 128, K = 16, A from tensor memory,
+// B from shared memory) issued by one thread; cycles from the first issue to the commit's arrival
+template <int N>
+__global__ void __launch_bounds__(128, 1) probe_mma_time(long long* out, int reps) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t tile = (smem_u32(smem) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t bar = smem_u32(&s_bar);
+    for (uint32_t i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + (tile - smem_u32(smem)))[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    long long t_issue = 0, t_done = 0;
+    if (warp == 1) {
+        const uint32_t idesc = idesc_bf16_f32(128, N);
+        const long long t0 = clock64();
+        if (elect_one()) {
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    mma_ts_f16(tmem + 256, tmem + 8 * k, smem_desc(tile + (k >> 2) * 2048 + (k & 3) * 32, 0, 1024, kSwizzle128B), idesc, k > 0);
+            }
+            mma_commit(bar);
+        }
+        __syncwarp();
+        t_issue = clock64() - t0;
+        mbar_wait(bar, 0);
+        t_done = clock64() - t0;
+        if ((threadIdx.x & 31) == 0) {
+            out[0] = t_issue;
+            out[1] = t_done;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---- 5. setmaxnreg across warpgroups: 4 warps give registers away, 12 warps take them
 __global__ void __launch_bounds__(512, 1) probe_setmaxnreg(float* out) {
     const int warp = threadIdx.x >> 5;
@@ -294,6 +341,24 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         printf("[setmaxnreg dec 32 / inc 160 over 4 warpgroups] %s\n", e == cudaSuccess ? "PASS" : cudaGetErrorString(e));
         failures += e != cudaSuccess;
+    }
+    {
+        long long* d_t;
+        CK(cudaMalloc(&d_t, 16));
+        const int reps = 32;
+        auto run = [&](auto kern, int n) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960));
+            for (int it = 0; it < 2; ++it) kern<<<1, 128, 40960>>>(d_t, reps);
+            CK(cudaDeviceSynchronize());
+            long long t[2];
+            CK(cudaMemcpy(t, d_t, 16, cudaMemcpyDeviceToHost));
+            printf("[mma time] M=128 N=%3d K=16 TS: %d instructions: issue %lld cycles, complete %lld cycles = %.1f cycles / instruction\n",
+                   n, reps * 32, t[0], t[1], (double)t[1] / (reps * 32));
+            return 0;
+        };
+        if (run(probe_mma_time<16>, 16) || run(probe_mma_time<32>, 32) || run(probe_mma_time<64>, 64) ||
+            run(probe_mma_time<128>, 128) || run(probe_mma_time<256>, 256))
+            return 2;
     }
     printf("tc_probe: %d failure(s)\n", failures);
     return failures ? 1 : 0;
