@@ -44,6 +44,9 @@ WORKLOADS = {
 WORKLOADS["c2nf"] = ("OPERA-CT linear-probe front-end exactly as the reference's callers invoke it (no band-pass, SURVEY F4): "
                      "silence trim + zero/tile pad to >=8 s + cut at 32 s + 64-mel log-spectrogram over 5272 ragged clips "
                      "(model_util.py:161-163)")
+WORKLOADS["c2raw"] = ("c2 from the file payload: 16-bit PCM at the recordings' native 4 kHz in host memory -> PCM16 decode + "
+                      "rate conversion to 16 kHz (the librosa.load(path, sr=16000) of src/util.py:222; torchaudio.transforms."
+                      "Resample algorithm, the pinned oracle) -> the c2 path")
 WORKLOADS["c4"] = ("COLA continued-pretraining input: 100000 synthetic multi-site recordings of 8-60 s -> silence trim + "
                    "whole-recording 64-mel log-spectrogram (heart_pressl.py:58-99) -> AudioDataset items: random_mask, two "
                    "random_crops of 251 frames, two random_multiplies (cola_training.py:56-80), batch 64")
@@ -51,7 +54,7 @@ WORKLOADS["c5"] = ("Throughput sweep: 1000000 CirCor-shaped clips (8 s @16 kHz -
                    "dealt round-robin, one in-place NCCL all-gather of the features per round, every rank ends with the "
                    "[1000000,251,64] tensor in global clip order")
 DEFAULT_CLIPS = {"c1": 1000, "c2": 5272, "c3": 1000, "c2nf": 5272, "c4": 100000, "c5": 1000000}
-CPU_SAMPLE = {"c1": 1000, "c2": 768, "c3": 1000, "c2nf": 1024}
+CPU_SAMPLE = {"c1": 1000, "c2": 768, "c3": 1000, "c2nf": 1024, "c2raw": 768}
 LENS_SEED = 1234          # clip lengths of rank r: synth.clip_lengths(seed=LENS_SEED + r)
 SEED_STRIDE = 10_000_000  # clip i of rank r: synth.make_clip(seed = SEED_STRIDE * r + i)
 C2_KW = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
@@ -59,7 +62,19 @@ C2NF_KW = dict(input_sec=8, butterworth_filter=None, pad=True, types="zero", max
 
 # ----------------------------------------------------------------------------- CPU reference arm
 
+NATIVE_SR = 4000  # c2raw: CirCor's native rate; host payload = 16-bit PCM at this rate
+
+
+def _to_native_pcm(x16k: np.ndarray) -> np.ndarray:
+    """The c2raw host payload of a synthetic 16 kHz clip: every 4th sample, quantised to 16-bit PCM."""
+    return np.clip(np.round(x16k[:: SR // NATIVE_SR] * 32768.0), -32768, 32767).astype(np.int16)
+
+
 def _cpu_process(workload, x, F):
+    if workload == "c2raw":  # x: int16 PCM at 4 kHz -> librosa.load's decode + rate conversion -> the c2 path
+        x16 = F.resample_torchaudio(x.astype(np.float32) / np.float32(32768.0), NATIVE_SR, SR)
+        out = F.entire_signal(x16, spectrogram=True, **C2_KW)
+        return 0 if out is None else out.shape[0]
     if workload == "c1":
         return F.log_mel(x, f_max=8000).shape[0]
     if workload in ("c2", "c2nf"):
@@ -69,7 +84,7 @@ def _cpu_process(workload, x, F):
     return 0 if fb is None else int(F.pad_to_model(fb.numpy()).shape[0])
 
 
-def _cpu_worker(rank, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs):
+def _cpu_worker(rank, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs, pregenerated=False):
     """One host core: generate its share of the sample (untimed), then run the oracle port clip by clip."""
     try:
         from threadpoolctl import threadpool_limits
@@ -85,10 +100,13 @@ def _cpu_worker(rank, cores, workload, lens, seed_base, repeats, barrier, queue,
 
     mine = []
     for i in range(rank, len(lens), cores):
-        x = synth.make_clip(int(lens[i]), seed_base + i).numpy()
-        if shared is not None:  # hand the clip to the parent: the GPU arm times the very same samples
-            np.frombuffer(shared, dtype=np.float32)[offs[i] : offs[i + 1]] = x
-        mine.append(x)
+        if pregenerated:  # clips made by an earlier call (inherited shared memory)
+            x = np.frombuffer(shared, dtype=np.float32)[offs[i] : offs[i + 1]].copy()
+        else:
+            x = synth.make_clip(int(lens[i]), seed_base + i).numpy()
+            if shared is not None:  # hand the clip to the parent: the GPU arm times the very same samples
+                np.frombuffer(shared, dtype=np.float32)[offs[i] : offs[i + 1]] = x
+        mine.append(_to_native_pcm(x) if workload == "c2raw" else x)
     if mine:
         _cpu_process(workload, mine[0], F)  # warm-up: imports, table construction, page-in
     spans = []
@@ -109,7 +127,7 @@ def sample_spec(workload, n_batch, rank=0):
     return lens[:k], SEED_STRIDE * rank
 
 
-def cpu_reference(workload: str, lens, seed_base: int, repeats: int = 1, keep_clips: bool = False):
+def cpu_reference(workload: str, lens, seed_base: int, repeats: int = 1, keep_clips: bool = False, clips=None):
     """Oracle port (numpy restatement of the librosa path + live scipy / torchaudio), one clip at a
     time on every host core - mirrors the reference's one-file-at-a-time loop (model_util.py:138)
     run as `cores` independent processes, clip i on core i mod cores.  Time = first start to last
@@ -123,10 +141,10 @@ def cpu_reference(workload: str, lens, seed_base: int, repeats: int = 1, keep_cl
     ctx = mp.get_context("fork")
     offs = np.zeros(n_clips + 1, dtype=np.int64)
     np.cumsum(lens, out=offs[1:])
-    shared = ctx.RawArray("f", int(offs[-1])) if keep_clips else None
+    shared = clips if clips is not None else (ctx.RawArray("f", int(offs[-1])) if keep_clips else None)
     barrier, queue = ctx.Barrier(cores), ctx.Queue()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs))
-             for r in range(cores)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, cores, workload, lens, seed_base, repeats, barrier, queue, shared, offs,
+                                                    clips is not None)) for r in range(cores)]
     for p in procs:
         p.start()
     results = [queue.get() for _ in procs]
@@ -139,7 +157,8 @@ def cpu_reference(workload: str, lens, seed_base: int, repeats: int = 1, keep_cl
         if best is None or t1 - t0 < best:
             best, frames = t1 - t0, sum(sp[k][2] for _, sp in results)
     return {"clips_per_s": n_clips / best, "frames_per_s": frames / best, "cores": cores, "seconds": best, "repeats": repeats,
-            "clips": np.frombuffer(shared, dtype=np.float32) if keep_clips else None, "offsets": offs,
+            "clips": np.frombuffer(shared, dtype=np.float32) if (keep_clips or clips is not None) else None, "offsets": offs,
+            "shared": shared,
             "sample": f"the first {n_clips} clips of the GPU arm's own batch of workload {workload} (same lengths, same "
                       f"per-clip seeds; {float(np.sum(lens)) / SR:.0f} s of audio, {best * cores:.0f} core-seconds per "
                       f"repeat, best of {repeats}), clip i on core i mod {cores}, one process per core, 1 BLAS thread each"}
@@ -270,6 +289,67 @@ def bench_fixed(wl, dev, steps, warmup, variant="auto"):
             "roofline": {"bound": "hbm", "kernel": dom, "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg[dom],
                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak},
             "l2_policy": f"inputs larger than L2 ({total * 4 / 1e6:.0f} MB of samples per step)"}
+
+
+def bench_c2raw(dev, wav, off, steps, warmup):
+    """c2 from native-rate PCM16: device-resident (int16 batch in HBM -> fused decode + resample -> c2 path) and end
+    to end through pipeline.entire_signal_from_host(sr_in=4000) from pinned host memory."""
+    import torch
+
+    from heart_murmur_detection_b200 import frontend, pipeline
+
+    n = off.size - 1
+    n4 = np.diff(off) // (SR // NATIVE_SR)
+    o4 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(n4, out=o4[1:])
+    d_pcm = torch.empty(int(o4[-1]), dtype=torch.int16, device=dev)
+    step4 = SR // NATIVE_SR
+    for i in range(n):  # every 4th sample of each clip, quantised like a 16-bit WAV (same rule as the CPU arm)
+        seg = wav[int(off[i]) : int(off[i]) + step4 * int(n4[i]) : step4]
+        d_pcm[int(o4[i]) : int(o4[i + 1])] = torch.clamp(torch.round(seg * 32768.0), -32768, 32767).to(torch.int16)
+    rplan = frontend.resample_plan(NATIVE_SR, SR, **frontend.RESAMPLE_PRESETS["torchaudio"])
+    o16 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rplan.out_lengths(n4), out=o16[1:])
+    wav16 = torch.empty(int(o16[-1]), dtype=torch.float32, device=dev)
+    probe = pipeline.entire_signal_batch(rplan(d_pcm, o4, out=wav16)[0], o16, spectrogram=True, **C2_KW)
+    rows = int(probe.row_offsets[-1])
+    work_buf = torch.empty(probe.chunks.work.numel(), dtype=torch.float32, device=dev)
+    out = torch.empty((rows, 64), dtype=torch.float32, device=dev)
+    del probe
+
+    def step():
+        rplan(d_pcm, o4, out=wav16)
+        pipeline.entire_signal_batch(wav16, o16, spectrogram=True, work=work_buf, out=out, **C2_KW)
+
+    ms = _event_ms(step, steps, warmup)
+    ms_rs = _event_ms(lambda: rplan(d_pcm, o4, out=wav16), steps, 1)
+    h_pcm = torch.empty(d_pcm.numel(), dtype=torch.int16, pin_memory=True)
+    h_pcm.copy_(d_pcm)
+    ub = int((1 + np.maximum(np.diff(o16), 8 * SR) // 512).sum())
+    h_out = torch.empty((ub, 64), dtype=torch.float32, pin_memory=True)
+    del wav16, work_buf, out
+
+    def e2e_step():
+        pipeline.entire_signal_from_host(h_pcm, o4, h_out, sr_in=NATIVE_SR, **C2_KW)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / reps
+    hbm_peak, _ = peaks()
+    rs_bytes = 2 * int(o4[-1]) + 4 * int(o16[-1])
+    return {"workload": WORKLOADS["c2raw"], "value": n / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms, "clips_per_step": n,
+            "native_rate_hz": NATIVE_SR, "resample_kernel_ms": ms_rs,
+            "resample_roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": rs_bytes, "achieved": rs_bytes / (ms_rs * 1e-3) / 1e9,
+                                  "peak": hbm_peak, "unit": "GB/s", "frac": rs_bytes / (ms_rs * 1e-3) / 1e9 / hbm_peak},
+            "e2e": {"value": n / e2e_s, "unit": "clips/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 2 * int(o4[-1]),
+                    "d2h_bytes_per_step": rows * 64 * 4, "steps": reps,
+                    "api": "pipeline.entire_signal_from_host(sr_in=4000)"}}
 
 
 def bench_c4(dev, rank, n_total=100000, pool=2048, max_len=251, batch=64):
@@ -556,7 +636,7 @@ def main():
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process (fork safety)
     if wl in ("c4", "c5"):
         return run_sub_as_main(args, rank, world, local_rank)
-    cpu, host_clips = None, None
+    cpu, host_clips, cpu_raw = None, None, None
     n_clips = args.clips or DEFAULT_CLIPS[wl]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         k_lens, k_seed = sample_spec(wl, n_clips)
@@ -564,6 +644,11 @@ def main():
         host_clips = (r["clips"], r["offsets"])
         cpu = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "frames_per_s": r["frames_per_s"]}
+        if wl == "c2" and not args.no_sub:  # the same clips as 4 kHz PCM16 through decode + resample + c2 on the CPU
+            r2 = cpu_reference("c2raw", k_lens, k_seed, repeats=2, clips=r["shared"])
+            cpu_raw = {"value": r2["clips_per_s"], "unit": "clips/s", "cores": r2["cores"], "kind": "port",
+                       "sample": r2["sample"] + "; every 4th sample as 16-bit PCM, torchaudio.functional.resample 4 kHz -> 16 kHz "
+                                 "(the oracle of the GPU resampler) inside the timed region"}
 
     import torch
     import torch.distributed as dist
@@ -787,6 +872,12 @@ def main():
     chunk_samples = int(state["res"].chunks.lengths.sum()) if wl in ("c2", "c2nf") else total_samples
     launches_per_step = int(state["launches"])
     subs = {}
+    if not args.no_sub and wl == "c2" and world == 1:
+        state.clear()
+        pipeline._host_pipes.clear()
+        torch.cuda.empty_cache()
+        subs["c2raw"] = bench_c2raw(dev, wav, off, args.steps, args.warmup)
+        subs["c2raw"]["cpu_baseline"] = cpu_raw
     if not args.no_sub and wl == "c2":
         state.clear()
         h_wav = h_out = h_pcm = h_out16 = None  # noqa: F841

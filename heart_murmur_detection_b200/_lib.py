@@ -148,6 +148,7 @@ hmfe_resample_plan_destroy = _sig("hmfe_resample_plan_destroy", None, c_voidp)
 hmfe_resample_out_len = _sig("hmfe_resample_out_len", C.c_int64, c_voidp, C.c_int64)
 hmfe_resample_taps = _sig("hmfe_resample_taps", C.c_int, c_voidp, C.POINTER(C.c_int), C.POINTER(C.c_int), c_voidp)
 hmfe_resample_batch = _sig("hmfe_resample_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp)
+hmfe_resample_batch_pcm16 = _sig("hmfe_resample_batch_pcm16", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, c_voidp)
 hmfe_resample_last_launches = _sig("hmfe_resample_last_launches", C.c_int, c_voidp)
 
 hmfe_spec_mean_batch = _sig(

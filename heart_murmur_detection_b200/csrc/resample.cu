@@ -19,23 +19,36 @@
 
 namespace hmfe {
 
+#define HMFE_RS_D __device__ __forceinline__
+
 struct ResampleBatch {
-    const float* x;
+    const void* x;           // float32 samples, or int16 PCM (decoded as x / 32768 on the fly)
     float* y;
     const int64_t* in_off;   // [n_clips+1]
     const int64_t* out_off;  // [n_clips+1]
     const float* kern;       // [U][W]
     int64_t n_clips, n_out_total;
     int U, D, W, width;
+    int taps_in_smem;        // 0: the tap table is too large for shared memory (e.g. 44.1 kHz -> 16 kHz: 160 x 475), read it through L1
 };
 
-constexpr int kRsTile = 1024;  // outputs per CTA
+constexpr int kRsTile = 2048;  // outputs per CTA
 
+HMFE_RS_D float rs_sample(const float* x, int64_t i) { return __ldg(x + i); }
+HMFE_RS_D float rs_sample(const int16_t* x, int64_t i) { return (float)__ldg(x + i) * (1.0f / 32768.0f); }  // exact
+
+// One CTA = one tile of kRsTile consecutive outputs of one clip.  The taps [U][W] and the input span of the tile
+// ((kRsTile / U) * D + W samples, zero padded at the clip edges) are staged in shared memory once; consecutive
+// threads compute consecutive outputs (for the integer up-factors of CirCor / PhysioNet audio, D = 1: the U
+// threads of one input position read the same samples - a broadcast - and U different tap rows).
+template <typename T>
 __global__ void __launch_bounds__(256) resample_kernel(const ResampleBatch b, const int64_t* tile_prefix) {
-    // tile -> clip (binary search over per-clip tile prefix)
+    extern __shared__ float rs_smem[];
+    const float* s_k = b.taps_in_smem ? rs_smem : b.kern;           // [U * W]
+    float* s_x = rs_smem + (b.taps_in_smem ? b.U * b.W : 0);        // [span]
     const int64_t tile = blockIdx.x;
     int64_t lo = 0, hi = b.n_clips;
-    while (hi - lo > 1) {
+    while (hi - lo > 1) {  // tile -> clip (binary search over the per-clip tile prefix)
         const int64_t mid = (lo + hi) >> 1;
         if (tile_prefix[mid] <= tile)
             lo = mid;
@@ -47,15 +60,29 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleBatch b, co
     const int n_in = (int)(b.in_off[clip + 1] - i0);
     const int64_t o0 = b.out_off[clip];
     const int n_out = (int)(b.out_off[clip + 1] - o0);
-    const float* x = b.x + i0;
+    const T* x = static_cast<const T*>(b.x) + i0;
     const int j0 = (int)(tile - tile_prefix[clip]) * kRsTile;
-    for (int j = j0 + threadIdx.x; j < min(n_out, j0 + kRsTile); j += 256) {
+    const int j1 = min(n_out, j0 + kRsTile);
+    const int q0 = j0 / b.U;
+    const int span = ((j1 - 1) / b.U - q0) * b.D + b.W;  // input positions q0 * D - width ... of this tile
+    const int base0 = q0 * b.D - b.width;
+    if (b.taps_in_smem)
+        for (int i = threadIdx.x; i < b.U * b.W; i += 256) rs_smem[i] = __ldg(b.kern + i);
+    for (int i = threadIdx.x; i < span; i += 256) {
+        const int g = base0 + i;
+        s_x[i] = (g >= 0 && g < n_in) ? rs_sample(x, g) : 0.0f;
+    }
+    __syncthreads();
+    for (int j = j0 + threadIdx.x; j < j1; j += 256) {
         const int p = j % b.U, q = j / b.U;
-        const float* k = b.kern + (size_t)p * b.W;
-        const int base = q * b.D - b.width;
+        const float* k = s_k + p * b.W;
+        const float* xs = s_x + (q - q0) * b.D;
+        // same order of accumulation as the per-output loop it replaces (t ascending; zero-padded samples add
+        // exact zeros), so results are unchanged bit for bit
         float acc = 0.0f;
+        const int base = q * b.D - b.width;
         const int k_lo = max(0, -base), k_hi = min(b.W, n_in - base);
-        for (int t = k_lo; t < k_hi; ++t) acc = fmaf(__ldg(k + t), __ldg(x + base + t), acc);
+        for (int t = k_lo; t < k_hi; ++t) acc = fmaf(k[t], xs[t], acc);
         b.y[o0 + j] = acc;
     }
 }
@@ -163,8 +190,8 @@ int hmfe_resample_taps(const hmfe_resample_plan* p, int* n_phases, int* n_taps, 
     return HMFE_OK;
 }
 
-int hmfe_resample_batch(hmfe_resample_plan* p, const float* d_in, const int64_t* h_in_offsets, int64_t n_clips,
-                        float* d_out, void* stream) {
+static int resample_launch(hmfe_resample_plan* p, const void* d_in, bool pcm16, const int64_t* h_in_offsets, int64_t n_clips,
+                           float* d_out, void* stream) {
     HMFE_REQUIRE(p && h_in_offsets, "NULL argument");
     HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
     p->last_launches = 0;
@@ -205,11 +232,33 @@ int hmfe_resample_batch(hmfe_resample_plan* p, const float* d_in, const int64_t*
     const int64_t tiles = ht[n_clips];
     if (tiles > 0) {
         HMFE_REQUIRE(tiles < (int64_t)INT32_MAX, "resample grid too large");
-        resample_kernel<<<(unsigned)tiles, 256, 0, st>>>(b, b.in_off + 2 * (n_clips + 1));
+        b.taps_in_smem = (size_t)p->U * p->W * sizeof(float) <= 64 * 1024;
+        const size_t smem = ((b.taps_in_smem ? (size_t)p->U * p->W : 0) + (size_t)((kRsTile + p->U - 1) / p->U + 1) * p->D + p->W) *
+                            sizeof(float);
+        HMFE_REQUIRE(smem <= 200 * 1024, "resampling ratio %d/%d with %d taps needs %zu bytes of shared memory", p->U, p->D, p->W,
+                     smem);
+        const int64_t* prefix = b.in_off + 2 * (n_clips + 1);
+        if (pcm16) {
+            HMFE_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            resample_kernel<int16_t><<<(unsigned)tiles, 256, smem, st>>>(b, prefix);
+        } else {
+            HMFE_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            resample_kernel<float><<<(unsigned)tiles, 256, smem, st>>>(b, prefix);
+        }
         HMFE_CHECK_CUDA(cudaGetLastError());
         p->last_launches = 1;
     }
     return p->ring.release(slot, st);
+}
+
+int hmfe_resample_batch(hmfe_resample_plan* p, const float* d_in, const int64_t* h_in_offsets, int64_t n_clips,
+                        float* d_out, void* stream) {
+    return resample_launch(p, d_in, false, h_in_offsets, n_clips, d_out, stream);
+}
+
+int hmfe_resample_batch_pcm16(hmfe_resample_plan* p, const int16_t* d_pcm, const int64_t* h_in_offsets, int64_t n_clips,
+                              float* d_out, void* stream) {
+    return resample_launch(p, d_pcm, true, h_in_offsets, n_clips, d_out, stream);
 }
 
 }  // extern "C"

@@ -624,20 +624,44 @@ class ResamplePlan:
     def last_launches(self) -> int:
         return int(_lib.hmfe_resample_last_launches(self._h))
 
-    def __call__(self, wav: torch.Tensor, offsets, stream=None):
-        """Returns (resampled wav, new offsets)."""
-        _require_cuda_f32(wav, "wav")
+    def __call__(self, wav: torch.Tensor, offsets, stream=None, out: torch.Tensor | None = None):
+        """Returns (resampled wav, new offsets).  ``wav``: float32 samples or int16 PCM (decoded as x / 32768 in the
+        same pass) on the device; ``out``: optional float32 buffer of at least the resampled size."""
+        pcm = isinstance(wav, torch.Tensor) and wav.is_cuda and wav.dtype == torch.int16 and wav.is_contiguous()
+        if not pcm:
+            _require_cuda_f32(wav, "wav")
         o = _as_offsets(offsets)
         no = np.zeros(o.size, dtype=np.int64)
         np.cumsum(self.out_lengths(np.diff(o)), out=no[1:])
-        out = torch.empty(int(no[-1]), dtype=torch.float32, device=wav.device)
+        if out is None:
+            out = torch.empty(int(no[-1]), dtype=torch.float32, device=wav.device)
+        else:
+            _require_cuda_f32(out, "out")
+            if out.numel() < int(no[-1]):
+                raise ValueError("out is too small")
+        fn = _lib.hmfe_resample_batch_pcm16 if pcm else _lib.hmfe_resample_batch
         with torch.cuda.device(wav.device):
             check(
-                _lib.hmfe_resample_batch(self._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1,
-                                         C.c_void_p(out.data_ptr()), _stream_ptr(stream)),
+                fn(self._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), o.size - 1, C.c_void_p(out.data_ptr()),
+                   _stream_ptr(stream)),
                 "hmfe_resample_batch",
             )
         return out, no
+
+
+# Named filter designs for ``resample_plan(..., **RESAMPLE_PRESETS[name])``.
+#   "torchaudio"   torchaudio.transforms.Resample defaults (Hann-windowed sinc, 6 zero crossings, roll-off 0.99): the
+#                  resampler the reference uses at src/model/models_eval.py:964-968 and the PINNED oracle of this kernel.
+#   "soxr_hq_like" a Kaiser-windowed sinc with the published figures of libsoxr's HQ recipe, which is what
+#                  ``librosa.load(path, sr=16000)`` runs (librosa 0.10.1 res_type="soxr_hq", environment.yml:117,188):
+#                  pass band flat to 0.913 of the input Nyquist, stop band from 1.0, about 125 dB rejection (20 bit).
+#                  Kaiser design formulas: beta = 0.1102 (A - 8.7) = 12.8, transition 0.087 Nyquist -> about 94 zero
+#                  crossings each side, cut-off in the middle of the transition band (roll-off 0.9565).  libsoxr itself
+#                  is not installable here: parity with it is UNPINNED; tests quantify the response of this design.
+RESAMPLE_PRESETS = {
+    "torchaudio": dict(lowpass_filter_width=6, rolloff=0.99, method="sinc_interp_hann"),
+    "soxr_hq_like": dict(lowpass_filter_width=94, rolloff=0.9565, method="sinc_interp_kaiser", beta=12.8),
+}
 
 
 def fbank_plan(**kw) -> FbankPlan:

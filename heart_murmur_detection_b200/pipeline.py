@@ -365,19 +365,33 @@ def individual_segments_batch(wav, offsets, input_sec=8, sample_rate=16000, hop_
 _host_pipes: dict = {}
 
 
-def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, *, chunk_bytes=512 << 20,
-                            device=None, **kw):
+def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | None = None, *, sr_in: int | None = None,
+                            resample: str = "torchaudio", chunk_bytes=512 << 20, device=None, **kw):
     """get_entire_signal_librosa(spectrogram=True) over a batch held in (pinned) HOST memory.
 
-    Sub-batches of about ``chunk_bytes`` flow through three streams - copy-in, compute,
-    copy-out - so the PCIe transfers of neighbouring sub-batches overlap the kernels.  All
-    device buffers (two sample buffers, two work buffers, two feature buffers) are allocated
-    once per device and reused across sub-batches and calls.
+    ``h_wav`` holds the decoded files back to back: float32 samples or the int16 PCM payload, at ``sr_in`` Hz
+    (default: already at ``sample_rate``).  With a native rate (CirCor: 4 kHz, PhysioNet 2016: 2 kHz) the batch
+    crosses PCIe as it is on disk and ``librosa.load(path, sr=16000)``'s rate conversion (src/util.py:222) runs on the
+    GPU (``frontend.RESAMPLE_PRESETS[resample]``), fused with the PCM16 decode.
+
+    Sub-batches of about ``chunk_bytes`` of 16 kHz float32 samples flow through three streams - copy-in (+ decode /
+    resample), compute, copy-out - so the PCIe transfers of neighbouring sub-batches overlap the kernels.  All device
+    buffers (two input buffers, two sample buffers, two work buffers, two feature buffers) are allocated once per
+    device and reused across sub-batches and calls.
     Returns (h_out [sum T, 64] host tensor, row_offsets [n_chunks+1], clip_ids, valid).
     """
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    o = fe._as_offsets(offsets)
-    n = o.size - 1
+    o_in = fe._as_offsets(offsets)
+    n = o_in.size - 1
+    sr = kw.get("sample_rate", 16000)
+    native = sr_in is not None and int(sr_in) != int(sr)
+    if native:
+        with torch.cuda.device(dev):
+            rplan = fe.resample_plan(int(sr_in), int(sr), **fe.RESAMPLE_PRESETS[resample])
+        o = np.zeros(o_in.size, dtype=np.int64)
+        np.cumsum(rplan.out_lengths(np.diff(o_in)), out=o[1:])
+    else:
+        o = o_in
     bounds = [0]
     while bounds[-1] < n:
         c0 = bounds[-1]
@@ -385,12 +399,13 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
         bounds.append(min(n, max(c0 + 1, c1)))
     subs = list(zip(bounds[:-1], bounds[1:]))
     hop = 512
-    input_sec, sr = kw.get("input_sec", 8), kw.get("sample_rate", 16000)
+    input_sec = kw.get("input_sec", 8)
     L = int(input_sec * sr)
     pad = bool(kw.get("pad", False))
     lens = np.diff(o)
     rows_ub = 1 + np.maximum(lens, L if pad else 0) // hop
     max_samples = max(int(o[b] - o[a]) for a, b in subs)
+    max_native = max(int(o_in[b] - o_in[a]) for a, b in subs)
     max_work = max(int(o[b] - o[a]) + (L * (b - a + 16) if pad else 0) for a, b in subs)
     max_rows = max(int(rows_ub[a:b].sum()) for a, b in subs)
     if h_out is None:
@@ -399,12 +414,15 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
     pcm = h_wav.dtype == torch.int16  # 16-bit WAV payload: half the PCIe bytes, decoded on the device
     if not pcm and h_wav.dtype != torch.float32:
         raise TypeError("h_wav must be float32 samples or int16 PCM")
-    pipe = _host_pipes.get((dev, pcm))
-    if pipe is None or pipe["cap"][0] < max_samples or pipe["cap"][1] < max_work or pipe["cap"][2] < max_rows:
-        cap = (max_samples, max_work, max_rows) if pipe is None else tuple(max(x, y) for x, y in zip(pipe["cap"], (max_samples, max_work, max_rows)))
-        pipe = _host_pipes[(dev, pcm)] = {
+    staged = pcm or native  # the host payload lands in a staging buffer first
+    key = (dev, h_wav.dtype, staged)
+    pipe = _host_pipes.get(key)
+    need = (max_samples, max_work, max_rows, max_native if staged else 0)
+    if pipe is None or any(c < x for c, x in zip(pipe["cap"], need)):
+        cap = need if pipe is None else tuple(max(x, y) for x, y in zip(pipe["cap"], need))
+        pipe = _host_pipes[key] = {
             "cap": cap,
-            "d_pcm": [torch.empty(cap[0] if pcm else 0, dtype=torch.int16, device=dev) for _ in range(2)],
+            "d_raw": [torch.empty(cap[3], dtype=h_wav.dtype, device=dev) for _ in range(2)],
             # sample buffers carry the padding spare too: without a band-pass they double as the work buffer
             "d_in": [torch.empty(cap[1], dtype=torch.float32, device=dev) for _ in range(2)],
             "work": [torch.empty(cap[1], dtype=torch.float32, device=dev) for _ in range(2)],
@@ -412,7 +430,7 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
             "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],
         }
     s_in, s_cmp, s_out = pipe["streams"]
-    d_in, work, feat, d_pcm = pipe["d_in"], pipe["work"], pipe["feat"], pipe["d_pcm"]
+    d_in, work, feat, d_raw = pipe["d_in"], pipe["work"], pipe["feat"], pipe["d_raw"]
     cur = torch.cuda.current_stream(dev)
     for s in pipe["streams"]:
         s.wait_stream(cur)
@@ -425,12 +443,16 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
         with torch.cuda.stream(s_in):
             if i >= 2:
                 s_in.wait_event(ev_free[i % 2])
-            ns = int(o[b] - o[a])
-            if pcm:
-                d_pcm[i % 2][:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
-                fe.pcm16_to_f32(d_pcm[i % 2][:ns], out=d_in[i % 2], stream=s_in)
+            n_in = int(o_in[b] - o_in[a])
+            src = h_wav[int(o_in[a]) : int(o_in[b])]
+            if native:  # (PCM16 decode +) rate conversion in one pass, straight into the sample buffer
+                d_raw[i % 2][:n_in].copy_(src, non_blocking=True)
+                rplan(d_raw[i % 2][:n_in], o_in[a : b + 1] - o_in[a], stream=s_in, out=d_in[i % 2])
+            elif pcm:
+                d_raw[i % 2][:n_in].copy_(src, non_blocking=True)
+                fe.pcm16_to_f32(d_raw[i % 2][:n_in], out=d_in[i % 2], stream=s_in)
             else:
-                d_in[i % 2][:ns].copy_(h_wav[int(o[a]) : int(o[b])], non_blocking=True)
+                d_in[i % 2][:n_in].copy_(src, non_blocking=True)
             ev_in[i % 2].record(s_in)
 
     row_offsets, clip_ids, valid = [np.zeros(1, np.int64)], [], np.zeros(n, dtype=bool)

@@ -244,6 +244,10 @@ int64_t hmfe_resample_out_len(const hmfe_resample_plan* plan, int64_t n_in);
 int hmfe_resample_taps(const hmfe_resample_plan* plan, int* n_phases, int* n_taps, float* h_out);
 int hmfe_resample_batch(hmfe_resample_plan* plan, const float* d_in, const int64_t* h_in_offsets, int64_t n_clips,
                         float* d_out, void* stream);
+/* same with the 16-bit PCM payload of the WAV file as input (sample = pcm / 32768, exact): decode and rate conversion
+ * in one pass, for loaders that ship native-rate PCM16 over PCIe (CirCor: 4 kHz, 1/8 of the bytes of 16 kHz float32) */
+int hmfe_resample_batch_pcm16(hmfe_resample_plan* plan, const int16_t* d_pcm, const int64_t* h_in_offsets, int64_t n_clips,
+                              float* d_out, void* stream);
 int hmfe_resample_last_launches(const hmfe_resample_plan* plan);
 
 /* ------------------------------------------------------------------------------------------

@@ -355,6 +355,37 @@ def test_cache_writers_resample_native_rate_files(tmp_path):
             assert got.shape == ref.shape and np.array_equal(got, ref), w
 
 
+def test_host_entry_from_native_rate_pcm16_matches_device_path_and_oracle():
+    """pipeline.entire_signal_from_host(sr_in=4000) - the 16-bit payload at the recordings' native rate crosses PCIe,
+    decode + rate conversion run on the GPU (librosa.load(path, sr=16000) of src/util.py:222) - equals the device
+    path (resample, then entire_signal_batch) bit for bit over several sub-batches, and the CPU oracle
+    (torchaudio.functional.resample + the restated reference path) within the log-mel tolerance."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200 import pipeline as pl
+    from oracle import frontend as F
+
+    kw = dict(input_sec=8, butterworth_filter=5, pad=True, types="zero", max_sec=32)
+    secs = [9.0, 3.1, 12.5, 40.0, 8.0, 1.0, 20.3, 5.0, 33.0]
+    pcm = [np.clip(np.round(golden_signal(int(s_ * 16000), 70 + i, SR, 0.1, 0.2)[::4] * 32768.0), -32768, 32767).astype(np.int16)
+           for i, s_ in enumerate(secs)]
+    o4 = np.zeros(len(pcm) + 1, dtype=np.int64)
+    np.cumsum([len(c) for c in pcm], out=o4[1:])
+    h_pcm = torch.from_numpy(np.concatenate(pcm)).pin_memory()
+    h_out, ro, clip_ids, valid = pl.entire_signal_from_host(h_pcm, o4, sr_in=4000, chunk_bytes=4 << 20, **kw)
+    assert valid.all() and list(clip_ids) == list(range(len(pcm)))
+    rplan = fe.resample_plan(4000, 16000, **fe.RESAMPLE_PRESETS["torchaudio"])
+    wav16, o16 = rplan(h_pcm.cuda(), o4)
+    ref = pl.entire_signal_batch(wav16, o16, spectrogram=True, **kw)
+    rows = int(ref.row_offsets[-1])
+    assert np.array_equal(ro, ref.row_offsets)
+    assert torch.equal(h_out[:rows], ref.features[:rows].cpu())
+    for i in (1, 3, 5):
+        x16 = F.resample_torchaudio(pcm[i].astype(np.float32) / np.float32(32768.0), 4000, 16000)
+        want = F.entire_signal(x16, spectrogram=True, **kw)
+        got = h_out[int(ro[i]) : int(ro[i + 1])].numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 3e-4
+
+
 def test_c2_full_size_properties():
     """BASELINE config 2 at full size (5 272 ragged clips, 1.78 G samples) through size-independent
     properties: the one-pass overlap band-pass equals the exact chunked scan on every sample; trim

@@ -375,6 +375,34 @@ def test_resample_matches_torchaudio(sr_in):
         assert np.abs(got - ref_f).max() <= 2e-5
 
 
+@pytest.mark.parametrize("preset", ["torchaudio", "soxr_hq_like"])
+def test_resample_presets_and_pcm16_input(preset):
+    """The named filter designs against torchaudio's own kernel builder with the same parameters, and the fused
+    PCM16 path (int16 in, / 32768 and rate conversion in one pass) bit-identical to decode-then-resample."""
+    import torchaudio
+
+    from heart_murmur_detection_b200 import frontend as fe
+
+    kw = fe.RESAMPLE_PRESETS[preset]
+    for sr_in in (4000, 2000, 8000):
+        plan = fe.ResamplePlan(sr_in, 16000, **kw)
+        lens = [1, 17, 1000, 12345, 3 * sr_in + 7]
+        clips = [golden_signal(n, seed=15 + i, sr=sr_in, lead=0, tail=0) for i, n in enumerate(lens)]
+        pcm = [np.clip(np.round(c * 32768.0), -32768, 32767).astype(np.int16) for c in clips]
+        deq = [(q.astype(np.float32) / np.float32(32768.0)) for q in pcm]
+        wav, off = _batch(deq)
+        out, no = plan(wav, off)
+        out16, no16 = plan(torch.from_numpy(np.concatenate(pcm)).cuda(), off)
+        assert np.array_equal(no, no16) and torch.equal(out, out16)
+        out = out.cpu().numpy()
+        for i, x in enumerate(deq):
+            ref = torchaudio.functional.resample(torch.from_numpy(x).double(), sr_in, 16000, lowpass_filter_width=kw["lowpass_filter_width"],
+                                                 rolloff=kw["rolloff"], resampling_method=kw["method"], beta=kw.get("beta")).numpy()
+            got = out[no[i] : no[i + 1]]
+            assert len(got) == len(ref) == int(np.ceil(len(x) * 16000 / sr_in))
+            assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(x).max()), (preset, sr_in, i)
+
+
 # ------------------------------------------------------------------------------------------- spectrogram ops
 
 
