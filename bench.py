@@ -313,13 +313,14 @@ def bench_c2raw(dev, wav, off, steps, warmup):
     wav16 = torch.empty(int(o16[-1]), dtype=torch.float32, device=dev)
     probe = pipeline.entire_signal_batch(rplan(d_pcm, o4, out=wav16)[0], o16, spectrogram=True, **C2_KW)
     rows = int(probe.row_offsets[-1])
-    work_buf = torch.empty(probe.chunks.work.numel(), dtype=torch.float32, device=dev)
-    out = torch.empty((rows, 64), dtype=torch.float32, device=dev)
     del probe
+    ub_rows = int((1 + np.maximum(np.diff(o16), 8 * SR) // 512).sum())
+    work_buf = torch.empty(int(o16[-1]) + 8 * SR * n, dtype=torch.float32, device=dev)
+    out = torch.empty((ub_rows, 64), dtype=torch.float32, device=dev)
 
     def step():
         rplan(d_pcm, o4, out=wav16)
-        pipeline.entire_signal_batch(wav16, o16, spectrogram=True, work=work_buf, out=out, **C2_KW)
+        pipeline.entire_signal_device(wav16, o16, work=work_buf, out=out, **C2_KW)
 
     ms = _event_ms(step, steps, warmup)
     ms_rs = _event_ms(lambda: rplan(d_pcm, o4, out=wav16), steps, 1)
@@ -686,12 +687,16 @@ def main():
     elif wl in ("c2", "c2nf"):
         probe = pipeline.entire_signal_batch(wav, off, spectrogram=True, **kw2)
         out_rows = int(probe.row_offsets[-1])
-        work_buf = torch.empty(probe.chunks.work.numel(), dtype=torch.float32, device=dev)
+        chunk_samples_probe = int(probe.chunks.lengths.sum())
         del probe
+        # the step is enqueued without any host round trip (device-side planner); buffers hold the upper bounds
+        L8 = 8 * SR
+        work_buf = torch.empty(total_samples + L8 * n_clips, dtype=torch.float32, device=dev)
+        ub_rows = int((1 + np.maximum(np.diff(off), L8) // 512).sum())
 
         def step(out):
-            res = pipeline.entire_signal_batch(wav, off, spectrogram=True, work=work_buf, out=out, **kw2)
-            state.update(features=res.features, rows=int(res.row_offsets[-1]), launches=res.launches, res=res)
+            res = pipeline.entire_signal_device(wav, off, work=work_buf, out=out, **kw2)
+            state.update(features=res.features, rows=out_rows, launches=res.launches, res=res)
     else:
         out_rows = n_clips * 1024
 
@@ -704,7 +709,7 @@ def main():
 
     n_cols = 128 if wl == "c3" else 64
     rows = out_rows
-    max_rows = rows
+    max_rows = ub_rows if wl in ("c2", "c2nf") else rows  # send / gather buffers hold the upper bound of rows
     if world > 1:
         t = torch.tensor([rows], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -807,7 +812,7 @@ def main():
     if not args.no_e2e:
         h_wav = torch.empty(total_samples, dtype=torch.float32, pin_memory=True)
         h_wav.copy_(wav)
-        h_out = torch.empty((rows, n_cols), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((ub_rows if wl in ("c2", "c2nf") else rows, n_cols), dtype=torch.float32, pin_memory=True)
 
         def e2e_step():
             if wl == "c1":
@@ -869,7 +874,7 @@ def main():
                                        "note": "same API, host buffer = 16-bit PCM WAV payload (quantised copy of the "
                                                "synthetic clips), int16 -> float32 / 32768 on the device"}
     # ---- the other BASELINE configs as sub-records of the same line (c1, c3, c4 at N = 1; the c5 sweep at every N)
-    chunk_samples = int(state["res"].chunks.lengths.sum()) if wl in ("c2", "c2nf") else total_samples
+    chunk_samples = chunk_samples_probe if wl in ("c2", "c2nf") else total_samples
     launches_per_step = int(state["launches"])
     subs = {}
     if not args.no_sub and wl == "c2" and world == 1:

@@ -56,6 +56,10 @@ hmfe_logmel_batch_views = _sig(
 hmfe_logmel_batch_views2 = _sig(
     "hmfe_logmel_batch_views2", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp
 )
+hmfe_logmel_batch_device = _sig(
+    "hmfe_logmel_batch_device", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp
+)
+hmfe_logmel_device_workspace_bytes = _sig("hmfe_logmel_device_workspace_bytes", C.c_int64, C.c_int64)
 hmfe_logmel_last_launches = _sig("hmfe_logmel_last_launches", C.c_int, c_voidp)
 hmfe_logmel_tc_status = _sig("hmfe_logmel_tc_status", C.c_int, c_voidp, C.POINTER(C.c_uint32))
 hmfe_logmel_set_profile = _sig("hmfe_logmel_set_profile", C.c_int, c_voidp, C.c_int)
@@ -97,6 +101,11 @@ class CropDesc(C.Structure):
                 ("mask_off", C.c_int32)]
 
 
+hmfe_entire_plan_batch = _sig(
+    "hmfe_entire_plan_batch", C.c_int, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+    C.c_int, C.c_int, C.c_int64, C.c_int, c_voidp, c_voidp, c_voidp,
+)
+hmfe_gather_device = _sig("hmfe_gather_device", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp)
 hmfe_gather_batch = _sig("hmfe_gather_batch", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp)
 hmfe_iir_sos_batch = _sig(
     "hmfe_iir_sos_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, c_voidp

@@ -104,7 +104,7 @@ logmel_power_kernel(const LogmelBatch b, const LogmelTables tb, const MelMeta mm
     // warps that start late (SMs shared with a concurrent collective kernel) or hit long clips simply
     // claim fewer blocks, instead of holding a fixed 1/grid share of the batch.
     constexpr int kItemBlock = 8;
-    const int64_t it_end = b.n_items;
+    const int64_t it_end = item_count(b);
     auto claim = [&]() -> int64_t {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
@@ -259,7 +259,7 @@ logmel_power_pair_kernel(const LogmelBatch b, const LogmelTables tb, const MelMe
     const int n_mels = mm.n_mels;
     const int n_slots = NSLOTS > 0 ? NSLOTS : mm.n_slots;
     constexpr int kItemBlock = 16;  // 16 items = 32 frames per claim, as in the packed kernel
-    const int64_t it_end = b.n_items;
+    const int64_t it_end = item_count(b);
     auto claim = [&]() -> int64_t {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
@@ -510,6 +510,36 @@ static int launch_pair(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t s
     }
 }
 
+// stats / queue initialisation, the power kernel of the plan's variant, the dB / min-max epilogue
+static int run_logmel(hmfe_logmel_plan* p, const LogmelBatch& b, int out_mode, cudaStream_t st) {
+    const int64_t n_clips = b.n_clips;
+    logmel_init_stats_kernel<<<(unsigned)((n_clips + 255) / 256), 256, 0, st>>>(b.stats, n_clips, b.queue);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (p->profile) {
+        for (int i = 0; i < 3; ++i) {
+            HMFE_CHECK_CUDA(cudaEventCreate(&ev[i]));
+            p->prof_events.push_back(ev[i]);
+        }
+        HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
+    }
+    int rc = p->variant == HMFE_VARIANT_TC       ? launch_logmel_tc(p, b, st)
+             : p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
+             : p->variant == HMFE_VARIANT_PAIR   ? launch_pair(p, b, st)
+                                                 : launch_power<float, 8, 2>(p, b, st);
+    if (rc != HMFE_OK) return rc;
+    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
+    p->last_launches = 2;
+    if (out_mode != HMFE_LOGMEL_OUT_POWER) {
+        const int grid = (int)std::min<int64_t>(n_clips, (int64_t)p->sm_count * 8);
+        logmel_finalize_kernel<<<grid, 256, 0, st>>>(b, p->n_mels, out_mode, 1e-10f, 80.0f);
+        HMFE_CHECK_CUDA(cudaGetLastError());
+        p->last_launches = 3;
+    }
+    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[2], st));
+    return HMFE_OK;
+}
+
 extern "C" {
 
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
@@ -728,31 +758,47 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
     b.stats = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(dbuf) + desc_bytes);
     b.queue = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(dbuf) + desc_bytes + stats_bytes);
 
-    logmel_init_stats_kernel<<<(unsigned)((n_clips + 255) / 256), 256, 0, st>>>(b.stats, n_clips, b.queue);
-    HMFE_CHECK_CUDA(cudaGetLastError());
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    if (p->profile) {
-        for (int i = 0; i < 3; ++i) {
-            HMFE_CHECK_CUDA(cudaEventCreate(&ev[i]));
-            p->prof_events.push_back(ev[i]);
-        }
-        HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
-    }
-    int rc = p->variant == HMFE_VARIANT_TC       ? launch_logmel_tc(p, b, st)
-             : p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
-             : p->variant == HMFE_VARIANT_PAIR ? launch_pair(p, b, st)
-                                               : launch_power<float, 8, 2>(p, b, st);
+    int rc = run_logmel(p, b, out_mode, st);
     if (rc != HMFE_OK) return rc;
-    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[1], st));
-    p->last_launches = 2;
-    if (out_mode != HMFE_LOGMEL_OUT_POWER) {
-        const int grid = (int)std::min<int64_t>(n_clips, (int64_t)p->sm_count * 8);
-        logmel_finalize_kernel<<<grid, 256, 0, st>>>(b, p->n_mels, out_mode, 1e-10f, 80.0f);
-        HMFE_CHECK_CUDA(cudaGetLastError());
-        p->last_launches = 3;
-    }
-    if (p->profile) HMFE_CHECK_CUDA(cudaEventRecord(ev[2], st));
     return p->ring.release(slot, st);
+}
+
+int64_t hmfe_logmel_device_workspace_bytes(int64_t n_clips) {
+    return n_clips < 0 ? -1 : (((int64_t)n_clips * 2 * (int64_t)sizeof(unsigned) + 15) & ~(int64_t)15) + 16;
+}
+
+int hmfe_logmel_batch_device(hmfe_logmel_plan* p, const float* d_wav, const float* d_wav_alt, const int64_t* d_desc,
+                             int64_t n_clips, float* d_out, int out_mode, void* d_workspace, void* stream) {
+    HMFE_REQUIRE(p, "NULL plan");
+    HMFE_REQUIRE(n_clips >= 0, "n_clips < 0");
+    HMFE_REQUIRE(out_mode >= 0 && out_mode <= 3, "bad out_mode %d", out_mode);
+    p->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_wav && d_desc && d_out && d_workspace, "NULL device pointer");
+    HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0,
+                 "d_out and d_workspace must be 16-byte aligned");
+    HMFE_REQUIRE(p->pad_mode == HMFE_PAD_CONSTANT, "device-planned batches use constant padding");
+    LogmelBatch b{};
+    b.wav = d_wav;
+    b.wav_alt = d_wav_alt ? d_wav_alt : d_wav;
+    b.out = d_out;
+    b.n_clips = n_clips;
+    b.hop = p->hop;
+    b.status = p->d_tc_status;
+    {
+        const char* e = getenv("HMFE_LOGMEL_STAGGER_NS");
+        b.stagger_ns = e ? atoi(e) : 500;
+    }
+    b.clip_start = d_desc;
+    b.clip_len = d_desc + n_clips;
+    b.frame_off = d_desc + 2 * n_clips;
+    b.item_prefix = d_desc + 3 * n_clips + 1;
+    b.n_items_dev = b.item_prefix + n_clips;
+    b.n_items = (int64_t)1 << 40;  // unknown to the host: full persistent grid
+    b.stats = static_cast<unsigned*>(d_workspace);
+    b.queue = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(d_workspace) +
+                                                    (((size_t)n_clips * 2 * sizeof(unsigned) + 15) & ~(size_t)15));
+    return run_logmel(p, b, out_mode, static_cast<cudaStream_t>(stream));
 }
 
 int hmfe_logmel_batch(hmfe_logmel_plan* p, const float* d_wav, const int64_t* h_offsets, int64_t n_clips, float* d_out,

@@ -29,6 +29,7 @@ struct LogmelBatch {
     unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
     unsigned long long* queue;   // next unclaimed work item (dynamic distribution over the warps)
     int64_t n_clips, n_items;
+    const int64_t* n_items_dev;  // != NULL: the item count is item_prefix[n_clips] in device memory (device-planned batches)
     int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
     int hop;
     int stagger_ns;  // start-up delay per warp index (HMFE_LOGMEL_STAGGER_NS overrides the default)
@@ -47,6 +48,8 @@ HMFE_D float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 HMFE_D f32x2 shfl(f32x2 v, int src) {
     return f32x2{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
 }
+
+HMFE_D int64_t item_count(const LogmelBatch& b) { return b.n_items_dev ? *b.n_items_dev : b.n_items; }
 
 // Work item descriptor: 2*NV consecutive frames of one clip.
 struct ItemCtx {

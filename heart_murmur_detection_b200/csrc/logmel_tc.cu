@@ -169,7 +169,7 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
     const int hop = HOP512 ? 512 : b.hop;
 
     constexpr int kItemBlock = 8;
-    const int64_t it_end = b.n_items;
+    const int64_t it_end = item_count(b);
     auto claim = [&]() -> int64_t {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);

@@ -229,6 +229,145 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ s
     }
 }
 
+// ---------------------------------------------------------------------------------- device-side planner
+// Control flow of get_entire_signal_librosa after the silence trim (/root/reference/src/util.py:248-259), evaluated
+// on the device from the trim indices so that the host never waits for them: duration test, "too short" (dropped or
+// padded to input_sec), cut at max_sec, pad descriptors (_zero_padding / _duplicate_padding, src/util.py:504-575),
+// then the exclusive scans that place every clip's feature rows and work items.  Same integer formulas as
+// frontend.plan_* / pipeline._entire_signal_fast (bit-exact index work); one CTA, n_clips is a few thousand.
+struct EntirePlanArgs {
+    const int64_t* clip_off;   // [n+1] device copy of the host offsets
+    const int64_t* start_end;  // [n][2] trim indices, clip relative
+    int64_t n_clips;
+    double sample_rate, input_sec, max_sec;  // max_sec <= 0: no cut
+    int pad, pad_zero;                       // pad: pad short clips; pad_zero: types == "zero" (else "repeat")
+    int hop, item_frames;
+    int64_t dst_base;  // first element of the padded copies in their buffer
+    int alt;           // padded copies live in a second buffer: start = -(offset + 1)
+    int64_t *out_start, *out_len, *frame_off, *item_prefix;  // [n], [n], [n+1], [n+1]
+    hmfe_gather_desc* descs;                                 // [n] (len = 0: nothing to materialise for this clip)
+};
+
+__global__ void __launch_bounds__(1024) entire_plan_kernel(const EntirePlanArgs a) {
+    __shared__ long long s_scan[3][32];
+    __shared__ long long s_carry[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long L = (long long)(a.input_sec * a.sample_rate);  // int(input_sec * sample_rate)
+    if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+    if (threadIdx.x == 0) a.frame_off[0] = a.item_prefix[0] = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < a.n_clips; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        long long T = 0, items = 0, padded = 0, n = 0, len = 0, start = 0;
+        bool valid = false, is_short = false;
+        if (i < a.n_clips) {
+            const long long s0 = a.start_end[2 * i], s1 = a.start_end[2 * i + 1];
+            n = s1 - s0;
+            const double dur = (double)n / a.sample_rate;
+            is_short = dur < a.input_sec;
+            valid = !is_short || (a.pad && n > 0);
+            start = a.clip_off[i] + s0;
+            len = n;
+            if (a.max_sec > 0 && dur > a.max_sec) len = min(len, (long long)(a.max_sec * a.sample_rate));
+            padded = (valid && is_short) ? 1 : 0;
+            if (padded) len = L;
+            T = valid ? 1 + len / a.hop : 0;
+            items = (T + a.item_frames - 1) / a.item_frames;
+        }
+        // block-wide exclusive scans of (T, items, padded)
+        long long v[3] = {T, items, padded}, incl[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            long long x = v[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            incl[k] = x;
+            if (lane == 31) s_scan[k][warp] = x;
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                long long x = lane < (int)(blockDim.x >> 5) ? s_scan[k][lane] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const long long y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= d) x += y;
+                }
+                s_scan[k][lane] = x;  // inclusive over warps
+            }
+        }
+        __syncthreads();
+        long long excl[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) excl[k] = s_carry[k] + (warp ? s_scan[k][warp - 1] : 0) + incl[k] - v[k];
+        if (i < a.n_clips) {
+            hmfe_gather_desc d{};
+            if (padded) {
+                const long long slot = a.dst_base + L * excl[2];
+                d.src_off = start;
+                d.dst_off = slot;
+                d.len = (int)L;
+                d.period = (int)n;
+                if (a.pad_zero) {  // _equally_slice_pad_sample -> one slice -> _zero_padding
+                    const bool tile = (double)n / (double)L < 0.5;
+                    const long long copies = (L - 1) / n;
+                    d.a_end = tile ? (int)(copies * n) : 0;
+                    d.b_end = tile ? (int)(copies * n) : (int)n;
+                } else {  // _duplicate_padding: source at the end, tail of the doubled clip in front
+                    const long long left = L - n;
+                    long long len_aug = n;
+                    while (len_aug < left) len_aug *= 2;
+                    d.a_end = (int)left;
+                    d.a_phase = (int)((len_aug - left) % n);
+                    d.b_end = (int)L;
+                }
+                start = a.alt ? -(slot + 1) : slot;
+            }
+            a.descs[i] = d;
+            a.out_start[i] = start;
+            a.out_len[i] = valid ? len : 0;
+            a.frame_off[i + 1] = excl[0] + T;
+            a.item_prefix[i + 1] = excl[1] + items;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s_carry[k] = excl[k] + v[k];
+        }
+        __syncthreads();
+    }
+}
+
+// gather with one descriptor per clip in device memory (len = 0: nothing to do)
+__global__ void __launch_bounds__(256) gather_device_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            const hmfe_gather_desc* __restrict__ descs, int tiles_per_chunk) {
+    const int64_t chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = (int)(blockIdx.x - chunk * tiles_per_chunk);
+    const hmfe_gather_desc d = descs[chunk];
+    const int t0 = tile * kGatherTile;
+    if (t0 >= d.len) return;
+    const float* s = src + d.src_off;
+    float* o = dst + d.dst_off;
+    const int t1 = min(d.len, t0 + kGatherTile);
+    const unsigned period = (unsigned)d.period;
+    unsigned ph = (unsigned)(((unsigned long long)d.a_phase + (unsigned)(t0 + threadIdx.x)) % period);
+    const unsigned step = 256u % period;
+    for (int i = t0 + threadIdx.x; i < t1; i += 256) {
+        float v = 0.0f;
+        if (i < d.a_end)
+            v = __ldg(s + ph);
+        else if (i < d.b_end)
+            v = __ldg(s + d.b_start + (i - d.a_end));
+        o[i] = v;
+        ph += step;
+        if (ph >= period) ph -= period;
+    }
+}
+
 // ---------------------------------------------------------------------------------- PCM16 decode
 // The sample conversion inside librosa.load / soundfile.read(dtype="float32") for 16-bit PCM WAV
 // payloads (/root/reference/src/util.py:153,222,323,391,805): x = int16 / 32768 (exact in float32).
@@ -464,6 +603,64 @@ int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmf
     ctx->prof_end(st);
     ctx->last_launches = 1;
     return ctx->ring.release(slot, st);
+}
+
+int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_clips, const int64_t* d_start_end,
+                           int sample_rate, double input_sec, int pad, int pad_zero, double max_sec, int hop, int item_frames,
+                           int64_t dst_base, int alt, int64_t* d_desc, hmfe_gather_desc* d_gather, void* stream) {
+    HMFE_REQUIRE(ctx && h_offsets, "NULL argument");
+    HMFE_REQUIRE(n_clips >= 0 && sample_rate > 0 && input_sec > 0 && hop >= 1 && item_frames >= 1, "bad plan arguments");
+    ctx->last_launches = 0;
+    if (n_clips == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_start_end && d_desc && d_gather, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)(n_clips + 1) * sizeof(int64_t);
+    void *hbuf = nullptr, *dbuf = nullptr;
+    const int slot = ctx->ring.acquire(bytes, &hbuf, &dbuf);
+    if (slot < 0) return slot;
+    memcpy(hbuf, h_offsets, bytes);
+    int rc = ctx->ring.upload(slot, bytes, st);
+    if (rc != HMFE_OK) return rc;
+    EntirePlanArgs a{};
+    a.clip_off = static_cast<int64_t*>(dbuf);
+    a.start_end = d_start_end;
+    a.n_clips = n_clips;
+    a.sample_rate = (double)sample_rate;
+    a.input_sec = input_sec;
+    a.max_sec = max_sec;
+    a.pad = pad;
+    a.pad_zero = pad_zero;
+    a.hop = hop;
+    a.item_frames = item_frames;
+    a.dst_base = dst_base;
+    a.alt = alt;
+    a.out_start = d_desc;
+    a.out_len = d_desc + n_clips;
+    a.frame_off = d_desc + 2 * n_clips;
+    a.item_prefix = d_desc + 3 * n_clips + 1;
+    a.descs = d_gather;
+    entire_plan_kernel<<<1, 1024, 0, st>>>(a);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->last_launches = 1;
+    return ctx->ring.release(slot, st);
+}
+
+int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs, int64_t n_chunks,
+                       int max_len, void* stream) {
+    HMFE_REQUIRE(ctx, "NULL argument");
+    HMFE_REQUIRE(n_chunks >= 0 && max_len >= 0, "bad arguments");
+    ctx->last_launches = 0;
+    if (n_chunks == 0 || max_len == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_src && d_dst && d_descs, "NULL device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles = (max_len + kGatherTile - 1) / kGatherTile;
+    HMFE_REQUIRE(n_chunks * tiles < (int64_t)INT32_MAX, "gather grid too large");
+    ctx->prof_begin(HMFE_K_GATHER, st);
+    gather_device_kernel<<<(unsigned)(n_chunks * tiles), 256, 0, st>>>(d_src, d_dst, d_descs, tiles);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    ctx->prof_end(st);
+    ctx->last_launches = 1;
+    return HMFE_OK;
 }
 
 }  // extern "C"

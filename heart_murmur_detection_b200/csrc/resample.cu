@@ -87,6 +87,91 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleBatch b, co
     }
 }
 
+// Integer up-factors (D = 1: 2 / 4 / 8 kHz -> 16 kHz, the rates of the heart-sound corpora).  One thread = 4 consecutive
+// input positions = 4 U consecutive outputs.  The input window is read as 16-byte shared-memory vectors (conflict
+// free; scalar reads at a stride of 4 floats would be 4-way bank conflicts) and slides through registers; the U
+// phases of a tap are one broadcast vector read, used for all 4 positions: (1 + 4) vector reads per 16 U FMAs.
+// Outputs leave as 16-byte stores.  Taps are padded with zeros to a multiple of 4 (an FMA with a zero tap leaves the
+// accumulator unchanged), accumulation runs over the taps in ascending order like the generic kernel: same results.
+constexpr int kUpTileQ = 1024;     // input positions per tile (256 threads x 4)
+constexpr int kUpTilesPerCta = 8;  // consecutive tiles per CTA: one clip lookup, then a linear walk
+
+template <typename T, int U>
+__global__ void __launch_bounds__(256) resample_up_kernel(const ResampleBatch b, const int64_t* tile_prefix, int64_t n_tiles) {
+    extern __shared__ __align__(16) float rs_smem[];
+    const int W = b.W, W4 = (W + 3) & ~3;
+    float* s_k = rs_smem;            // [W4][U]: the U phases of one tap are adjacent
+    float* s_x = rs_smem + U * W4;   // [kUpTileQ + W4 + 4]
+    for (int i = threadIdx.x; i < U * W4; i += 256) {
+        const int t = i / U, p = i - t * U;
+        s_k[i] = t < W ? __ldg(b.kern + p * W + t) : 0.0f;
+    }
+    const int64_t tile0 = (int64_t)blockIdx.x * kUpTilesPerCta;
+    int64_t lo = 0, hi = b.n_clips;
+    while (hi - lo > 1) {  // tile -> clip
+        const int64_t mid = (lo + hi) >> 1;
+        if (tile_prefix[mid] <= tile0)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    int64_t clip = lo;
+    for (int64_t tile = tile0; tile < min(tile0 + kUpTilesPerCta, n_tiles); ++tile) {
+        while (tile >= tile_prefix[clip + 1]) ++clip;
+        const int64_t i0 = b.in_off[clip];
+        const int n_in = (int)(b.in_off[clip + 1] - i0);
+        const int64_t o0 = b.out_off[clip];
+        const T* x = static_cast<const T*>(b.x) + i0;
+        const int q0 = (int)(tile - tile_prefix[clip]) * kUpTileQ;
+        const int span = kUpTileQ + W4 + 4, base0 = q0 - b.width;
+        __syncthreads();  // the previous tile's window has been consumed (and the taps are in place)
+        for (int i = threadIdx.x; i < span; i += 256) {
+            const int g = base0 + i;
+            s_x[i] = (g >= 0 && g < n_in) ? rs_sample(x, g) : 0.0f;
+        }
+        __syncthreads();
+        const int ql = threadIdx.x * 4;
+        if (q0 + ql >= n_in) continue;
+        float acc[4][U];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int p = 0; p < U; ++p) acc[r][p] = 0.0f;
+        float4 xa = *reinterpret_cast<const float4*>(s_x + ql);
+        for (int t0 = 0; t0 < W4; t0 += 4) {
+            const float4 xb = *reinterpret_cast<const float4*>(s_x + ql + t0 + 4);
+            const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+                float kv[U];
+#pragma unroll
+                for (int p = 0; p < U; ++p) kv[p] = s_k[(t0 + tt) * U + p];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int p = 0; p < U; ++p) acc[r][p] = fmaf(kv[p], xs[tt + r], acc[r][p]);
+            }
+            xa = xb;
+        }
+        float* y = b.y + o0 + (int64_t)(q0 + ql) * U;
+        if ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && q0 + ql + 4 <= n_in) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) {  // 4 U floats = U float4
+                const int e = 4 * i;
+                reinterpret_cast<float4*>(y)[i] = make_float4(acc[e / U][e % U], acc[(e + 1) / U][(e + 1) % U],
+                                                              acc[(e + 2) / U][(e + 2) % U], acc[(e + 3) / U][(e + 3) % U]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (q0 + ql + r >= n_in) break;
+#pragma unroll
+                for (int p = 0; p < U; ++p) y[r * U + p] = acc[r][p];
+            }
+        }
+    }
+}
+
 static double bessel_i0(double x) {
     double sum = 1.0, term = 1.0;
     const double q = x * x / 4.0;
@@ -206,13 +291,16 @@ static int resample_launch(hmfe_resample_plan* p, const void* d_in, bool pcm16, 
     int64_t* ho = hi + (n_clips + 1);
     int64_t* ht = ho + (n_clips + 1);
     ho[0] = ht[0] = 0;
+    // integer up-factors take the register-tiled kernel (tiles count input positions there)
+    const bool up = p->D == 1 && (p->U == 2 || p->U == 4 || p->U == 8) &&
+                    ((size_t)(p->U + 1) * (p->W + 4) + kUpTileQ + 8) * sizeof(float) <= 96 * 1024;
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t n = h_in_offsets[i + 1] - h_in_offsets[i];
         HMFE_REQUIRE(n >= 0 && n < (int64_t)1 << 28, "clip %lld has invalid length %lld", (long long)i, (long long)n);
         const int64_t m = hmfe_resample_out_len(p, n);
         hi[i] = h_in_offsets[i];
         ho[i + 1] = ho[i] + m;
-        ht[i + 1] = ht[i] + (m + kRsTile - 1) / kRsTile;
+        ht[i + 1] = ht[i] + (up ? (n + kUpTileQ - 1) / kUpTileQ : (m + kRsTile - 1) / kRsTile);
     }
     hi[n_clips] = h_in_offsets[n_clips];
     int rc = p->ring.upload(slot, bytes, st);
@@ -238,7 +326,21 @@ static int resample_launch(hmfe_resample_plan* p, const void* d_in, bool pcm16, 
         HMFE_REQUIRE(smem <= 200 * 1024, "resampling ratio %d/%d with %d taps needs %zu bytes of shared memory", p->U, p->D, p->W,
                      smem);
         const int64_t* prefix = b.in_off + 2 * (n_clips + 1);
-        if (pcm16) {
+        if (up) {
+            const size_t smem_up = ((size_t)(p->U + 1) * ((p->W + 3) / 4 * 4) + kUpTileQ + 8) * sizeof(float);
+            const unsigned ctas = (unsigned)((tiles + kUpTilesPerCta - 1) / kUpTilesPerCta);
+#define HMFE_RS_UP(TYPE, UF)                                                                                                \
+    {                                                                                                                       \
+        HMFE_CHECK_CUDA(cudaFuncSetAttribute(resample_up_kernel<TYPE, UF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up)); \
+        resample_up_kernel<TYPE, UF><<<ctas, 256, smem_up, st>>>(b, prefix, tiles);                                          \
+    }
+            if (pcm16) {
+                if (p->U == 2) HMFE_RS_UP(int16_t, 2) else if (p->U == 4) HMFE_RS_UP(int16_t, 4) else HMFE_RS_UP(int16_t, 8)
+            } else {
+                if (p->U == 2) HMFE_RS_UP(float, 2) else if (p->U == 4) HMFE_RS_UP(float, 4) else HMFE_RS_UP(float, 8)
+            }
+#undef HMFE_RS_UP
+        } else if (pcm16) {
             HMFE_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             resample_kernel<int16_t><<<(unsigned)tiles, 256, smem, st>>>(b, prefix);
         } else {

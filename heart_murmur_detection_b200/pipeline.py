@@ -274,13 +274,148 @@ def _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter
                       is_view[keep], sos is not None, alt)
 
 
+class DeviceFeatures:
+    """Result of ``entire_signal_device``: everything has been ENQUEUED, nothing has been read back.  ``features`` holds
+    the rows of the kept recordings back to back (its row count is only an upper bound until ``resolve``);
+    ``resolve()`` waits for the small descriptor copy and returns the usual FeatureBatch with host-side offsets."""
+
+    def __init__(self, features, work, alt, h_meta, event, n_clips, total, L, filtered, types, launches, keep_alive):
+        self.features, self.work, self.alt = features, work, alt
+        self._h_meta, self._event, self._n, self._total, self._L = h_meta, event, n_clips, total, L
+        self._filtered, self._types, self.launches, self._keep = filtered, types, launches, keep_alive
+        self._fb = None
+
+    def resolve(self) -> FeatureBatch:
+        if self._fb is None:
+            self._event.synchronize()
+            n = self._n
+            m = self._h_meta.numpy()
+            se = m[: 2 * n].reshape(n, 2).copy()
+            starts, lengths = m[2 * n : 3 * n], m[3 * n : 4 * n]
+            frame_off = m[4 * n : 5 * n + 1]
+            rows = np.diff(frame_off)
+            keep = np.flatnonzero(rows > 0)
+            nn = se[:, 1] - se[:, 0]
+            valid = np.zeros(n, dtype=bool)
+            valid[keep] = True
+            padded = (lengths[keep] == self._L) & (nn[keep] < self._L)
+            is_view = ~padded
+            dup = bool(padded.any()) and self._types != "zero"
+            cb = ChunkBatch(self.work, starts[keep].copy(), lengths[keep].copy(), keep.astype(np.int64), n, valid, se, dup,
+                            self.launches, is_view, self._filtered, self.alt)
+            ro = np.zeros(keep.size + 1, dtype=np.int64)
+            np.cumsum(rows[keep], out=ro[1:])
+            self._fb = FeatureBatch(self.features, ro, cb, self.launches)
+        return self._fb
+
+
+class _Resolved:
+    """A FeatureBatch that was planned on the host, behind the DeviceFeatures interface."""
+
+    def __init__(self, fb):
+        self.features, self._fb = fb.features, fb
+
+    def resolve(self):
+        return self._fb
+
+
+_dev_scratch: dict = {}
+
+
+def entire_signal_device(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, pad=False, types="repeat",
+                         lowcut=200, highcut=1800, max_sec=None, f_max=8000, work=None, out=None, ctx=None) -> DeviceFeatures:
+    """get_entire_signal_librosa(spectrogram=True) over a batch with NO host round trip: band-pass + trim, the
+    planner kernel (duration test, pad / cut decisions, row and work-item offsets: ``hmfe_entire_plan_batch``), the
+    padded copies, the log-mel kernels and an asynchronous copy of the descriptors are enqueued back to back on the
+    current stream.  The reference's control flow (src/util.py:248-259) runs on the device; the host learns the row
+    offsets when it asks (``DeviceFeatures.resolve``).  ``out`` must hold sum(1 + max(len_i, L) // 512) rows."""
+    import ctypes as C
+
+    from . import _lib
+
+    if max_sec and max_sec < input_sec:
+        raise ValueError("max_sec < input_sec (pad, then cut) is planned on the host: use entire_signal_batch")
+    ctx = ctx or fe.default_ctx()
+    o = fe._as_offsets(offsets)
+    n, total = o.size - 1, int(o[-1])
+    dev = wav.device
+    L = int(input_sec * sample_rate)
+    hop = 512
+    plan = fe.logmel_plan(16000, 64, 50, f_max, 1024, hop)
+    lens = np.diff(o)
+    rows_ub = int((1 + np.maximum(lens, L if pad else 0) // hop).sum())
+    launches = 0
+    sos = _sos_for(butterworth_filter, lowcut, highcut, sample_rate)
+    frame_len = int(sample_rate / 10)
+    se = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    pad_elems = L * n if pad else 0  # upper bound: every recording may turn out short after the trim
+    alt = None
+    with torch.cuda.device(dev):
+        if sos is not None:
+            if work is None or work.numel() < total + pad_elems:
+                work = torch.empty(total + pad_elems, dtype=torch.float32, device=dev)
+            _lib.check(_lib.hmfe_iir_sos_trim_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), n,
+                                                    np.ascontiguousarray(sos, dtype=np.float64).ctypes.data_as(C.c_void_p),
+                                                    sos.shape[0], C.c_void_p(work.data_ptr()), C.c_void_p(), frame_len,
+                                                    int(frame_len / 2), 60.0, C.c_void_p(se.data_ptr()), fe._stream_ptr()),
+                       "hmfe_iir_sos_trim_batch")
+            signal, dst, dst_base, use_alt = work, work, total, 0
+        else:
+            if pad and (work is None or work.data_ptr() == wav.data_ptr() or work.numel() < pad_elems):
+                work = torch.empty(max(pad_elems, 1), dtype=torch.float32, device=dev)
+            _lib.check(_lib.hmfe_trim_batch(ctx._h, C.c_void_p(wav.data_ptr()), o.ctypes.data_as(C.c_void_p), n, frame_len,
+                                            int(frame_len / 2), 60.0, C.c_void_p(se.data_ptr()), fe._stream_ptr()), "hmfe_trim_batch")
+            signal, dst, dst_base, use_alt = wav, work, 0, 1
+            alt = work if pad else None
+        launches += ctx.last_launches
+        key = (dev, n, torch.cuda.current_stream().cuda_stream)  # scratch is reused by stream-ordered calls only
+        sc = _dev_scratch.get(key)
+        if sc is None:
+            ws = int(_lib.hmfe_logmel_device_workspace_bytes(n))
+            sc = _dev_scratch[key] = {"desc": torch.empty(4 * n + 2, dtype=torch.int64, device=dev),
+                                      "gather": torch.empty(n * 40, dtype=torch.uint8, device=dev),
+                                      "ws": torch.empty(ws, dtype=torch.uint8, device=dev)}
+            if len(_dev_scratch) > 64:
+                _dev_scratch.pop(next(iter(_dev_scratch)))
+        _lib.check(_lib.hmfe_entire_plan_batch(ctx._h, o.ctypes.data_as(C.c_void_p), n, C.c_void_p(se.data_ptr()), int(sample_rate),
+                                               float(input_sec), int(bool(pad)), int(types == "zero"), float(max_sec or 0.0), hop, 4,
+                                               dst_base, use_alt, C.c_void_p(sc["desc"].data_ptr()),
+                                               C.c_void_p(sc["gather"].data_ptr()), fe._stream_ptr()), "hmfe_entire_plan_batch")
+        launches += 1
+        if pad:
+            _lib.check(_lib.hmfe_gather_device(ctx._h, C.c_void_p(signal.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                               C.c_void_p(sc["gather"].data_ptr()), n, L, fe._stream_ptr()), "hmfe_gather_device")
+            launches += 1
+        if out is None or out.numel() < rows_ub * 64:
+            out = torch.empty((rows_ub, 64), dtype=torch.float32, device=dev)
+        _lib.check(_lib.hmfe_logmel_batch_device(plan._h, C.c_void_p(signal.data_ptr()),
+                                                 C.c_void_p(alt.data_ptr()) if alt is not None else C.c_void_p(),
+                                                 C.c_void_p(sc["desc"].data_ptr()), n, C.c_void_p(out.data_ptr()), 0,
+                                                 C.c_void_p(sc["ws"].data_ptr()), fe._stream_ptr()), "hmfe_logmel_batch_device")
+        launches += plan.last_launches
+        h_meta = torch.empty(5 * n + 1, dtype=torch.int64, pin_memory=True)
+        h_meta[: 2 * n].copy_(se.view(-1), non_blocking=True)
+        h_meta[2 * n :].copy_(sc["desc"][: 3 * n + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+    return DeviceFeatures(out, signal, alt, h_meta, ev, n, total, L, sos is not None, types, launches, (se, sc))
+
+
 def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,
                         pad=False, types="repeat", lowcut=200, highcut=1800, max_sec=None, f_max=8000, work=None,
-                        out=None):
+                        out=None, planner="device"):
     """get_entire_signal_librosa over a batch.  Returns FeatureBatch (spectrogram=True) or ChunkBatch.
+
+    ``planner="device"`` (default for spectrograms): the pad / cut / offset planning runs in a kernel and the host reads
+    the descriptors back once, after everything has been enqueued (``entire_signal_device``); ``"host"``: the trim
+    indices are read back in the middle of the step and numpy plans (the first implementation, kept as the
+    cross-check of the planner kernel).
 
     ``work`` / ``out`` are optional pre-allocated device buffers (filtered signal + padded copies,
     feature rows) for callers that run many batches back to back."""
+    if spectrogram and planner == "device" and (not max_sec or max_sec >= input_sec) and len(np.atleast_1d(offsets)) > 1:
+        return entire_signal_device(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut,
+                                    max_sec, f_max, work=work, out=out).resolve()
     if not max_sec or max_sec >= input_sec:
         cb = _entire_signal_fast(wav, offsets, input_sec, sample_rate, butterworth_filter, pad, types, lowcut, highcut,
                                  max_sec, work=work)
@@ -455,30 +590,50 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
                 d_in[i % 2][:n_in].copy_(src, non_blocking=True)
             ev_in[i % 2].record(s_in)
 
+    # Every sub-batch is enqueued without waiting for its OWN trim indices (device-side planner).  Where its rows go in
+    # h_out depends on the row counts of the sub-batches before it, so its copy-out is enqueued after the descriptors of
+    # the PREVIOUS sub-batch have arrived - by then its own kernels are already queued and the GPU never idles.  The
+    # copy moves the sub-batch's upper-bound row count; the surplus rows are overwritten by the next sub-batch's copy
+    # (same stream), and h_out holds the upper bound of the whole batch.
+    if h_out.shape[0] < int(rows_ub.sum()):
+        raise ValueError(f"h_out needs {int(rows_ub.sum())} rows (upper bound: 1 + max(len, L) // 512 per recording)")
+    pending = []
     row_offsets, clip_ids, valid = [np.zeros(1, np.int64)], [], np.zeros(n, dtype=bool)
     base = 0
+
+    def account(j):  # descriptors of sub-batch j -> host offsets; returns its row count
+        a_, b_, res_ = pending[j]
+        fb = res_.resolve()
+        row_offsets.append(base + fb.row_offsets[1:])
+        clip_ids.append(a_ + fb.chunks.clip_ids)
+        valid[a_:b_] = fb.chunks.valid
+        return int(fb.row_offsets[-1])
+
     copy_in(0)
     for i, (a, b) in enumerate(subs):
         if i + 1 < len(subs):
             copy_in(i + 1)
+        ub = int(rows_ub[a:b].sum())
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i % 2])
             if i >= 2:
                 s_cmp.wait_event(ev_out[i % 2])  # feat[i % 2] still being copied out by sub-batch i - 2
-            res = entire_signal_batch(d_in[i % 2], o[a : b + 1] - o[a], spectrogram=True,
-                                      work=work[i % 2], out=feat[i % 2], **kw)
+            if kw.get("max_sec") and kw["max_sec"] < input_sec:  # pad-then-cut corner: host planner
+                res = _Resolved(entire_signal_batch(d_in[i % 2], o[a : b + 1] - o[a], spectrogram=True, work=work[i % 2],
+                                                    out=feat[i % 2], **kw))
+            else:
+                res = entire_signal_device(d_in[i % 2], o[a : b + 1] - o[a], work=work[i % 2], out=feat[i % 2], **kw)
             ev_free[i % 2].record(s_cmp)
             done = torch.cuda.Event()
             done.record(s_cmp)
-        rows = int(res.row_offsets[-1])
+        pending.append((a, b, res))
+        if i >= 1:
+            base += account(i - 1)
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
-            h_out[base : base + rows].copy_(res.features[:rows], non_blocking=True)
+            h_out[base : base + ub].copy_(res.features[:ub], non_blocking=True)
             ev_out[i % 2].record(s_out)
-        row_offsets.append(base + res.row_offsets[1:])
-        clip_ids.append(a + res.chunks.clip_ids)
-        valid[a:b] = res.chunks.valid
-        base += rows
+    base += account(len(subs) - 1)
     s_out.synchronize()
     s_cmp.synchronize()
     return h_out, np.concatenate(row_offsets), (np.concatenate(clip_ids) if clip_ids else np.zeros(0, np.int64)), valid

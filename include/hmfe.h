@@ -79,6 +79,13 @@ int hmfe_logmel_batch_views(hmfe_logmel_plan* plan, const float* d_wav, const in
  * d_wav_alt[-s - 1 : -s - 1 + length] (padded copies kept apart from a read-only signal buffer) */
 int hmfe_logmel_batch_views2(hmfe_logmel_plan* plan, const float* d_wav, const float* d_wav_alt, const int64_t* h_starts,
                              const int64_t* h_lengths, int64_t n_clips, float* d_out, int out_mode, void* stream);
+/* same with the per-clip descriptors already in device memory (written by hmfe_entire_plan_batch): d_desc[4 n + 2] =
+ * clip_start | clip_len | frame_off | item_prefix.  Nothing is read back: the call is asynchronous and the step it
+ * belongs to can be captured in a CUDA graph.  d_out must hold the caller's upper bound of rows. */
+int hmfe_logmel_batch_device(hmfe_logmel_plan* plan, const float* d_wav, const float* d_wav_alt, const int64_t* d_desc,
+                             int64_t n_clips, float* d_out, int out_mode, void* d_workspace, void* stream);
+/* bytes of d_workspace for n_clips (per-clip statistics and the work queue) */
+int64_t hmfe_logmel_device_workspace_bytes(int64_t n_clips);
 /* HMFE_VARIANT_TC only: protocol-error word of the kernel's bounded mbarrier waits (0 = no error); synchronises. */
 int hmfe_logmel_tc_status(hmfe_logmel_plan* plan, uint32_t* h_status);
 /* number of kernel launches the last hmfe_logmel_batch call on this plan issued */
@@ -146,6 +153,21 @@ typedef struct hmfe_gather_desc {
 } hmfe_gather_desc;
 int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* h_descs,
                       int64_t n_chunks, void* stream);
+
+/* Device-side planner: the control flow of get_entire_signal_librosa between the silence trim and the log-mel
+ * (src/util.py:248-259: duration test, "too short" -> dropped or padded to input_sec by _zero_padding /
+ * _duplicate_padding (src/util.py:504-575), cut at max_sec) evaluated ON THE DEVICE from the trim indices
+ * d_start_end[n_clips][2], so that the host does not wait for them.  Writes, for hmfe_logmel_batch_device,
+ *   d_desc[4 n + 2] = clip_start[n] | clip_len[n] | frame_off[n + 1] | item_prefix[n + 1]   (int64)
+ * (dropped clips get zero rows) and one gather record per clip for hmfe_gather_device (len = 0 when the clip needs no
+ * padded copy; padded copy k of the batch goes to element dst_base + k * int(input_sec * sample_rate) of the destination;
+ * with `alt` the clip start is encoded as -(offset + 1), the second-buffer convention of hmfe_logmel_batch_views2).
+ * item_frames = frames per work item of the log-mel variant (4).  All outputs are caller-provided device memory. */
+int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_clips, const int64_t* d_start_end,
+                           int sample_rate, double input_sec, int pad, int pad_zero, double max_sec, int hop, int item_frames,
+                           int64_t dst_base, int alt, int64_t* d_desc, hmfe_gather_desc* d_gather, void* stream);
+int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs, int64_t n_chunks,
+                       int max_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Band-pass IIR: replaces scipy.signal.lfilter(b, a, x) in _butter_bandpass_filter

@@ -448,3 +448,33 @@ def test_c3_full_size_properties():
     # the frames land in other lanes / packed pairs of the warp: equal within the fbank tolerance, not bit for bit
     shifted, _ = plan(wav[off[7] + 160 : off[8]].clone(), np.array([0, lens[7] - 160]))
     assert (shifted - out[7, 1:1022]).abs().max().item() <= 2.3e-3
+
+
+@pytest.mark.parametrize("bp", [None, 5])
+@pytest.mark.parametrize("pad,types,max_sec", [(True, "zero", 32), (True, "repeat", None), (False, "repeat", 32), (True, "zero", None)])
+def test_device_planner_equals_host_planner(bp, pad, types, max_sec):
+    """hmfe_entire_plan_batch (duration test, pad / cut decisions, padding descriptors, row and work-item offsets on the
+    device) against the numpy planner that reads the trim indices back: identical chunk tables, identical features."""
+    from heart_murmur_detection_b200 import pipeline as pl
+    from heart_murmur_detection_b200 import synth
+
+    lens = synth.clip_lengths("c2", 96, seed=31)
+    lens[:8] = [1, 2000, 16000, 63999, 64000, 64001, 127999, 128000]  # knife edges of the pad rules (L = 128000)
+    lens[8:12] = [128001, 511999, 512000, 512001]                      # and of the 32 s cut
+    wav, off = synth.make_batch(lens, base_seed=9100, device="cuda")
+    wav[off[20] : off[21]] = 0.0                                       # an all-silent recording: trims to nothing
+    kw = dict(input_sec=8, butterworth_filter=bp, pad=pad, types=types, max_sec=max_sec, spectrogram=True)
+    host = pl.entire_signal_batch(wav, off, planner="host", **kw)
+    dev = pl.entire_signal_batch(wav, off, planner="device", **kw)
+    np.testing.assert_array_equal(dev.row_offsets, host.row_offsets)
+    np.testing.assert_array_equal(dev.chunks.clip_ids, host.chunks.clip_ids)
+    np.testing.assert_array_equal(dev.chunks.valid, host.chunks.valid)
+    np.testing.assert_array_equal(dev.chunks.trim, host.chunks.trim)
+    np.testing.assert_array_equal(dev.chunks.lengths, host.chunks.lengths)
+    np.testing.assert_array_equal(dev.chunks.is_view, host.chunks.is_view)
+    assert dev.chunks.used_duplicate_padding == host.chunks.used_duplicate_padding
+    rows = int(host.row_offsets[-1])
+    assert torch.equal(dev.features[:rows], host.features[:rows])
+    for k in range(len(host.chunks.starts)):  # the padded copies themselves
+        if not host.chunks.is_view[k]:
+            assert torch.equal(dev.chunks.samples(k), host.chunks.samples(k))
