@@ -105,7 +105,7 @@ hmfe_entire_plan_batch = _sig(
     "hmfe_entire_plan_batch", C.c_int, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
     C.c_int, C.c_int, C.c_int64, C.c_int, c_voidp, c_voidp, c_voidp,
 )
-hmfe_gather_device = _sig("hmfe_gather_device", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp)
+hmfe_gather_device = _sig("hmfe_gather_device", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, C.c_int, c_voidp)
 hmfe_gather_batch = _sig("hmfe_gather_batch", C.c_int, c_voidp, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp)
 hmfe_iir_sos_batch = _sig(
     "hmfe_iir_sos_batch", C.c_int, c_voidp, c_voidp, c_voidp, C.c_int64, c_voidp, C.c_int, c_voidp, c_voidp, c_voidp

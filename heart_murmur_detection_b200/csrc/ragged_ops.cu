@@ -245,7 +245,8 @@ struct EntirePlanArgs {
     int64_t dst_base;  // first element of the padded copies in their buffer
     int alt;           // padded copies live in a second buffer: start = -(offset + 1)
     int64_t *out_start, *out_len, *frame_off, *item_prefix;  // [n], [n], [n+1], [n+1]
-    hmfe_gather_desc* descs;                                 // [n] (len = 0: nothing to materialise for this clip)
+    hmfe_gather_desc* descs;                                 // [n] compact list of the padded copies to materialise
+    int64_t* n_descs;                                        // how many of them
 };
 
 __global__ void __launch_bounds__(1024) entire_plan_kernel(const EntirePlanArgs a) {
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(1024) entire_plan_kernel(const EntirePlanArgs 
                 }
                 start = a.alt ? -(slot + 1) : slot;
             }
-            a.descs[i] = d;
+            if (padded) a.descs[excl[2]] = d;
             a.out_start[i] = start;
             a.out_len[i] = valid ? len : 0;
             a.frame_off[i + 1] = excl[0] + T;
@@ -340,31 +341,48 @@ __global__ void __launch_bounds__(1024) entire_plan_kernel(const EntirePlanArgs 
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) *a.n_descs = s_carry[2];
 }
 
-// gather with one descriptor per clip in device memory (len = 0: nothing to do)
+// gather from a compact descriptor list in device memory whose length is only known on the device: a fixed grid
+// walks the (descriptor, tile) pairs
 __global__ void __launch_bounds__(256) gather_device_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                            const hmfe_gather_desc* __restrict__ descs, int tiles_per_chunk) {
-    const int64_t chunk = blockIdx.x / tiles_per_chunk;
-    const int tile = (int)(blockIdx.x - chunk * tiles_per_chunk);
-    const hmfe_gather_desc d = descs[chunk];
-    const int t0 = tile * kGatherTile;
-    if (t0 >= d.len) return;
-    const float* s = src + d.src_off;
-    float* o = dst + d.dst_off;
-    const int t1 = min(d.len, t0 + kGatherTile);
-    const unsigned period = (unsigned)d.period;
-    unsigned ph = (unsigned)(((unsigned long long)d.a_phase + (unsigned)(t0 + threadIdx.x)) % period);
-    const unsigned step = 256u % period;
-    for (int i = t0 + threadIdx.x; i < t1; i += 256) {
-        float v = 0.0f;
-        if (i < d.a_end)
-            v = __ldg(s + ph);
-        else if (i < d.b_end)
-            v = __ldg(s + d.b_start + (i - d.a_end));
-        o[i] = v;
-        ph += step;
-        if (ph >= period) ph -= period;
+                                                            const hmfe_gather_desc* __restrict__ descs,
+                                                            const int64_t* __restrict__ n_descs, int tiles_per_chunk) {
+    const int64_t n_work = *n_descs * tiles_per_chunk;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int64_t chunk = w / tiles_per_chunk;
+        const int tile = (int)(w - chunk * tiles_per_chunk);
+        const hmfe_gather_desc d = descs[chunk];
+        const int t0 = tile * kGatherTile;
+        if (t0 >= d.len) continue;
+        const float* s = src + d.src_off;
+        float* o = dst + d.dst_off;
+        const int t1 = min(d.len, t0 + kGatherTile);
+        const unsigned period = (unsigned)d.period;
+        unsigned ph = (unsigned)(((unsigned long long)d.a_phase + (unsigned)(t0 + threadIdx.x)) % period);
+        const unsigned step = 256u % period;
+        for (int i0 = t0 + threadIdx.x; i0 < t1; i0 += 1024) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 256 * u;
+                v[u] = 0.0f;
+                if (i < t1) {
+                    if (i < d.a_end)
+                        v[u] = __ldg(s + ph);
+                    else if (i < d.b_end)
+                        v[u] = __ldg(s + d.b_start + (i - d.a_end));
+                }
+                ph += step;
+                if (ph >= period) ph -= period;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 256 * u;
+                if (i < t1) o[i] = v[u];
+            }
+        }
     }
 }
 
@@ -638,6 +656,7 @@ int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_cl
     a.out_len = d_desc + n_clips;
     a.frame_off = d_desc + 2 * n_clips;
     a.item_prefix = d_desc + 3 * n_clips + 1;
+    a.n_descs = d_desc + 4 * n_clips + 2;
     a.descs = d_gather;
     entire_plan_kernel<<<1, 1024, 0, st>>>(a);
     HMFE_CHECK_CUDA(cudaGetLastError());
@@ -645,18 +664,18 @@ int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_cl
     return ctx->ring.release(slot, st);
 }
 
-int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs, int64_t n_chunks,
-                       int max_len, void* stream) {
+int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs,
+                       const int64_t* d_n_descs, int64_t max_chunks, int max_len, void* stream) {
     HMFE_REQUIRE(ctx, "NULL argument");
-    HMFE_REQUIRE(n_chunks >= 0 && max_len >= 0, "bad arguments");
+    HMFE_REQUIRE(max_chunks >= 0 && max_len >= 0, "bad arguments");
     ctx->last_launches = 0;
-    if (n_chunks == 0 || max_len == 0) return HMFE_OK;
-    HMFE_REQUIRE(d_src && d_dst && d_descs, "NULL device pointer");
+    if (max_chunks == 0 || max_len == 0) return HMFE_OK;
+    HMFE_REQUIRE(d_src && d_dst && d_descs && d_n_descs, "NULL device pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = (max_len + kGatherTile - 1) / kGatherTile;
-    HMFE_REQUIRE(n_chunks * tiles < (int64_t)INT32_MAX, "gather grid too large");
+    const unsigned grid = (unsigned)std::min<int64_t>(max_chunks * tiles, (int64_t)ctx->sm_count * 16);
     ctx->prof_begin(HMFE_K_GATHER, st);
-    gather_device_kernel<<<(unsigned)(n_chunks * tiles), 256, 0, st>>>(d_src, d_dst, d_descs, tiles);
+    gather_device_kernel<<<grid, 256, 0, st>>>(d_src, d_dst, d_descs, d_n_descs, tiles);
     HMFE_CHECK_CUDA(cudaGetLastError());
     ctx->prof_end(st);
     ctx->last_launches = 1;

@@ -372,7 +372,7 @@ def entire_signal_device(wav, offsets, input_sec=8, sample_rate=16000, butterwor
         sc = _dev_scratch.get(key)
         if sc is None:
             ws = int(_lib.hmfe_logmel_device_workspace_bytes(n))
-            sc = _dev_scratch[key] = {"desc": torch.empty(4 * n + 2, dtype=torch.int64, device=dev),
+            sc = _dev_scratch[key] = {"desc": torch.empty(4 * n + 3, dtype=torch.int64, device=dev),
                                       "gather": torch.empty(n * 40, dtype=torch.uint8, device=dev),
                                       "ws": torch.empty(ws, dtype=torch.uint8, device=dev)}
             if len(_dev_scratch) > 64:
@@ -384,7 +384,9 @@ def entire_signal_device(wav, offsets, input_sec=8, sample_rate=16000, butterwor
         launches += 1
         if pad:
             _lib.check(_lib.hmfe_gather_device(ctx._h, C.c_void_p(signal.data_ptr()), C.c_void_p(dst.data_ptr()),
-                                               C.c_void_p(sc["gather"].data_ptr()), n, L, fe._stream_ptr()), "hmfe_gather_device")
+                                               C.c_void_p(sc["gather"].data_ptr()),
+                                               C.c_void_p(sc["desc"].data_ptr() + 8 * (4 * n + 2)), n, L, fe._stream_ptr()),
+                       "hmfe_gather_device")
             launches += 1
         if out is None or out.numel() < rows_ub * 64:
             out = torch.empty((rows_ub, 64), dtype=torch.float32, device=dev)
@@ -590,30 +592,31 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
                 d_in[i % 2][:n_in].copy_(src, non_blocking=True)
             ev_in[i % 2].record(s_in)
 
-    # Every sub-batch is enqueued without waiting for its OWN trim indices (device-side planner).  Where its rows go in
-    # h_out depends on the row counts of the sub-batches before it, so its copy-out is enqueued after the descriptors of
-    # the PREVIOUS sub-batch have arrived - by then its own kernels are already queued and the GPU never idles.  The
-    # copy moves the sub-batch's upper-bound row count; the surplus rows are overwritten by the next sub-batch's copy
-    # (same stream), and h_out holds the upper bound of the whole batch.
-    if h_out.shape[0] < int(rows_ub.sum()):
-        raise ValueError(f"h_out needs {int(rows_ub.sum())} rows (upper bound: 1 + max(len, L) // 512 per recording)")
+    # Every sub-batch is enqueued without waiting for its own trim indices (device-side planner).  Its copy-out needs
+    # its row count and its position in h_out, so it is enqueued one iteration later, after its descriptors have
+    # arrived - by then the next sub-batch's kernels are already queued and the GPU never idles.
     pending = []
     row_offsets, clip_ids, valid = [np.zeros(1, np.int64)], [], np.zeros(n, dtype=bool)
     base = 0
 
-    def account(j):  # descriptors of sub-batch j -> host offsets; returns its row count
-        a_, b_, res_ = pending[j]
+    def copy_out(j):  # descriptors of sub-batch j -> host offsets, rows -> h_out
+        nonlocal base
+        a_, b_, res_, done_ = pending[j]
         fb = res_.resolve()
+        rows = int(fb.row_offsets[-1])
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done_)
+            h_out[base : base + rows].copy_(fb.features[:rows], non_blocking=True)
+            ev_out[j % 2].record(s_out)
         row_offsets.append(base + fb.row_offsets[1:])
         clip_ids.append(a_ + fb.chunks.clip_ids)
         valid[a_:b_] = fb.chunks.valid
-        return int(fb.row_offsets[-1])
+        base += rows
 
     copy_in(0)
     for i, (a, b) in enumerate(subs):
         if i + 1 < len(subs):
             copy_in(i + 1)
-        ub = int(rows_ub[a:b].sum())
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[i % 2])
             if i >= 2:
@@ -626,14 +629,10 @@ def entire_signal_from_host(h_wav: torch.Tensor, offsets, h_out: torch.Tensor | 
             ev_free[i % 2].record(s_cmp)
             done = torch.cuda.Event()
             done.record(s_cmp)
-        pending.append((a, b, res))
+        pending.append((a, b, res, done))
         if i >= 1:
-            base += account(i - 1)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(done)
-            h_out[base : base + ub].copy_(res.features[:ub], non_blocking=True)
-            ev_out[i % 2].record(s_out)
-    base += account(len(subs) - 1)
+            copy_out(i - 1)
+    copy_out(len(subs) - 1)
     s_out.synchronize()
     s_cmp.synchronize()
     return h_out, np.concatenate(row_offsets), (np.concatenate(clip_ids) if clip_ids else np.zeros(0, np.int64)), valid

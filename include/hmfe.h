@@ -158,16 +158,16 @@ int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmf
  * (src/util.py:248-259: duration test, "too short" -> dropped or padded to input_sec by _zero_padding /
  * _duplicate_padding (src/util.py:504-575), cut at max_sec) evaluated ON THE DEVICE from the trim indices
  * d_start_end[n_clips][2], so that the host does not wait for them.  Writes, for hmfe_logmel_batch_device,
- *   d_desc[4 n + 2] = clip_start[n] | clip_len[n] | frame_off[n + 1] | item_prefix[n + 1]   (int64)
- * (dropped clips get zero rows) and one gather record per clip for hmfe_gather_device (len = 0 when the clip needs no
- * padded copy; padded copy k of the batch goes to element dst_base + k * int(input_sec * sample_rate) of the destination;
+ *   d_desc[4 n + 3] = clip_start[n] | clip_len[n] | frame_off[n + 1] | item_prefix[n + 1] | n_padded   (int64)
+ * (dropped clips get zero rows) and the compact list d_gather[0 .. n_padded) of the padded copies for hmfe_gather_device
+ * (room for n records; padded copy k of the batch goes to element dst_base + k * int(input_sec * sample_rate) of the destination;
  * with `alt` the clip start is encoded as -(offset + 1), the second-buffer convention of hmfe_logmel_batch_views2).
  * item_frames = frames per work item of the log-mel variant (4).  All outputs are caller-provided device memory. */
 int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_clips, const int64_t* d_start_end,
                            int sample_rate, double input_sec, int pad, int pad_zero, double max_sec, int hop, int item_frames,
                            int64_t dst_base, int alt, int64_t* d_desc, hmfe_gather_desc* d_gather, void* stream);
-int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs, int64_t n_chunks,
-                       int max_len, void* stream);
+int hmfe_gather_device(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmfe_gather_desc* d_descs,
+                       const int64_t* d_n_descs, int64_t max_chunks, int max_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Band-pass IIR: replaces scipy.signal.lfilter(b, a, x) in _butter_bandpass_filter

@@ -176,3 +176,32 @@ def test_tensor_core_variant_full_size_and_other_shapes(fft_warps, monkeypatch):
     assert tc.tc_status() == 0
     with pytest.raises(Exception):
         LogMelPlan(f_max=8000, n_mels=128, variant="tc")
+
+
+def test_cuda_output_against_independent_implementations():
+    """The CUDA kernels directly (not through this repository's restatement) against two independent librosa-compatible
+    implementations: torchaudio.transforms.MelSpectrogram (float32 FFT) and transformers.audio_utils (float64, pinned
+    against librosa outputs in its own test-suite)."""
+    import torchaudio
+
+    from heart_murmur_detection_b200.frontend import LogMelPlan
+
+    au = pytest.importorskip("transformers.audio_utils")
+    clips = [golden_signal(n, seed=21 + i) for i, n in enumerate((128000, 90000, 20000, 300000))]
+    tf = torchaudio.transforms.MelSpectrogram(16000, n_fft=1024, hop_length=512, f_min=50.0, f_max=8000.0, n_mels=64, norm="slaney",
+                                              mel_scale="slaney", center=True, pad_mode="constant", power=2.0)
+    fb = au.mel_filter_bank(513, 64, 50.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+    win = au.window_function(1024, "hann", periodic=True)
+    for variant in ("packed", "tc"):
+        plan = LogMelPlan(f_max=8000, variant=variant)
+        P = _run(plan, clips, "power")
+        D = _run(plan, clips, "db")
+        for x, p, d in zip(clips, P, D):
+            St = tf(torch.from_numpy(x)).numpy().T
+            assert p.shape == St.shape
+            assert np.abs(p - St).max() <= POWER_RTOL * np.abs(St).max(), variant
+            Su = au.spectrogram(x, win, frame_length=1024, hop_length=512, fft_length=1024, power=2.0, center=True,
+                                pad_mode="constant", mel_filters=fb, mel_floor=0.0).T
+            assert np.abs(p - Su).max() <= POWER_RTOL * np.abs(Su).max(), variant
+            dbu = au.power_to_db(Su, reference=float(Su.max()), min_value=1e-10, db_range=80.0)
+            assert np.abs(d - dbu).max() <= DB_TOL, variant

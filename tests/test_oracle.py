@@ -264,3 +264,22 @@ def test_resampler_designs_quantified():
     f, Ht = gain["torchaudio"]
     assert -3.0 <= 20 * np.log10(Ht[np.argmin(np.abs(f - 0.913))]) <= -2.5
     assert np.abs(20 * np.log10(Ht[f <= 0.5]) - 20 * np.log10(H[f <= 0.5])).max() <= 0.03
+
+
+def test_known_answers_from_librosa_documentation():
+    """Constants printed in librosa's own docstrings (librosa.hz_to_mel, librosa.mel_to_hz, librosa.mel_frequencies,
+    version 0.10 documentation) - values that do not come from this repository's restatement: the Slaney scale the
+    mel basis is built on (librosa.filters.mel under feature.melspectrogram, src/util.py:484-492) is pinned by them."""
+    assert abs(lr.hz_to_mel(60) - 0.9) <= 1e-12
+    np.testing.assert_allclose(lr.hz_to_mel(np.array([110, 220, 440])), [1.65, 3.3, 6.6], rtol=0, atol=1e-12)
+    assert abs(lr.mel_to_hz(3) - 200.0) <= 1e-9
+    np.testing.assert_allclose(lr.mel_to_hz(np.array([1, 2, 3, 4, 5])), [66.667, 133.333, 200.0, 266.667, 333.333], rtol=0, atol=5e-4)
+    doc = np.array([0.0, 85.317, 170.635, 255.952, 341.269, 426.586, 511.904, 597.221, 682.538, 767.855, 853.173, 938.49,
+                    1024.856, 1119.114, 1222.042, 1334.436, 1457.167, 1591.187, 1737.532, 1897.337, 2071.84, 2262.393,
+                    2470.47, 2697.686, 2945.799, 3216.731, 3512.582, 3835.643, 4188.417, 4573.636, 4994.285, 5453.621,
+                    5955.205, 6502.92, 7101.009, 7754.107, 8467.272, 9246.028, 10096.408, 11025.0])
+    np.testing.assert_allclose(lr.mel_frequencies(40, fmin=0.0, fmax=11025.0), doc, rtol=0, atol=6e-4)  # printed to 3 decimals
+    # power_to_db by its definition in the docstring: 10 * log10(S / ref), floor at max - top_db
+    S = np.array([[1.0, 1e-3], [1e-12, 4.0]], dtype=np.float32)
+    want = np.maximum(10 * np.log10(np.maximum(S, 1e-10) / 4.0), -80.0)
+    np.testing.assert_allclose(lr.power_to_db(S, ref=np.max), want, rtol=0, atol=1e-5)
