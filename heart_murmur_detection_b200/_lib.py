@@ -70,6 +70,10 @@ hmfe_logmel_profile_ms = _sig(
 
 hmfe_ctx_create = _sig("hmfe_ctx_create", C.c_int, C.POINTER(c_voidp))
 hmfe_ctx_destroy = _sig("hmfe_ctx_destroy", None, c_voidp)
+hmfe_ctx_set_workspace = _sig("hmfe_ctx_set_workspace", C.c_int, c_voidp, c_voidp, C.c_size_t)
+hmfe_ctx_reserve = _sig("hmfe_ctx_reserve", C.c_int, c_voidp, C.c_int64)
+hmfe_trim_workspace_bytes = _sig("hmfe_trim_workspace_bytes", C.c_int64, c_voidp, C.c_int64, C.c_int, C.c_int)
+hmfe_iir_workspace_bytes = _sig("hmfe_iir_workspace_bytes", C.c_int64, c_voidp, C.c_int64, C.c_int, C.c_int)
 hmfe_ctx_last_launches = _sig("hmfe_ctx_last_launches", C.c_int, c_voidp)
 hmfe_ctx_set_profile = _sig("hmfe_ctx_set_profile", C.c_int, c_voidp, C.c_int)
 hmfe_ctx_profile_ms = _sig("hmfe_ctx_profile_ms", C.c_int, c_voidp, C.POINTER(C.c_double), C.POINTER(C.c_int))

@@ -31,6 +31,10 @@ int DescRing::acquire(size_t bytes, void** host, void** dev) {
         pending_[s] = false;
     }
     if (bytes > cap_[s]) {
+        if (fixed_) {
+            set_error("descriptor staging of %zu bytes was reserved, this call needs %zu (hmfe_ctx_reserve)", cap_[s], bytes);
+            return HMFE_ERR_INVALID;
+        }
         size_t cap = cap_[s] ? cap_[s] : 4096;
         while (cap < bytes) cap *= 2;
         if (h_[s]) HMFE_CHECK_CUDA(cudaFreeHost(h_[s]));
@@ -44,6 +48,25 @@ int DescRing::acquire(size_t bytes, void** host, void** dev) {
     *host = h_[s];
     *dev = d_[s];
     return s;
+}
+
+int DescRing::reserve(size_t bytes) {
+    for (int s = 0; s < kSlots; ++s) {
+        if (!ev_[s]) HMFE_CHECK_CUDA(cudaEventCreateWithFlags(&ev_[s], cudaEventDisableTiming));
+        if (bytes <= cap_[s]) continue;
+        if (pending_[s]) {
+            HMFE_CHECK_CUDA(cudaEventSynchronize(ev_[s]));
+            pending_[s] = false;
+        }
+        if (h_[s]) HMFE_CHECK_CUDA(cudaFreeHost(h_[s]));
+        if (d_[s]) HMFE_CHECK_CUDA(cudaFree(d_[s]));
+        h_[s] = d_[s] = nullptr;
+        cap_[s] = 0;
+        HMFE_CHECK_CUDA(cudaMallocHost(&h_[s], bytes));
+        HMFE_CHECK_CUDA(cudaMalloc(&d_[s], bytes));
+        cap_[s] = bytes;
+    }
+    return HMFE_OK;
 }
 
 int DescRing::upload(int slot, size_t bytes, cudaStream_t s) {

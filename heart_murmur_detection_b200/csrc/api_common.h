@@ -41,6 +41,8 @@ class DescRing {
     int acquire(size_t bytes, void** host, void** dev);
     int upload(int slot, size_t bytes, cudaStream_t s);  // H2D async of the first `bytes`
     int release(int slot, cudaStream_t s);               // record the reuse event
+    int reserve(size_t bytes);  // allocate every slot up front: later calls needing <= bytes allocate nothing
+    void forbid_growth() { fixed_ = true; }
 
    private:
     void* h_[kSlots] = {};
@@ -49,6 +51,7 @@ class DescRing {
     cudaEvent_t ev_[kSlots] = {};
     bool pending_[kSlots] = {};
     int next_ = 0;
+    bool fixed_ = false;
 };
 
 int device_sm_count();

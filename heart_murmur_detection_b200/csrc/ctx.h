@@ -25,6 +25,7 @@ struct hmfe_ctx {
     hmfe::DescRing ring;
     void* scratch = nullptr;
     size_t scratch_cap = 0;
+    bool scratch_external = false;  // caller-provided workspace (hmfe_ctx_set_workspace): never (re)allocated here
     int sm_count = 148;
     int last_launches = 0;
     // IIR algorithm choice (hmfe_ctx_set_iir_algo) and what the last call used
@@ -61,6 +62,11 @@ struct hmfe_ctx {
     // so kernels still using it have finished)
     int reserve_scratch(size_t bytes) {
         if (bytes <= scratch_cap) return HMFE_OK;
+        if (scratch_external) {
+            hmfe::set_error("caller-provided workspace of %zu bytes is too small: this call needs %zu (query hmfe_*_workspace_bytes)",
+                            scratch_cap, bytes);
+            return HMFE_ERR_INVALID;
+        }
         size_t cap = scratch_cap ? scratch_cap : (size_t)1 << 20;
         while (cap < bytes) cap *= 2;
         if (scratch) HMFE_CHECK_CUDA(cudaFree(scratch));

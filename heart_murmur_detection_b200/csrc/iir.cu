@@ -364,6 +364,9 @@ struct IirOverlap4Batch {
     int align;                    // (address of x / 4) mod 4
 };
 
+#ifndef HMFE_IIR_CONV_DEFAULT
+#define HMFE_IIR_CONV_DEFAULT 0
+#endif
 constexpr int kRing = 4;                  // 32-sample column blocks per tile row
 constexpr int kRow4 = 32 * kRing + 4;     // tile row stride in floats: 16-byte aligned rows, conflict-free LDS.128 by row
 
@@ -372,7 +375,44 @@ struct __align__(16) IirRow4 {
     int lo, hi;      // stream positions [lo, hi) hold clip samples
 };
 
-template <int S, bool BP>
+// float <-> double without the conversion instructions (F2F.F64.F32 / F2F.F32.F64 issue at a fraction of the DFMA
+// rate and sit at both ends of every sample's dependency chain): exponent re-biasing on the integer pipe, which
+// this kernel leaves idle.  Exact for normal numbers; float denormals (|x| < 1.2e-38) and doubles below the float
+// normal range are flushed to (signed) zero, far below the 1e-10 agreement the tests demand.  CONV bit 0: input,
+// bit 1: output (round to nearest even on the 29 dropped mantissa bits, like cvt.rn).
+HMFE_D double f32_to_f64_int(float x) {
+    const unsigned u = __float_as_uint(x);
+    const unsigned a = u & 0x7fffffffu;
+    unsigned hi = (u & 0x80000000u) | ((a >> 3) + 0x38000000u);
+    unsigned lo = u << 29;
+    if (a < 0x00800000u) {
+        hi = u & 0x80000000u;
+        lo = 0u;
+    }
+    return __hiloint2double((int)hi, (int)lo);
+}
+HMFE_D float f64_to_f32_int(double y) {
+    const unsigned hi = (unsigned)__double2hiint(y), lo = (unsigned)__double2loint(y);
+    const unsigned mh = hi & 0x7fffffffu;
+    // round to nearest even at bit 29 of the 63-bit magnitude: add 0x0fffffff + lsb, carry into the high word
+    const unsigned lsb = (lo >> 29) & 1u;
+    const unsigned long long m = (((unsigned long long)mh << 32) | lo) + 0x0fffffffull + lsb;
+    unsigned f = (unsigned)(m >> 29) - (896u << 23);
+    if (mh < (897u << 20)) f = 0u;  // below the float normal range
+    return __uint_as_float(f | (hi & 0x80000000u));
+}
+template <int CONV>
+HMFE_D double to_f64(float x) {
+    if constexpr (CONV & 1) return f32_to_f64_int(x);
+    return (double)x;
+}
+template <int CONV>
+HMFE_D float to_f32(double y) {
+    if constexpr (CONV & 2) return f64_to_f32_int(y);
+    return (float)y;
+}
+
+template <int S, bool BP, int CONV>
 HMFE_D void iir_block32(const IirCoef<S>& cf, float gain, float* row, double (&s1)[S], double (&s2)[S], bool emit,
                         float& body, float (&head)[4]) {
     // 32 consecutive samples of this lane's row: read as 8 float4, filter, write back in place
@@ -382,7 +422,7 @@ HMFE_D void iir_block32(const IirCoef<S>& cf, float gain, float* row, double (&s
         float* e = reinterpret_cast<float*>(&v);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float f = (float)cascade<S, BP, false>(cf, (double)e[c], s1, s2) * gain;
+            const float f = to_f32<CONV>(cascade<S, BP, false>(cf, to_f64<CONV>(e[c]), s1, s2)) * gain;
             e[c] = f;
             if (u == 0)
                 head[c] = f * f;
@@ -414,7 +454,7 @@ HMFE_D void cp_async_wait() {
 // so the global-load latency of a block is covered by the filtering of the kRing - 1 blocks before it.
 // The folded band-pass gain is applied to the float32 output (FP32 pipe) instead of the float64 input.
 // Measured on B200 (c2, 1.78 G samples): ring 4 x 3 CTAs/SM 3.55 ms, 3 x 3 3.58, 3 x 4 3.72, 2 x 4 3.73, 2 x 5 3.90.
-template <int S, bool BP, bool POWER>
+template <int S, bool BP, bool POWER, int CONV>
 __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const IirOverlap4Batch b, const IirCoef<S> cf) {
     extern __shared__ __align__(16) unsigned char iir_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,7 +557,7 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
         const int rem = hi_self - tb;
         if (rem >= 32) {
             body = 0.0f;
-            iir_block32<S, BP>(cf, gain, &tile[lane][col0], s1, s2, emit, body, head);
+            iir_block32<S, BP, CONV>(cf, gain, &tile[lane][col0], s1, s2, emit, body, head);
             if (POWER && emit) {
                 if (group_start) {
 #pragma unroll
@@ -532,7 +572,7 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
             if (POWER && emit && group_start) q[0] = q[1] = q[2] = q[3] = 0.0f;
 #pragma unroll 1
             for (int k = 0; k < rem; ++k) {
-                const float f = (float)cascade<S, BP, false>(cf, (double)tile[lane][col0 + k], s1, s2) * gain;
+                const float f = to_f32<CONV>(cascade<S, BP, false>(cf, to_f64<CONV>(tile[lane][col0 + k]), s1, s2)) * gain;
                 tile[lane][col0 + k] = f;
                 if (POWER && emit) {
                     if (group_start && k < 4) {  // (no dynamic register indexing)
@@ -806,14 +846,34 @@ static int run_iir_overlap(hmfe_ctx* ctx, const IirOverlapBatch& b, const double
 
 constexpr size_t kOverlap4Smem = (size_t)kIirWarps * 32 * kRow4 * sizeof(float) + (size_t)kIirWarps * 32 * sizeof(IirRow4);
 
-template <int S, bool BP, bool POWER>
-static int launch_overlap4_k(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
-    auto kern = iir_overlap4_kernel<S, BP, POWER>;
+template <int S, bool BP, bool POWER, int CONV>
+static int launch_overlap4_c(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
+    auto kern = iir_overlap4_kernel<S, BP, POWER, CONV>;
     HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOverlap4Smem));
     const unsigned grid = (unsigned)((b.n_chunks + kIirWarps * 32 - 1) / (kIirWarps * 32));
     kern<<<grid, kIirWarps * 32, kOverlap4Smem, st>>>(b, cf);
     HMFE_CHECK_CUDA(cudaGetLastError());
     return HMFE_OK;
+}
+
+// float <-> double conversions of the one-pass kernel: 0 = conversion instructions, 1 = integer re-biasing on the way
+// in, 3 = both ways (HMFE_IIR_CONV overrides; measured on B200)
+static int iir_conv_mode() {
+    static const int mode = [] {
+        const char* e = getenv("HMFE_IIR_CONV");
+        const int m = e ? atoi(e) : HMFE_IIR_CONV_DEFAULT;
+        return (m == 1 || m == 3) ? m : 0;
+    }();
+    return mode;
+}
+
+template <int S, bool BP, bool POWER>
+static int launch_overlap4_k(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
+    switch (iir_conv_mode()) {
+        case 1: return launch_overlap4_c<S, BP, POWER, 1>(b, cf, st);
+        case 3: return launch_overlap4_c<S, BP, POWER, 3>(b, cf, st);
+        default: return launch_overlap4_c<S, BP, POWER, 0>(b, cf, st);
+    }
 }
 
 template <int S>

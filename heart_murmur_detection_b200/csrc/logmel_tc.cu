@@ -372,7 +372,11 @@ HMFE_TC_D void mma_role(const LogmelBatch& b, const TcSmem& sm, uint32_t regions
         const uint32_t lo0 = (regions_addr + w * kRegionBytes) >> 4;
         const uint32_t d = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
         if (elect_one()) {
-#pragma unroll
+            // a ROLLED loop on purpose: this warp runs once per tile, in between the FFT warps stream ~50 KB of
+            // unrolled code per item through the instruction cache; with the 32 instructions unrolled (144
+            // instructions, 18 cache lines) this warp spent 38 % of its time waiting for instruction fetches
+            // and fell behind (ncu: stall_no_inst; the FFT warps then wait for their tile to be consumed)
+#pragma unroll 1
             for (int k = 0; k < 32; ++k)
                 mma_ts_f16(d, 8 * k, desc_hi | (uint64_t)(lo0 + (k >> 2) * 64 + (k & 3) * 2), idesc, k > 0);
             *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot) = w;

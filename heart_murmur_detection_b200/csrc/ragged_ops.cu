@@ -468,9 +468,58 @@ int hmfe_ctx_create(hmfe_ctx** ctx) {
     return HMFE_OK;
 }
 
+// ---- caller-provided workspace ("never allocate, caller workspace")
+int hmfe_ctx_set_workspace(hmfe_ctx* ctx, void* d_workspace, size_t bytes) {
+    HMFE_REQUIRE(ctx, "NULL ctx");
+    HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    if (ctx->scratch && !ctx->scratch_external) HMFE_CHECK_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = d_workspace;
+    ctx->scratch_cap = d_workspace ? bytes : 0;
+    ctx->scratch_external = d_workspace != nullptr;
+    return HMFE_OK;
+}
+
+int hmfe_ctx_reserve(hmfe_ctx* ctx, int64_t max_clips) {
+    HMFE_REQUIRE(ctx && max_clips >= 0, "bad arguments");
+    // the largest per-call descriptor block of any ctx stage: the IIR stages upload 4 int64 arrays of n_clips + 1
+    // entries plus the (2S)^2 transition matrix of the exact scan (S <= 8); gather / crop records are 40 / 24 bytes
+    const size_t bytes = (size_t)(max_clips + 1) * 48 + 16 * 16 * sizeof(double) + 4096;
+    int rc = ctx->ring.reserve(bytes);
+    if (rc != HMFE_OK) return rc;
+    ctx->ring.forbid_growth();
+    return HMFE_OK;
+}
+
+int64_t hmfe_trim_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int frame_length, int hop_length) {
+    if (!h_offsets || n_clips < 0 || frame_length < 2 || hop_length < 1) return -1;
+    const bool by_hop = frame_length == 2 * hop_length;
+    int64_t units = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        units += by_hop ? (n + hop_length - 1) / hop_length : hmfe_trim_num_frames(n, frame_length, hop_length);
+    }
+    return std::max<int64_t>(1, units) * (int64_t)sizeof(float);
+}
+
+int64_t hmfe_iir_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int n_sections, int hop_length) {
+    if (!h_offsets || n_clips < 0 || n_sections < 1 || n_sections > 8) return -1;
+    // upper bound over the algorithms hmfe_iir_sos_batch / hmfe_iir_sos_trim_batch may choose: hop energies of the fused
+    // trim (8 floats per hop group, one extra group per clip for the 16-byte alignment shift) or the carry vectors of the
+    // exact scan (two 2S-vectors of doubles per chunk, chunks of at least 512 samples)
+    int64_t groups = 0, chunks = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t n = h_offsets[i + 1] - h_offsets[i];
+        if (hop_length > 0) groups += (n + 3 + hop_length - 1) / hop_length + 1;
+        chunks += (n + 3 + 511) / 512 + 1;
+    }
+    const int64_t a = std::max<int64_t>(1, groups) * 8 * (int64_t)sizeof(float);
+    const int64_t b = 2 * chunks * 2 * n_sections * (int64_t)sizeof(double);
+    return std::max(a, b);
+}
+
 void hmfe_ctx_destroy(hmfe_ctx* ctx) {
     if (!ctx) return;
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch && !ctx->scratch_external) cudaFree(ctx->scratch);
     for (auto& r : ctx->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);

@@ -209,6 +209,17 @@ class Context:
     def set_profile(self, enable: bool):
         check(_lib.hmfe_ctx_set_profile(self._h, int(bool(enable))))
 
+    def use_workspace(self, workspace: torch.Tensor | None, max_clips: int | None = None):
+        """Caller-provided memory (include/hmfe.h): ``workspace`` (uint8 CUDA tensor, kept alive here) becomes the
+        scratch of every stage run on this context; with ``max_clips`` the descriptor staging is reserved once and
+        no later call allocates.  Sizes: ``trim_workspace_bytes`` / ``iir_workspace_bytes``."""
+        self._ws = workspace
+        ptr, n = (C.c_void_p(workspace.data_ptr()), workspace.numel()) if workspace is not None else (C.c_void_p(), 0)
+        with torch.cuda.device(self.device):
+            check(_lib.hmfe_ctx_set_workspace(self._h, ptr, n), "hmfe_ctx_set_workspace")
+            if max_clips is not None:
+                check(_lib.hmfe_ctx_reserve(self._h, int(max_clips)), "hmfe_ctx_reserve")
+
     def set_iir_algo(self, algo: str = "auto"):
         """"auto" | "scan" (exact chunked scan) | "overlap" (one pass with warm-up) - include/hmfe.h."""
         check(_lib.hmfe_ctx_set_iir_algo(self._h, _lib.IIR_ALGOS[algo]), "hmfe_ctx_set_iir_algo")
@@ -229,6 +240,16 @@ class Context:
         ms, cnt = (C.c_double * n)(), (C.c_int * n)()
         check(_lib.hmfe_ctx_profile_ms(self._h, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_NAMES)}
+
+
+def trim_workspace_bytes(offsets, frame_length=1600, hop_length=800) -> int:
+    o = _as_offsets(offsets)
+    return int(_lib.hmfe_trim_workspace_bytes(o.ctypes.data_as(C.c_void_p), o.size - 1, int(frame_length), int(hop_length)))
+
+
+def iir_workspace_bytes(offsets, n_sections=5, hop_length=800) -> int:
+    o = _as_offsets(offsets)
+    return int(_lib.hmfe_iir_workspace_bytes(o.ctypes.data_as(C.c_void_p), o.size - 1, int(n_sections), int(hop_length)))
 
 
 _ctxs: dict = {}

@@ -17,6 +17,7 @@
 #ifndef HMFE_H_
 #define HMFE_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -103,6 +104,22 @@ int hmfe_logmel_profile_ms(hmfe_logmel_plan* plan, double* power_ms, double* fin
 typedef struct hmfe_ctx hmfe_ctx;
 int hmfe_ctx_create(hmfe_ctx** ctx);
 void hmfe_ctx_destroy(hmfe_ctx* ctx);
+/* Caller-provided memory (the "never allocate" contract): by default a context grows its device scratch and its
+ * pinned / device descriptor staging on demand (convenient, but a call may then allocate and, when it has to grow,
+ * synchronise).  With
+ *   hmfe_ctx_set_workspace(ctx, d_ws, bytes)   the stages use the caller's device workspace as scratch (256-byte
+ *                                               aligned; NULL returns to the internal scratch) and fail with
+ *                                               HMFE_ERR_INVALID, naming the size they need, when it is too small;
+ *   hmfe_ctx_reserve(ctx, max_clips)           descriptor staging for batches of up to max_clips clips is allocated
+ *                                               now, once; later calls allocate nothing and larger batches fail.
+ * Sizes: hmfe_trim_workspace_bytes (hmfe_trim_batch), hmfe_iir_workspace_bytes (hmfe_iir_sos_batch and
+ * hmfe_iir_sos_trim_batch: an upper bound over the algorithms they may pick; hop_length = 0 without the trim),
+ * hmfe_sosfiltfilt_workspace_bytes, hmfe_hear_workspace_bytes, hmfe_logmel_device_workspace_bytes.  The gather,
+ * planner and spectrogram stages need no scratch. */
+int hmfe_ctx_set_workspace(hmfe_ctx* ctx, void* d_workspace, size_t bytes);
+int hmfe_ctx_reserve(hmfe_ctx* ctx, int64_t max_clips);
+int64_t hmfe_trim_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int frame_length, int hop_length);
+int64_t hmfe_iir_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int n_sections, int hop_length);
 /* number of kernel launches issued by the last call made on this context */
 int hmfe_ctx_last_launches(const hmfe_ctx* ctx);
 /* Measurement hook: with profiling enabled every kernel a ctx stage launches is bracketed by

@@ -640,3 +640,35 @@ def test_trim_near_the_threshold_stress():
     print(f"trim knife edge: {diff.size} of {n_clips} clips differ from the numpy restatement")
     assert diff.size <= n_clips // 500
     assert np.all(np.abs(se[diff, 1] - ref[diff, 1]) <= hop * blocks)
+
+
+@pytest.mark.gpu
+def test_caller_provided_workspace_contract():
+    """hmfe_ctx_set_workspace / hmfe_ctx_reserve (never allocate, caller workspace): with a workspace of the
+    queried size the band-pass + trim and the stand-alone trim give the results of the allocating context; a
+    workspace that is too small is refused with the size that is needed, and so is a batch beyond the reservation."""
+    from heart_murmur_detection_b200 import frontend as fe
+    from heart_murmur_detection_b200._lib import HmfeError
+
+    clips = [golden_signal(n, seed=60 + i) for i, n in enumerate((90000, 20000, 128000, 300000, 513, 47999))]
+    wav, off = _batch(clips)
+    sos = fe.butter_bandpass_sos(200, 1800, 16000, order=5)
+    y0, se0 = fe.iir_sos_trim(wav, off, sos)
+    t0 = fe.trim_indices(wav, off)
+    ctx = fe.Context()
+    need = max(fe.iir_workspace_bytes(off, 5, 800), fe.trim_workspace_bytes(off, 1600, 800))
+    ctx.use_workspace(torch.empty(need, dtype=torch.uint8, device="cuda"), max_clips=len(clips))
+    for algo in ("overlap", "scan"):
+        ctx.set_iir_algo(algo)
+        y1, se1 = fe.iir_sos_trim(wav, off, sos, ctx=ctx)
+        assert torch.equal(se1, se0)
+        assert (y1 - y0).abs().max().item() <= 1e-6
+    assert torch.equal(fe.trim_indices(wav, off, ctx=ctx), t0)
+    small = fe.Context()
+    small.use_workspace(torch.empty(256, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(HmfeError, match="too small"):
+        fe.iir_sos_trim(wav, off, sos, ctx=small)
+    tight = fe.Context()
+    tight.use_workspace(torch.empty(need, dtype=torch.uint8, device="cuda"), max_clips=2)
+    with pytest.raises(HmfeError, match="reserved"):
+        fe.trim_indices(wav, off, ctx=tight)
