@@ -6,8 +6,11 @@
 //   warps 0-3    "epilogue": tensor-memory lane quarter q = warp; read the accumulators (tcgen05.ld), add the four
 //                partial products, store the mel rows, clip max / min
 //   warps 4..    NF "FFT" warps, each autonomous as in logmel.cu: claim 4-frame items, window + 1024-point FFT of two
-//                packed transforms, power -> bf16 (hi, lo) pairs -> the warp's B tile in shared memory
-//   warp 15      "MMA": one thread issues the 32 tcgen05.mma (K = 16 each) of every ready tile and commits them
+//                packed transforms, power -> bf16 (hi, lo) pairs -> the warp's B tile in shared memory, then one
+//                elected lane issues the 32 tcgen05.mma (K = 16 each) of the tile and commits them.  (A dedicated
+//                MMA warp was measured first: ~15 dependent instructions per MMA at single-warp latency = ~2 600
+//                cycles per tile, the whole kernel ran at the pace of that one warp, 0.60 ms on c1; issued from the
+//                FFT warps the same instructions hide behind ten other warps.)
 // Frames reach shared memory by 1-D bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) issued one item ahead and
 // completed on an mbarrier; no thread waits for global memory.
 //
@@ -40,11 +43,10 @@ constexpr int kTcThreads = 512;
 constexpr int kRegionBytes = 19456;                        // per FFT warp: [B tile 8192 | frame staging 11264]
 constexpr int kPowerBytes = 8192;                          //   the 16 896-byte FFT exchange tile overlays both
 constexpr int kTmemCols = 512, kTmemD = 256, kDCols = 16;  // A: columns 0-255, accumulator of FFT warp w: 256 + 16 w
-constexpr int kMmaWarp = 15;
 static_assert(32 * kXStride * 16 <= kRegionBytes, "exchange tile must fit its region");
 
 enum : uint32_t {
-    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrMmaSpin = 16u, kErrTmemBase = 32u,
+    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrTmemBase = 32u,
 };
 
 struct __align__(16) TcMeta {
@@ -70,11 +72,11 @@ struct TcSmem {  // pointers into the dynamic shared memory of the CTA
     // per FFT warp: full (its MMAs are complete: the B tile may be overwritten), dfree (all four epilogue warps have
     // read its accumulator and meta record), raw (its frame copy has landed)
     uint64_t *full, *dfree, *raw;
-    // two in-order rings replace polling of per-warp barriers (an mbarrier test costs ~150 cycles: sweeping 11 of
-    // them took longer than an item): FFT warps append their index to the "ready" ring, the MMA warp issues the
-    // tiles in that order and appends them to the "done" ring, whose barriers the tensor core completes in order
-    uint64_t *ready_seq, *done_seq;
-    uint32_t *ready_who, *done_who;
+    // an in-order ring replaces polling of per-warp barriers (an mbarrier test costs ~150 cycles: sweeping 11 of
+    // them took longer than an item): an FFT warp appends its index to the "done" ring when it issues the MMAs of
+    // a tile and commits them to the ring slot's barrier; the epilogue warps consume the slots in ring order
+    uint64_t* done_seq;
+    uint32_t* done_who;
     TcMeta* meta;
     uint32_t *tmem, *done, *tail;
 };
@@ -91,12 +93,10 @@ HMFE_TC_D TcSmem carve(uint8_t* base) {
     s.full = reinterpret_cast<uint64_t*>(p);
     s.dfree = s.full + NF;
     s.raw = s.dfree + NF;
-    s.ready_seq = s.raw + NF;
-    s.done_seq = s.ready_seq + kRing;
-    p += (3 * NF + 2 * kRing) * sizeof(uint64_t);
-    s.ready_who = reinterpret_cast<uint32_t*>(p);
-    s.done_who = s.ready_who + kRing;
-    p += 2 * kRing * sizeof(uint32_t);
+    s.done_seq = s.raw + NF;
+    p += (3 * NF + kRing) * sizeof(uint64_t);
+    s.done_who = reinterpret_cast<uint32_t*>(p);
+    p += kRing * sizeof(uint32_t);
     p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
     s.meta = reinterpret_cast<TcMeta*>(p);
     p += NF * sizeof(TcMeta);
@@ -107,37 +107,25 @@ HMFE_TC_D TcSmem carve(uint8_t* base) {
 }
 template <int NF>
 constexpr size_t tc_smem_bytes() {
-    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + (3 * NF + 2 * kRing) * 8 +
-           2 * kRing * 4 + 16 + NF * sizeof(TcMeta) + 16;
+    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + (3 * NF + kRing) * 8 +
+           kRing * 4 + 16 + NF * sizeof(TcMeta) + 16;
 }
 
-// Frame span of an item in its clip, and where it sits in the staging buffer.
-struct Span {
-    const float* src;  // 16-byte aligned global address
-    uint32_t bytes;    // multiple of 16 (0: nothing to copy)
-    int soff;          // staging index of clip sample i is i + soff
-    bool interior;     // all four frames exist and none needs zero padding
+// What an FFT warp keeps about an item between the start of its frame copy and the hand-over of its power tile.
+// The staging buffer holds the span of the item's four frames, clip positions [P0, P0 + 3 hop + 1024) with
+// P0 = f0 hop - 512, from staging index `a`; positions outside the clip (centre padding, frames beyond the last
+// one) are ZERO there: one fetch path for interior and edge items (three unrolled paths tripled the kernel's code:
+// the compiler cloned the whole item loop per path, 15 800 instructions, and the warps starved on instruction
+// fetches), and no NaN bit pattern of stale shared memory can reach a transform that packs an existing frame.
+struct Prep {
+    float* out;     // first output row of the item
+    int clip;
+    int nvalid;     // frames of the item that exist (1..4); 0 = no item
+    int a;          // staging index of span position 0 (0..3: keeps the bulk copy 16-byte aligned on both sides)
+    int zlo, zhi;   // span positions [0, zlo) and [zhi, span length) lie outside the clip
 };
-HMFE_TC_D Span item_span(const ItemCtx& c, int hop) {
-    Span s;
-    s.src = c.x;
-    s.bytes = 0;
-    s.soff = 0;
-    s.interior = false;
-    if (!c.valid) return s;
-    const int last_frame = min(c.f0 + 3, c.T - 1);
-    const int first = max(0, c.f0 * hop - kNfft / 2);
-    const int end = min(c.nsamp, last_frame * hop + kNfft / 2);
-    if (end > first) {
-        const float* g = c.x + first;
-        const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
-        s.src = g - skip;
-        s.bytes = (uint32_t)(((end - first + skip) * 4 + 15) & ~15);
-        s.soff = skip - first;
-    }
-    s.interior = c.f0 + 3 < c.T && c.f0 * hop - kNfft / 2 >= 0 && (c.f0 + 3) * hop + kNfft / 2 <= c.nsamp;
-    return s;
-}
+constexpr int kStageFloats = 3 + (3 * 512 + kNfft) + 3 + 2;  // 2568: offset a, span at hop 512, round-up of the copy
+static_assert(kStageFloats * 4 <= kRegionBytes - kPowerBytes, "staging area too small");
 
 // bf16 (hi, lo) split of eight powers -> one 16-byte chunk each
 HMFE_TC_D void split8(const float (&p)[8], uint4& hi, uint4& lo) {
@@ -163,10 +151,15 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
     constexpr int FR = 4;
     uint8_t* region = sm.regions + w * kRegionBytes;
     xelem<V>* tile = reinterpret_cast<xelem<V>*>(region);
-    const float* stage = reinterpret_cast<const float*>(region + kPowerBytes);
+    float* stage = reinterpret_cast<float*>(region + kPowerBytes);
     const uint32_t tile_addr = smem_u32(region), stage_addr = tile_addr + kPowerBytes;
     const uint32_t bar_full = smem_u32(sm.full + w), bar_free = smem_u32(sm.dfree + w), bar_raw = smem_u32(sm.raw + w);
     const int hop = HOP512 ? 512 : b.hop;
+    const int span_len = 3 * hop + kNfft;
+    constexpr uint64_t desc_hi = smem_desc(0, 0, 1024, kSwizzle128B);
+    constexpr uint32_t idesc = idesc_bf16_f32(128, kDCols);
+    const uint32_t desc_lo = tile_addr >> 4;
+    const uint32_t d_tmem = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
 
     constexpr int kItemBlock = 8;
     const int64_t it_end = item_count(b);
@@ -183,34 +176,63 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
         blk_end = nb + kItemBlock;
         return nb;
     };
-    auto issue_raw = [&](const Span& s) {  // lane 0
-        if (s.bytes) {
-            mbar_expect_tx(bar_raw, s.bytes);
-            bulk_g2s(stage_addr, s.src, s.bytes, bar_raw);
-        } else {
-            mbar_arrive(bar_raw);
+    // a wait that gave up (protocol error) is reported once; the warp then stops waiting so that the kernel ends
+    bool alive = true;
+    auto wait = [&](uint32_t bar, uint32_t parity, uint32_t err) {
+        if (alive && !mbar_wait(bar, parity)) {
+            alive = false;
+            if (lane == 0) atomicOr(b.status, err);
         }
     };
     int64_t clip_cursor = -1;
+    // locate the item, start the bulk copy of its frame span into the staging buffer (lane 0)
+    auto prepare = [&](int64_t item) -> Prep {
+        const ItemCtx c = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
+        Prep p;
+        p.out = c.o + (int64_t)c.f0 * n_mels;
+        p.clip = (int)c.clip;
+        p.nvalid = c.valid ? min(4, c.T - c.f0) : 0;
+        p.a = 0;
+        p.zlo = span_len;
+        p.zhi = span_len;
+        if (!c.valid) return p;
+        const int P0 = c.f0 * hop - kNfft / 2;
+        const int first = max(0, P0), end = min(c.nsamp, P0 + span_len);
+        if (end > first) {
+            const float* g = c.x + first;
+            const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
+            const int d0 = first - P0 - skip;  // span position of the first copied sample (>= -3)
+            p.a = (-d0) & 3;
+            p.zlo = first - P0;
+            p.zhi = end - P0;
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(((end - first + skip) * 4 + 15) & ~15);
+                mbar_expect_tx(bar_raw, bytes);
+                bulk_g2s(stage_addr + 4u * (uint32_t)(p.a + d0), g - skip, bytes, bar_raw);
+            }
+        } else if (lane == 0) {
+            mbar_arrive(bar_raw);
+        }
+        return p;
+    };
+
     if (b.stagger_ns > 0) __nanosleep((unsigned)(w * b.stagger_ns));
     int64_t item = claim();
     blk_end = item + kItemBlock;
-    ItemCtx cur = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
-    Span span = item_span(cur, hop);
-    if (lane == 0 && item < it_end) issue_raw(span);
+    Prep cur = prepare(item);
     uint32_t n_done = 0;
-    bool ok = true;
 
-    while (item < it_end && ok) {
-        if (!mbar_wait(bar_raw, n_done & 1)) {
-            if (lane == 0) atomicOr(b.status, kErrRawWait);
-            ok = false;
-            break;
+    while (item < it_end) {
+        wait(bar_raw, n_done & 1, kErrRawWait);
+        if (cur.zlo > 0 || cur.zhi < span_len) {  // edge item: zeros outside the clip (after the copy, which rounds outwards)
+            for (int j = lane; j < cur.zlo; j += 32) stage[cur.a + j] = 0.0f;
+            for (int j = cur.zhi + lane; j < span_len; j += 32) stage[cur.a + j] = 0.0f;
+            __syncwarp();
         }
         V re[32], im[32];
         {
-            const float* sp = stage + span.soff + cur.f0 * hop - kNfft / 2 + lane;  // sample `lane` of frame f0
-            if (HOP512 && span.interior) {
+            const float* sp = stage + cur.a + lane;  // sample `lane` of the item's first frame
+            if (HOP512) {
                 // 50 % overlap: frame j = half-frames (j, j + 1) of the span, every staged sample is read once
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
@@ -223,7 +245,7 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
                     re[brev(m + 16, 5)] = vmuls(V{h5[1], h5[3]}, w1);
                     im[brev(m + 16, 5)] = vmuls(V{h5[2], h5[4]}, w1);
                 }
-            } else if (span.interior) {
+            } else {
 #pragma unroll
                 for (int n2 = 0; n2 < 32; ++n2) {
                     const float wv = sm.win[lane + 32 * n2];
@@ -231,25 +253,11 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
                     re[brev(n2, 5)] = vmuls(V{q[0], q[2 * hop]}, wv);
                     im[brev(n2, 5)] = vmuls(V{q[hop], q[3 * hop]}, wv);
                 }
-            } else {
-#pragma unroll
-                for (int n2 = 0; n2 < 32; ++n2) {
-                    const float wv = sm.win[lane + 32 * n2];
-                    float x[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = (cur.f0 + j) * hop - kNfft / 2 + lane + 32 * n2;
-                        x[j] = (cur.f0 + j < cur.T && i >= 0 && i < cur.nsamp) ? stage[i + span.soff] : 0.0f;
-                    }
-                    re[brev(n2, 5)] = vmuls(V{x[0], x[2]}, wv);
-                    im[brev(n2, 5)] = vmuls(V{x[1], x[3]}, wv);
-                }
             }
         }
         __syncwarp();
         int64_t nitem = item;
-        ItemCtx nxt = cur;
-        Span nspan = span;
+        Prep nxt = cur;
         // both 32-point passes run the same unrolled butterfly code (one copy in the instruction cache)
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
@@ -257,22 +265,15 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
             if (pass == 0) {
                 apply_twiddle<V>(lane, sm.tw, re, im);
                 // the tensor core must be done with the previous B tile before the exchange overwrites it
-                if (n_done > 0 && !mbar_wait(bar_full, (n_done - 1) & 1)) {
-                    if (lane == 0) atomicOr(b.status, kErrFullWait);
-                    ok = false;
-                }
+                wait(bar_full, n_done & 1, kErrFullWait);  // completion n_done (completion 0 is the arrival at start-up)
                 exchange_store<V>(lane, tile, re, im);
                 __syncwarp();
                 exchange_load<V>(lane, tile, re, im);
                 __syncwarp();
                 // the staging area is free again: claim the next item and start the copy of its frames
                 nitem = next_item(item);
-                nxt = locate_item<FR>(b, n_mels, nitem, it_end, clip_cursor);
-                nspan = item_span(nxt, hop);
-                if (lane == 0 && nitem < it_end) {
-                    fence_proxy_async();
-                    issue_raw(nspan);
-                }
+                fence_proxy_async();
+                nxt = prepare(nitem);
             }
         }
         {   // separation of the packed frames, power, bf16 (hi, lo) split, B tile rows
@@ -307,87 +308,42 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
             }
         }
         // the epilogue must have consumed the previous item's accumulator and meta record
-        if (n_done > 0 && !mbar_wait(bar_free, (n_done - 1) & 1)) {
-            if (lane == 0) atomicOr(b.status, kErrFreeWait);
-            ok = false;
-        }
-        fence_proxy_async();
+        wait(bar_free, n_done & 1, kErrFreeWait);
+        fence_proxy_async();  // the B tile (generic-proxy stores of all lanes) becomes visible to the tensor core
         __syncwarp();
-        if (lane == 0) {
+        tc_fence_after();     // after the epilogue's tcgen05.ld of this accumulator (its mbarrier arrive was observed)
+        if (elect_one()) {
             TcMeta m;
-            m.out = cur.o + (int64_t)cur.f0 * n_mels;
+            m.out = cur.out;
             m.clip = cur.clip;
-            m.nvalid = min(4, cur.T - cur.f0);
+            m.nvalid = cur.nvalid;
             m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
             sm.meta[w] = m;
             const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
-            sm.ready_who[slot] = (uint32_t)w;
-            mbar_arrive(smem_u32(sm.ready_seq + slot));  // release: the tile, the meta record and the ring entry
+            sm.done_who[slot] = (uint32_t)w;
+            __threadfence_block();  // meta record and ring entry before the barrier the commits complete
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                mma_ts_f16(d_tmem, 8 * k, desc_hi | (uint64_t)(desc_lo + (k >> 2) * 64 + (k & 3) * 2), idesc, k > 0);
+            mma_commit(smem_u32(sm.done_seq + slot));  // -> epilogue warps, in ring order
+            mma_commit(bar_full);                      // -> this warp: its B tile may be overwritten
         }
+        __syncwarp();
         ++n_done;
         item = nitem;
         cur = nxt;
-        span = nspan;
     }
     // all of this warp's accumulators have been produced before it reports completion
-    if (n_done > 0 && ok) mbar_wait(bar_full, (n_done - 1) & 1);
+    wait(bar_full, n_done & 1, kErrFullWait);
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();
-        if (atomicAdd(sm.done, 1u) == (uint32_t)NF - 1) {  // the last FFT warp closes the ready ring
+        if (atomicAdd(sm.done, 1u) == (uint32_t)NF - 1) {  // the last FFT warp closes the ring
             const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
-            sm.ready_who[slot] = kSentinel;
-            mbar_arrive(smem_u32(sm.ready_seq + slot));
+            sm.done_who[slot] = kSentinel;
+            mbar_arrive(smem_u32(sm.done_seq + slot));
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------ MMA warp
-// The whole warp runs this loop with warp-uniform values (loop counters, kernel parameters, shared-memory window
-// base, tensor-memory base 0): the descriptors and tensor-memory addresses then live in uniform registers and every
-// tcgen05.mma is ONE issue slot of the elected lane.  (With a single active lane and operands in vector registers
-// the compiler wraps every instruction in an elect / broadcast loop: 12 instructions per MMA, measured 3x slower
-// than the FP32 kernel because this warp could not keep up with the FFT warps.)
-template <int NF>
-HMFE_TC_D void mma_role(const LogmelBatch& b, const TcSmem& sm, uint32_t regions_addr) {
-    constexpr uint64_t desc_hi = smem_desc(0, 0, 1024, kSwizzle128B);
-    constexpr uint32_t idesc = idesc_bf16_f32(128, kDCols);
-    uint32_t parity = 0, started = 0;  // bit w: parity of the number of tiles of FFT warp w issued so far / any issued
-    const uint32_t ready_seq = smem_u32(sm.ready_seq), done_seq = smem_u32(sm.done_seq);
-    for (uint32_t seq = 0; seq < (1u << 30); ++seq) {
-        const uint32_t slot = seq % kRing, ring_par = (seq / kRing) & 1u;
-        if (!mbar_wait(ready_seq + 8u * slot, ring_par)) break;
-        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sm.ready_who + slot);
-        if (w == kSentinel) {  // every FFT warp has finished: pass the sentinel on to the epilogue warps
-            if (elect_one()) {
-                *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot) = kSentinel;
-                mbar_arrive(done_seq + 8u * slot);
-            }
-            __syncwarp();
-            return;
-        }
-        // the accumulator of this warp's previous item must have been read
-        if (((started >> w) & 1u) && !mbar_wait(smem_u32(sm.dfree + w), ((parity >> w) & 1u) ^ 1u)) break;
-        tc_fence_after();
-        const uint32_t lo0 = (regions_addr + w * kRegionBytes) >> 4;
-        const uint32_t d = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
-        if (elect_one()) {
-            // a ROLLED loop on purpose: this warp runs once per tile, in between the FFT warps stream ~50 KB of
-            // unrolled code per item through the instruction cache; with the 32 instructions unrolled (144
-            // instructions, 18 cache lines) this warp spent 38 % of its time waiting for instruction fetches
-            // and fell behind (ncu: stall_no_inst; the FFT warps then wait for their tile to be consumed)
-#pragma unroll 1
-            for (int k = 0; k < 32; ++k)
-                mma_ts_f16(d, 8 * k, desc_hi | (uint64_t)(lo0 + (k >> 2) * 64 + (k & 3) * 2), idesc, k > 0);
-            *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot) = w;
-            mma_commit(done_seq + 8u * slot);        // -> epilogue warps, in issue order
-            mma_commit(smem_u32(sm.full + w));       // -> the FFT warp: its B tile is free
-        }
-        __syncwarp();
-        parity ^= 1u << w;
-        started |= 1u << w;
-    }
-    if ((threadIdx.x & 31) == 0) atomicOr(b.status, kErrMmaSpin);
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue warps
@@ -461,9 +417,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBa
             mbar_init(smem_u32(sm.full + w), 1);
             mbar_init(smem_u32(sm.dfree + w), 4);
             mbar_init(smem_u32(sm.raw + w), 1);
+            // phase 0 of "B tile free" and "accumulator free" completes here: the first item of a warp waits like any other
+            mbar_arrive(smem_u32(sm.full + w));
+            for (int q = 0; q < 4; ++q) mbar_arrive(smem_u32(sm.dfree + w));
         }
         for (int i = 0; i < kRing; ++i) {
-            mbar_init(smem_u32(sm.ready_seq + i), 1);
             mbar_init(smem_u32(sm.done_seq + i), 1);
         }
         *sm.done = 0;
@@ -498,14 +456,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBa
         } else {
             if (warp < 12) setmaxnreg_inc<216>(); else setmaxnreg_dec<40>();
         }
-        if (warp - 4 < NF) {
-            fft_role<NF, HOP512>(b, sm, warp - 4, lane, n_mels);
-        } else if (warp == kMmaWarp) {
-            if (tmem != 0) {  // cannot happen while the CTA owns all 512 columns; the MMA role assumes base 0
-                if (lane == 0) atomicOr(b.status, kErrTmemBase);
-            } else {
-                mma_role<NF>(b, sm, (raw_addr + 1023u) & ~1023u);
+        if (tmem != 0) {  // cannot happen while the CTA owns all 512 columns; the roles assume base 0
+            if (threadIdx.x == 128) {  // report, and close the ring so that the epilogue warps return
+                atomicOr(b.status, kErrTmemBase);
+                sm.done_who[0] = kSentinel;
+                mbar_arrive(smem_u32(sm.done_seq));
             }
+        } else if (warp - 4 < NF) {
+            fft_role<NF, HOP512>(b, sm, warp - 4, lane, n_mels);
         }
     }
     tc_fence_before();

@@ -505,12 +505,15 @@ int64_t hmfe_iir_workspace_bytes(const int64_t* h_offsets, int64_t n_clips, int 
     if (!h_offsets || n_clips < 0 || n_sections < 1 || n_sections > 8) return -1;
     // upper bound over the algorithms hmfe_iir_sos_batch / hmfe_iir_sos_trim_batch may choose: hop energies of the fused
     // trim (8 floats per hop group, one extra group per clip for the 16-byte alignment shift) or the carry vectors of the
-    // exact scan (two 2S-vectors of doubles per chunk, chunks of at least 512 samples)
+    // exact scan (two 2S-vectors of doubles per chunk; chunks of 512 samples for batches of 32 Mi samples and more, of
+    // 128 samples below that: the rule of iir_impl in iir.cu)
     int64_t groups = 0, chunks = 0;
+    const int64_t total = n_clips > 0 ? h_offsets[n_clips] - h_offsets[0] : 0;
+    const int64_t c_exact = total >= ((int64_t)32 << 20) ? 512 : 128;
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t n = h_offsets[i + 1] - h_offsets[i];
         if (hop_length > 0) groups += (n + 3 + hop_length - 1) / hop_length + 1;
-        chunks += (n + 3 + 511) / 512 + 1;
+        chunks += (n + 3 + c_exact - 1) / c_exact + 1;
     }
     const int64_t a = std::max<int64_t>(1, groups) * 8 * (int64_t)sizeof(float);
     const int64_t b = 2 * chunks * 2 * n_sections * (int64_t)sizeof(double);

@@ -53,6 +53,8 @@ HMFE_TC_D bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // non-blocking 
 }
 // false = gave up (protocol error)
 HMFE_TC_D bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;  // the common case: one test, no loop
+#pragma unroll 1
     for (uint32_t i = 0; i < kSpinLimit; ++i)
         if (mbar_try_wait(bar, parity)) return true;
     return false;

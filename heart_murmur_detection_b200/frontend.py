@@ -59,7 +59,10 @@ class LogMelPlan:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h and _lib is not None:  # module globals are gone at interpreter shutdown
-            _lib.hmfe_logmel_plan_destroy(h)
+            try:
+                _lib.hmfe_logmel_plan_destroy(h)
+            except TypeError:  # interpreter shutdown: the ctypes entry is already gone
+                pass
             self._h = None
 
     def frame_offsets(self, offsets) -> np.ndarray:
@@ -199,7 +202,10 @@ class Context:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h and _lib is not None:  # module globals are gone at interpreter shutdown
-            _lib.hmfe_ctx_destroy(h)
+            try:
+                _lib.hmfe_ctx_destroy(h)
+            except TypeError:  # interpreter shutdown: the ctypes entry is already gone
+                pass
             self._h = None
 
     @property
@@ -501,7 +507,10 @@ class FbankPlan:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h and _lib is not None:  # module globals are gone at interpreter shutdown
-            _lib.hmfe_fbank_plan_destroy(h)
+            try:
+                _lib.hmfe_fbank_plan_destroy(h)
+            except TypeError:  # interpreter shutdown: the ctypes entry is already gone
+                pass
             self._h = None
 
     def num_frames(self, lengths) -> np.ndarray:
@@ -625,7 +634,10 @@ class ResamplePlan:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h and _lib is not None:  # module globals are gone at interpreter shutdown
-            _lib.hmfe_resample_plan_destroy(h)
+            try:
+                _lib.hmfe_resample_plan_destroy(h)
+            except TypeError:  # interpreter shutdown: the ctypes entry is already gone
+                pass
             self._h = None
 
     def out_lengths(self, lengths) -> np.ndarray:

@@ -80,7 +80,10 @@ class HearPlan:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h and _lib is not None:  # module globals are gone at interpreter shutdown
-            _lib.hmfe_hear_plan_destroy(h)
+            try:
+                _lib.hmfe_hear_plan_destroy(h)
+            except TypeError:  # interpreter shutdown: the ctypes entry is already gone
+                pass
             self._h = None
 
     @property

@@ -668,7 +668,10 @@ def test_caller_provided_workspace_contract():
     small.use_workspace(torch.empty(256, dtype=torch.uint8, device="cuda"))
     with pytest.raises(HmfeError, match="too small"):
         fe.iir_sos_trim(wav, off, sos, ctx=small)
+    # the reservation for 2 clips carries a few KB of slack for the fixed-size records: a 700-clip batch is beyond it
+    many = [golden_signal(1000, seed=70 + i % 5) for i in range(700)]
+    wav_m, off_m = _batch(many)
     tight = fe.Context()
-    tight.use_workspace(torch.empty(need, dtype=torch.uint8, device="cuda"), max_clips=2)
+    tight.use_workspace(torch.empty(fe.trim_workspace_bytes(off_m, 1600, 800), dtype=torch.uint8, device="cuda"), max_clips=2)
     with pytest.raises(HmfeError, match="reserved"):
-        fe.trim_indices(wav, off, ctx=tight)
+        fe.trim_indices(wav_m, off_m, ctx=tight)
