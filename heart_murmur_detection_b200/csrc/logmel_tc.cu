@@ -39,21 +39,20 @@ namespace hmfe {
 
 using namespace tc;
 
-constexpr int kTcThreads = 512;
 constexpr int kRegionBytes = 19456;                        // per FFT warp: [B tile 8192 | frame staging 11264]
 constexpr int kPowerBytes = 8192;                          //   the 16 896-byte FFT exchange tile overlays both
 constexpr int kTmemCols = 512, kTmemD = 256, kDCols = 16;  // A: columns 0-255, accumulator of FFT warp w: 256 + 16 w
 static_assert(32 * kXStride * 16 <= kRegionBytes, "exchange tile must fit its region");
 
 enum : uint32_t {
-    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrTmemBase = 32u,
+    kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrSmemAlign = 16u, kErrTmemBase = 32u,
 };
 
 struct __align__(16) TcMeta {
-    float* out;     // first output row of the item
-    int64_t clip;
+    uint32_t row0;  // first output row of the item (frame index in the whole batch)
+    int clip;
     int nvalid;     // frames of the item that exist (1..4)
-    int pad_[3];
+    int pad_;
 };
 
 struct TcTables {
@@ -65,64 +64,55 @@ struct TcTables {
 constexpr int kRing = 16;          // > NF: at most one tile per FFT warp is in flight
 constexpr uint32_t kSentinel = 0xffu;
 
-struct TcSmem {  // pointers into the dynamic shared memory of the CTA
-    uint8_t* regions;
-    float2* tw;
-    float* win;
-    // per FFT warp: full (its MMAs are complete: the B tile may be overwritten), dfree (all four epilogue warps have
-    // read its accumulator and meta record), raw (its frame copy has landed)
-    uint64_t *full, *dfree, *raw;
-    // an in-order ring replaces polling of per-warp barriers (an mbarrier test costs ~150 cycles: sweeping 11 of
-    // them took longer than an item): an FFT warp appends its index to the "done" ring when it issues the MMAs of
-    // a tile and commits them to the ring slot's barrier; the epilogue warps consume the slots in ring order
-    uint64_t* done_seq;
-    uint32_t* done_who;
-    TcMeta* meta;
-    uint32_t *tmem, *done, *tail;
-};
-
+// Shared-memory layout, as compile-time offsets from the (1024-byte aligned) start of the dynamic shared memory: every
+// address in the kernel is then "symbol + constant (+ warp region)", no pointer lives in a register.
+//   regions   per FFT warp, see kRegionBytes
+//   tw, win   twiddle plane [32][32] float2, window 0.5 * Hann [1024]
+//   full      per FFT warp: its MMAs are complete (the B tile may be overwritten)
+//   dfree     per FFT warp: all four epilogue warps have read its accumulator and meta record
+//   raw       per FFT warp: its frame copy has landed
+//   done_seq / done_who   an in-order ring instead of polling per-warp barriers (an mbarrier test costs ~150 cycles:
+//             sweeping 11 of them took longer than an item): an FFT warp appends its index when it issues the MMAs of a
+//             tile and commits them to the slot's barrier; the epilogue warps consume the slots in ring order
 template <int NF>
-HMFE_TC_D TcSmem carve(uint8_t* base) {
-    TcSmem s;
-    s.regions = base;
-    uint8_t* p = base + NF * kRegionBytes;
-    s.tw = reinterpret_cast<float2*>(p);
-    p += 1024 * sizeof(float2);
-    s.win = reinterpret_cast<float*>(p);
-    p += 1024 * sizeof(float);
-    s.full = reinterpret_cast<uint64_t*>(p);
-    s.dfree = s.full + NF;
-    s.raw = s.dfree + NF;
-    s.done_seq = s.raw + NF;
-    p += (3 * NF + kRing) * sizeof(uint64_t);
-    s.done_who = reinterpret_cast<uint32_t*>(p);
-    p += kRing * sizeof(uint32_t);
-    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-    s.meta = reinterpret_cast<TcMeta*>(p);
-    p += NF * sizeof(TcMeta);
-    s.tmem = reinterpret_cast<uint32_t*>(p);
-    s.done = s.tmem + 1;
-    s.tail = s.tmem + 2;
-    return s;
-}
+struct Lay {
+    static constexpr uint32_t tw = NF * kRegionBytes;
+    static constexpr uint32_t win = tw + 1024 * 8;
+    static constexpr uint32_t full = win + 1024 * 4;
+    static constexpr uint32_t dfree = full + NF * 8;
+    static constexpr uint32_t raw = dfree + NF * 8;
+    static constexpr uint32_t done_seq = raw + NF * 8;
+    static constexpr uint32_t done_who = done_seq + kRing * 8;
+    static constexpr uint32_t meta = (done_who + kRing * 4 + 15) & ~15u;
+    static constexpr uint32_t tmem = meta + NF * sizeof(TcMeta);  // tensor-memory base, finished-warp count, ring tail
+    static constexpr uint32_t done = tmem + 4;
+    static constexpr uint32_t tail = tmem + 8;
+    static constexpr uint32_t bytes = tmem + 16;
+};
 template <int NF>
 constexpr size_t tc_smem_bytes() {
-    return 1024 /* alignment slack */ + (size_t)NF * kRegionBytes + 1024 * 8 + 1024 * 4 + (3 * NF + kRing) * 8 +
-           kRing * 4 + 16 + NF * sizeof(TcMeta) + 16;
+    return Lay<NF>::bytes;
 }
 
-// What an FFT warp keeps about an item between the start of its frame copy and the hand-over of its power tile.
-// The staging buffer holds the span of the item's four frames, clip positions [P0, P0 + 3 hop + 1024) with
-// P0 = f0 hop - 512, from staging index `a`; positions outside the clip (centre padding, frames beyond the last
-// one) are ZERO there: one fetch path for interior and edge items (three unrolled paths tripled the kernel's code:
-// the compiler cloned the whole item loop per path, 15 800 instructions, and the warps starved on instruction
-// fetches), and no NaN bit pattern of stale shared memory can reach a transform that packs an existing frame.
+extern __shared__ __align__(1024) uint8_t tc_smem[];
+
+template <typename T>
+HMFE_TC_D T* sptr(uint32_t off) { return reinterpret_cast<T*>(tc_smem + off); }
+HMFE_TC_D uint32_t saddr(uint32_t off) { return smem_u32(tc_smem) + off; }
+
+// What an FFT warp keeps about an item while its registers hold a transform.  The staging buffer holds the span of the
+// item's four frames, clip positions [P0, P0 + 3 hop + 1024) with P0 = f0 hop - 512, from staging index `a`; positions
+// outside the clip (centre padding, frames beyond the last one) are ZERO there: one fetch path for interior and edge
+// items, and no NaN bit pattern of stale shared memory can reach a transform that packs an existing frame.
 struct Prep {
-    float* out;     // first output row of the item
+    uint32_t item;
+    uint32_t row0;       // first output row of the item
     int clip;
-    int nvalid;     // frames of the item that exist (1..4); 0 = no item
-    int a;          // staging index of span position 0 (0..3: keeps the bulk copy 16-byte aligned on both sides)
-    int zlo, zhi;   // span positions [0, zlo) and [zhi, span length) lie outside the clip
+    uint32_t packed;     // nvalid | a << 3 | zlo << 5 | zhi << 17: frames that exist (0 = no item), staging index of span
+                         // position 0 (0..3: keeps the bulk copy 16-byte aligned on both sides), span positions [0, zlo)
+                         // and [zhi, span length) lie outside the clip
+    const float* src;    // bulk copy of the frames: global source, 16-byte aligned
+    uint32_t dst_bytes;  // staging index of the first copied float | bytes << 12 (0 bytes: nothing to copy)
 };
 constexpr int kStageFloats = 3 + (3 * 512 + kNfft) + 3 + 2;  // 2568: offset a, span at hop 512, round-up of the copy
 static_assert(kStageFloats * 4 <= kRegionBytes - kPowerBytes, "staging area too small");
@@ -140,41 +130,48 @@ HMFE_TC_D void split8(const float (&p)[8], uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// Exchange store as ONE 16-byte store per element: the two 8-byte halves of store_halves() (stride 16 bytes between
+// lanes) are a 2-way bank conflict each unless ptxas merges them, which it does in logmel.cu but not here
+// (ncu: 257 wavefronts per item for 64 STS.64 instead of 128).
+HMFE_TC_D void exchange_store_v4(uint32_t base, const f32x2 (&re)[32], const f32x2 (&im)[32]) {
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(k2 * kXStride * 16)), "f"(re[k2].x),
+                     "f"(re[k2].y), "f"(im[k2].x), "f"(im[k2].y)
+                     : "memory");
+}
 HMFE_TC_D void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ FFT warps
 template <int NF, bool HOP512>
-HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane, int n_mels) {
+HMFE_TC_D void fft_role(const LogmelBatch& b, int w, int lane, int n_mels) {
     using V = f32x2;
+    using L = Lay<NF>;
     constexpr int FR = 4;
-    uint8_t* region = sm.regions + w * kRegionBytes;
-    xelem<V>* tile = reinterpret_cast<xelem<V>*>(region);
-    float* stage = reinterpret_cast<float*>(region + kPowerBytes);
-    const uint32_t tile_addr = smem_u32(region), stage_addr = tile_addr + kPowerBytes;
-    const uint32_t bar_full = smem_u32(sm.full + w), bar_free = smem_u32(sm.dfree + w), bar_raw = smem_u32(sm.raw + w);
+    const uint32_t region = (uint32_t)w * kRegionBytes;
+    const uint32_t tile_addr = saddr(region), stage_addr = tile_addr + kPowerBytes;
+    const uint32_t bar_full = saddr(L::full + 8 * w), bar_free = saddr(L::dfree + 8 * w), bar_raw = saddr(L::raw + 8 * w);
     const int hop = HOP512 ? 512 : b.hop;
     const int span_len = 3 * hop + kNfft;
     constexpr uint64_t desc_hi = smem_desc(0, 0, 1024, kSwizzle128B);
     constexpr uint32_t idesc = idesc_bf16_f32(128, kDCols);
-    const uint32_t desc_lo = tile_addr >> 4;
-    const uint32_t d_tmem = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
 
-    constexpr int kItemBlock = 8;
-    const int64_t it_end = item_count(b);
-    auto claim = [&]() -> int64_t {
+    // item indices fit 32 bits (the host checks n_items < 2^31 - 2^20 for this variant; the shared queue counter
+    // is 64 bits wide): half the registers of the 64-bit bookkeeping of logmel.cu
+    constexpr uint32_t kItemBlock = 8;
+    const uint32_t it_end = (uint32_t)min(item_count(b), (int64_t)0x7ff00000);
+    auto claim = [&]() -> uint32_t {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(b.queue, (unsigned long long)kItemBlock);
-        return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        return (uint32_t)min(v, (unsigned long long)0x7ff00000u);
     };
-    int64_t blk_end = 0;
-    auto next_item = [&](int64_t item) -> int64_t {
-        if (item + 1 < blk_end) return item + 1;
+    auto next_item = [&](uint32_t item) -> uint32_t {  // blocks are aligned to kItemBlock: no block-end register
+        if ((item + 1) % kItemBlock != 0) return item + 1;
         if (item >= it_end) return item;
-        const int64_t nb = claim();
-        blk_end = nb + kItemBlock;
-        return nb;
+        return claim();
     };
     // a wait that gave up (protocol error) is reported once; the warp then stops waiting so that the kernel ends
     bool alive = true;
@@ -185,53 +182,65 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
         }
     };
     int64_t clip_cursor = -1;
-    // locate the item, start the bulk copy of its frame span into the staging buffer (lane 0)
-    auto prepare = [&](int64_t item) -> Prep {
-        const ItemCtx c = locate_item<FR>(b, n_mels, item, it_end, clip_cursor);
+    // Everything about an item is worked out while the warp's registers are free (between two transforms), the
+    // copy itself is started later, when the previous item has left the staging buffer.
+    auto locate = [&](uint32_t item) -> Prep {
+        const ItemCtx c = locate_item<FR>(b, n_mels, (int64_t)item, (int64_t)it_end, clip_cursor);
         Prep p;
-        p.out = c.o + (int64_t)c.f0 * n_mels;
+        p.item = item;
+        p.row0 = 0;
         p.clip = (int)c.clip;
-        p.nvalid = c.valid ? min(4, c.T - c.f0) : 0;
-        p.a = 0;
-        p.zlo = span_len;
-        p.zhi = span_len;
+        p.packed = 0;
+        p.src = b.wav;
+        p.dst_bytes = 0;
         if (!c.valid) return p;
+        p.row0 = (uint32_t)((c.o - b.out) / n_mels) + (uint32_t)c.f0;
         const int P0 = c.f0 * hop - kNfft / 2;
         const int first = max(0, P0), end = min(c.nsamp, P0 + span_len);
+        uint32_t a = 0, zlo = (uint32_t)span_len, zhi = (uint32_t)span_len;
         if (end > first) {
             const float* g = c.x + first;
             const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
             const int d0 = first - P0 - skip;  // span position of the first copied sample (>= -3)
-            p.a = (-d0) & 3;
-            p.zlo = first - P0;
-            p.zhi = end - P0;
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)(((end - first + skip) * 4 + 15) & ~15);
-                mbar_expect_tx(bar_raw, bytes);
-                bulk_g2s(stage_addr + 4u * (uint32_t)(p.a + d0), g - skip, bytes, bar_raw);
-            }
-        } else if (lane == 0) {
+            a = (uint32_t)((-d0) & 3);
+            zlo = (uint32_t)(first - P0);
+            zhi = (uint32_t)(end - P0);
+            p.src = g - skip;
+            p.dst_bytes = (uint32_t)((int)a + d0) | ((uint32_t)(((end - first + skip) * 4 + 15) & ~15) << 12);
+        }
+        p.packed = (uint32_t)min(4, c.T - c.f0) | (a << 3) | (zlo << 5) | (zhi << 17);
+        return p;
+    };
+    auto start_copy = [&](const Prep& p) {  // lane 0
+        if ((p.packed & 7u) == 0) return;
+        const uint32_t bytes = p.dst_bytes >> 12;
+        if (bytes) {
+            mbar_expect_tx(bar_raw, bytes);
+            bulk_g2s(stage_addr + 4u * (p.dst_bytes & 0xfffu), p.src, bytes, bar_raw);
+        } else {
             mbar_arrive(bar_raw);
         }
-        return p;
     };
 
     if (b.stagger_ns > 0) __nanosleep((unsigned)(w * b.stagger_ns));
-    int64_t item = claim();
-    blk_end = item + kItemBlock;
-    Prep cur = prepare(item);
+    Prep cur = locate(claim());
+    if (lane == 0) start_copy(cur);
+    Prep nxt = locate(next_item(cur.item));
     uint32_t n_done = 0;
 
-    while (item < it_end) {
+    while (cur.item < it_end) {
+        const uint32_t a = (cur.packed >> 3) & 3u, zlo = (cur.packed >> 5) & 0xfffu, zhi = cur.packed >> 17;
+        float* stage = sptr<float>(region + kPowerBytes) + a;  // span position 0
         wait(bar_raw, n_done & 1, kErrRawWait);
-        if (cur.zlo > 0 || cur.zhi < span_len) {  // edge item: zeros outside the clip (after the copy, which rounds outwards)
-            for (int j = lane; j < cur.zlo; j += 32) stage[cur.a + j] = 0.0f;
-            for (int j = cur.zhi + lane; j < span_len; j += 32) stage[cur.a + j] = 0.0f;
+        if (zlo > 0 || zhi < (uint32_t)span_len) {  // edge item: zeros outside the clip (after the copy, which rounds outwards)
+            for (uint32_t j = lane; j < zlo; j += 32) stage[j] = 0.0f;
+            for (uint32_t j = zhi + lane; j < (uint32_t)span_len; j += 32) stage[j] = 0.0f;
             __syncwarp();
         }
         V re[32], im[32];
         {
-            const float* sp = stage + cur.a + lane;  // sample `lane` of the item's first frame
+            const float* sp = stage + lane;  // sample `lane` of the item's first frame
+            const float* win = sptr<float>(L::win) + lane;
             if (HOP512) {
                 // 50 % overlap: frame j = half-frames (j, j + 1) of the span, every staged sample is read once
 #pragma unroll
@@ -239,7 +248,8 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
                     float h5[5];
 #pragma unroll
                     for (int q = 0; q < 5; ++q) h5[q] = sp[512 * q + 32 * m];
-                    const float w0 = sm.win[lane + 32 * m], w1 = sm.win[lane + 32 * (m + 16)];
+                    // 0.5 * Hann: win[n + 512] = 0.25 + 0.25 cos(2 pi n / 1024) = 0.5 - win[n] (one table read per pair)
+                    const float w0 = win[32 * m], w1 = 0.5f - w0;
                     re[brev(m, 5)] = vmuls(V{h5[0], h5[2]}, w0);
                     im[brev(m, 5)] = vmuls(V{h5[1], h5[3]}, w0);
                     re[brev(m + 16, 5)] = vmuls(V{h5[1], h5[3]}, w1);
@@ -248,7 +258,7 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
             } else {
 #pragma unroll
                 for (int n2 = 0; n2 < 32; ++n2) {
-                    const float wv = sm.win[lane + 32 * n2];
+                    const float wv = win[32 * n2];
                     const float* q = sp + 32 * n2;
                     re[brev(n2, 5)] = vmuls(V{q[0], q[2 * hop]}, wv);
                     im[brev(n2, 5)] = vmuls(V{q[hop], q[3 * hop]}, wv);
@@ -256,24 +266,21 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
             }
         }
         __syncwarp();
-        int64_t nitem = item;
-        Prep nxt = cur;
         // both 32-point passes run the same unrolled butterfly code (one copy in the instruction cache)
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             fft_dit<32, V>(re, im);
             if (pass == 0) {
-                apply_twiddle<V>(lane, sm.tw, re, im);
+                apply_twiddle<V>(lane, sptr<const float2>(L::tw), re, im);
                 // the tensor core must be done with the previous B tile before the exchange overwrites it
                 wait(bar_full, n_done & 1, kErrFullWait);  // completion n_done (completion 0 is the arrival at start-up)
-                exchange_store<V>(lane, tile, re, im);
+                exchange_store_v4(tile_addr + 16u * (uint32_t)lane, re, im);
                 __syncwarp();
-                exchange_load<V>(lane, tile, re, im);
+                exchange_load<V>(lane, sptr<const xelem<V>>(region), re, im);
                 __syncwarp();
-                // the staging area is free again: claim the next item and start the copy of its frames
-                nitem = next_item(item);
+                // the staging area is free again: start the copy of the next item's frames
                 fence_proxy_async();
-                nxt = prepare(nitem);
+                if (lane == 0) start_copy(nxt);
             }
         }
         {   // separation of the packed frames, power, bf16 (hi, lo) split, B tile rows
@@ -314,57 +321,61 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, const TcSmem& sm, int w, int lane,
         tc_fence_after();     // after the epilogue's tcgen05.ld of this accumulator (its mbarrier arrive was observed)
         if (elect_one()) {
             TcMeta m;
-            m.out = cur.out;
+            m.row0 = cur.row0;
             m.clip = cur.clip;
-            m.nvalid = cur.nvalid;
-            m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
-            sm.meta[w] = m;
-            const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
-            sm.done_who[slot] = (uint32_t)w;
+            m.nvalid = (int)(cur.packed & 7u);
+            m.pad_ = 0;
+            sptr<TcMeta>(L::meta)[w] = m;
+            const uint32_t slot = atomicAdd(sptr<uint32_t>(L::tail), 1u) % kRing;
+            sptr<uint32_t>(L::done_who)[slot] = (uint32_t)w;
             __threadfence_block();  // meta record and ring entry before the barrier the commits complete
+            const uint32_t desc_lo = tile_addr >> 4;
+            const uint32_t d_tmem = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
 #pragma unroll
             for (int k = 0; k < 32; ++k)
                 mma_ts_f16(d_tmem, 8 * k, desc_hi | (uint64_t)(desc_lo + (k >> 2) * 64 + (k & 3) * 2), idesc, k > 0);
-            mma_commit(smem_u32(sm.done_seq + slot));  // -> epilogue warps, in ring order
-            mma_commit(bar_full);                      // -> this warp: its B tile may be overwritten
+            mma_commit(saddr(L::done_seq) + 8u * slot);  // -> epilogue warps, in ring order
+            mma_commit(bar_full);                        // -> this warp: its B tile may be overwritten
         }
         __syncwarp();
         ++n_done;
-        item = nitem;
+        // registers are free here: locate the item after the next one
         cur = nxt;
+        nxt = locate(next_item(cur.item));
     }
     // all of this warp's accumulators have been produced before it reports completion
     wait(bar_full, n_done & 1, kErrFullWait);
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();
-        if (atomicAdd(sm.done, 1u) == (uint32_t)NF - 1) {  // the last FFT warp closes the ring
-            const uint32_t slot = atomicAdd(sm.tail, 1u) % kRing;
-            sm.done_who[slot] = kSentinel;
-            mbar_arrive(smem_u32(sm.done_seq + slot));
+        if (atomicAdd(sptr<uint32_t>(L::done), 1u) == (uint32_t)NF - 1) {  // the last FFT warp closes the ring
+            const uint32_t slot = atomicAdd(sptr<uint32_t>(L::tail), 1u) % kRing;
+            sptr<uint32_t>(L::done_who)[slot] = kSentinel;
+            mbar_arrive(saddr(L::done_seq) + 8u * slot);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue warps
 template <int NF>
-HMFE_TC_D void epilogue_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tmem, int q, int lane, int n_mels) {
+HMFE_TC_D void epilogue_role(const LogmelBatch& b, uint32_t tmem, int q, int lane, int n_mels) {
+    using L = Lay<NF>;
     const int col = 16 * q + (lane & 15);
     const int fsel = lane >> 4;  // lanes 0-15 store frames 0 and 1, lanes 16-31 frames 2 and 3
-    const uint32_t done_seq = smem_u32(sm.done_seq);
+    const uint32_t done_seq = saddr(L::done_seq);
     for (uint32_t seq = 0; seq < (1u << 30); ++seq) {
         const uint32_t slot = seq % kRing;
         if (!mbar_wait(done_seq + 8u * slot, (seq / kRing) & 1u)) break;
-        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sm.done_who + slot);
+        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sptr<uint32_t>(L::done_who) + slot);
         if (w == kSentinel) return;
         tc_fence_after();
-        const TcMeta m = sm.meta[w];
+        const TcMeta m = sptr<TcMeta>(L::meta)[w];
         uint32_t v[8];
         tmem_ld8(tmem + kTmemD + kDCols * w + ((uint32_t)(32 * q) << 16), v);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(sm.dfree + w));
+        if (lane == 0) mbar_arrive(saddr(L::dfree) + 8u * w);
         float d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -375,8 +386,9 @@ HMFE_TC_D void epilogue_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tm
         const float va = fsel ? d[2] : d[0], vb = fsel ? d[3] : d[1];
         const int fa = 2 * fsel, fb = fa + 1;
         const bool oka = col < n_mels && fa < m.nvalid, okb = col < n_mels && fb < m.nvalid;
-        if (oka) m.out[(int64_t)fa * n_mels + col] = va;
-        if (okb) m.out[(int64_t)fb * n_mels + col] = vb;
+        float* out = b.out + (int64_t)m.row0 * n_mels;
+        if (oka) out[(int64_t)fa * n_mels + col] = va;
+        if (okb) out[(int64_t)fb * n_mels + col] = vb;
         uint32_t hi = 0u, lo = 0x7f800000u;
         if (oka) {
             hi = __float_as_uint(va) & 0x7fffffffu;
@@ -390,49 +402,58 @@ HMFE_TC_D void epilogue_role(const LogmelBatch& b, const TcSmem& sm, uint32_t tm
         hi = __reduce_max_sync(0xffffffffu, hi);  // non-negative floats order like their bit patterns
         lo = __reduce_min_sync(0xffffffffu, lo);
         if (lane == 0) {
-            atomicMax(b.stats + 2 * m.clip, hi);
-            atomicMin(b.stats + 2 * m.clip + 1, lo);
+            atomicMax(b.stats + 2 * (int64_t)m.clip, hi);
+            atomicMin(b.stats + 2 * (int64_t)m.clip + 1, lo);
         }
     }
     if (lane == 0) atomicOr(b.status, kErrEpiSpin);
 }
 
-// NF FFT warps.  Registers per thread after re-allocation (65 536 per SM):
-//   NF = 11: epilogue warpgroup 32, the three other warpgroups 160      (128*32 + 384*160 = 65 536)
-//   NF = 8 : epilogue 40, two FFT warpgroups 216, last warpgroup 40     (256*40 + 256*216 = 65 536)
+// 4 epilogue warps + NF FFT warps, in whole warpgroups: setmaxnreg acts on warpgroups, and a block with a partial
+// warpgroup is charged registers for the whole of it (480 threads at 136 registers: "too many resources requested").
+//   NF = 11: 512 threads launched at 128 registers; epilogue warpgroup -> 32, the other three warpgroups -> 160
+//            (128 * 32 + 384 * 160 = 65 536); warp 15 has no region in shared memory and idles
+//   NF = 8 : 384 threads launched at 168 registers; epilogue -> 32, the two FFT warpgroups -> 224 (61 440)
+template <int NF>
+struct TcCfg {
+    static constexpr int threads = NF > 8 ? 512 : 384;
+    static constexpr int fft_regs = NF > 8 ? 160 : 224;
+    static constexpr int epi_regs = 32;
+};
+
 template <int NF, bool HOP512>
-__global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBatch b, const TcTables tb, int n_mels) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    uint8_t* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    const TcSmem sm = carve<NF>(base);
+__global__ void __launch_bounds__(TcCfg<NF>::threads, 1) logmel_tc_kernel(const LogmelBatch b, const TcTables tb, int n_mels) {
+    constexpr int kTcThreads = TcCfg<NF>::threads;
+    using L = Lay<NF>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((smem_u32(tc_smem) & 1023u) != 0) {  // the swizzled B tiles need the 1024-byte alignment the declaration asks for
+        if (threadIdx.x == 0) atomicOr(b.status, kErrSmemAlign);
+        return;
+    }
 
     for (int i = threadIdx.x; i < 1024; i += kTcThreads) {
-        sm.tw[i] = tb.tw[i];
-        sm.win[i] = tb.win[i];
+        sptr<float2>(L::tw)[i] = tb.tw[i];
+        sptr<float>(L::win)[i] = tb.win[i];
     }
     if (threadIdx.x == 0) {
         for (int w = 0; w < NF; ++w) {
-            mbar_init(smem_u32(sm.full + w), 1);
-            mbar_init(smem_u32(sm.dfree + w), 4);
-            mbar_init(smem_u32(sm.raw + w), 1);
+            mbar_init(saddr(L::full + 8 * w), 1);
+            mbar_init(saddr(L::dfree + 8 * w), 4);
+            mbar_init(saddr(L::raw + 8 * w), 1);
             // phase 0 of "B tile free" and "accumulator free" completes here: the first item of a warp waits like any other
-            mbar_arrive(smem_u32(sm.full + w));
-            for (int q = 0; q < 4; ++q) mbar_arrive(smem_u32(sm.dfree + w));
+            mbar_arrive(saddr(L::full + 8 * w));
+            for (int q = 0; q < 4; ++q) mbar_arrive(saddr(L::dfree + 8 * w));
         }
-        for (int i = 0; i < kRing; ++i) {
-            mbar_init(smem_u32(sm.done_seq + i), 1);
-        }
-        *sm.done = 0;
-        *sm.tail = 0;
+        for (int i = 0; i < kRing; ++i) mbar_init(saddr(L::done_seq + 8 * i), 1);
+        *sptr<uint32_t>(L::done) = 0;
+        *sptr<uint32_t>(L::tail) = 0;
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(smem_u32(sm.tmem), kTmemCols);
+    if (warp == 0) tmem_alloc(saddr(L::tmem), kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *sm.tmem;
+    const uint32_t tmem = *sptr<uint32_t>(L::tmem);
     if (warp < 4) {  // the mel weights: row 32 warp + lane of A, 256 words
         const uint32_t* row = tb.a_words + (32 * warp + lane) * 256;
         for (int c = 0; c < 256; c += 8) {
@@ -448,22 +469,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) logmel_tc_kernel(const LogmelBa
     tc_fence_after();
 
     if (warp < 4) {
-        if constexpr (NF > 8) setmaxnreg_dec<32>(); else setmaxnreg_dec<40>();
-        epilogue_role<NF>(b, sm, tmem, warp, lane, n_mels);
+        setmaxnreg_dec<TcCfg<NF>::epi_regs>();
+        epilogue_role<NF>(b, tmem, warp, lane, n_mels);
     } else {
-        if constexpr (NF > 8) {
-            setmaxnreg_inc<160>();
-        } else {
-            if (warp < 12) setmaxnreg_inc<216>(); else setmaxnreg_dec<40>();
-        }
+        setmaxnreg_inc<TcCfg<NF>::fft_regs>();
         if (tmem != 0) {  // cannot happen while the CTA owns all 512 columns; the roles assume base 0
             if (threadIdx.x == 128) {  // report, and close the ring so that the epilogue warps return
                 atomicOr(b.status, kErrTmemBase);
-                sm.done_who[0] = kSentinel;
-                mbar_arrive(smem_u32(sm.done_seq));
+                sptr<uint32_t>(L::done_who)[0] = kSentinel;
+                mbar_arrive(saddr(L::done_seq));
             }
         } else if (warp - 4 < NF) {
-            fft_role<NF, HOP512>(b, sm, warp - 4, lane, n_mels);
+            fft_role<NF, HOP512>(b, warp - 4, lane, n_mels);
         }
     }
     tc_fence_before();
@@ -519,7 +536,7 @@ static int launch_tc_n(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t s
     const int64_t want = (b.n_items + NF - 1) / NF;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)p->sm_count));
     TcTables tb{p->d_win, p->d_tw, p->d_tc_a};
-    kern<<<grid, kTcThreads, smem, st>>>(b, tb, p->n_mels);
+    kern<<<grid, TcCfg<NF>::threads, smem, st>>>(b, tb, p->n_mels);
     HMFE_CHECK_CUDA(cudaGetLastError());
     return HMFE_OK;
 }
@@ -527,6 +544,8 @@ static int launch_tc_n(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t s
 int launch_logmel_tc(hmfe_logmel_plan* p, const LogmelBatch& b, cudaStream_t st) {
     HMFE_REQUIRE(p->tc_ok && p->d_tc_a && p->pad_mode == HMFE_PAD_CONSTANT,
                  "the tensor-core log-mel variant needs n_mels <= 64, hop <= 512 and constant padding");
+    HMFE_REQUIRE(b.n_items_dev != nullptr || b.n_items < (int64_t)0x7ff00000,
+                 "the tensor-core log-mel variant indexes work items with 32 bits: %lld items in one call", (long long)b.n_items);
     const bool h512 = p->hop == 512;
     if (p->tc_fft_warps <= 8) return h512 ? launch_tc_n<8, true>(p, b, st) : launch_tc_n<8, false>(p, b, st);
     return h512 ? launch_tc_n<11, true>(p, b, st) : launch_tc_n<11, false>(p, b, st);
