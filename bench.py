@@ -614,7 +614,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "scalar", "packed", "pair"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "scalar", "packed", "pair", "tc"])
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (0 = the workload's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -705,7 +705,7 @@ def main():
             state.update(features=out, rows=out_rows, launches=fb_plan.last_launches)
 
     if wl in ("c2", "c2nf") and args.variant != "auto":  # make the pipeline pick the requested log-mel variant
-        frontend._plans[("logmel", torch.cuda.current_device(), 16000, 64, 50.0, 8000.0, 1024, 512, "auto")] = lm_plan
+        frontend._plans[("logmel", torch.cuda.current_device(), 16000, 64, 50.0, 8000.0, 1024, 512, "auto", "constant")] = lm_plan
 
     n_cols = 128 if wl == "c3" else 64
     rows = out_rows

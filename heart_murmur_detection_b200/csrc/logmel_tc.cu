@@ -35,6 +35,10 @@
 #include "tables.h"
 #include "tc_ptx.cuh"
 
+#ifndef HMFE_TC_EPI_SPIN
+#define HMFE_TC_EPI_SPIN 0
+#endif
+
 namespace hmfe {
 
 using namespace tc;
@@ -48,12 +52,24 @@ enum : uint32_t {
     kErrRawWait = 1u, kErrFullWait = 2u, kErrFreeWait = 4u, kErrEpiSpin = 8u, kErrSmemAlign = 16u, kErrTmemBase = 32u,
 };
 
+// Item record, written to shared memory by lane 0 of the FFT warp when the item is located (while the warp's registers
+// are free) and read back by whoever needs a field: all lanes (`packed`, before the frame fetch), lane 0 (the bulk copy),
+// the epilogue warps (row0, clip, nvalid).  Keeping it in registers across the transform cost ~40 local-memory spill
+// instructions per item at the 160 registers the FFT warps get (ncu: 18 % of their stall samples on those loads).
+// Three records per warp, item i in record i % 3: the record of item i - 2 is free when item i + 1 is located, because
+// the epilogue's release of item i - 2 was awaited before item i - 1 was handed over.
 struct __align__(16) TcMeta {
-    uint32_t row0;  // first output row of the item (frame index in the whole batch)
+    uint32_t row0;       // first output row of the item (frame index in the whole batch)
     int clip;
-    int nvalid;     // frames of the item that exist (1..4)
-    int pad_;
+    uint32_t packed;     // nvalid | a << 3 | zlo << 5 | zhi << 17: frames that exist (0 = no item), staging index of span
+                         // position 0 (0..3: keeps the bulk copy 16-byte aligned on both sides), span positions [0, zlo)
+                         // and [zhi, span length) lie outside the clip (zero)
+    uint32_t dst_bytes;  // bulk copy: staging index of the first copied float | bytes << 12 (0 bytes: nothing to copy)
+    const float* src;    // bulk copy: global source, 16-byte aligned
+    uint32_t item;
+    uint32_t pad_;
 };
+static_assert(sizeof(TcMeta) == 32, "TcMeta is two 16-byte words");
 
 struct TcTables {
     const float* win;
@@ -84,7 +100,7 @@ struct Lay {
     static constexpr uint32_t done_seq = raw + NF * 8;
     static constexpr uint32_t done_who = done_seq + kRing * 8;
     static constexpr uint32_t meta = (done_who + kRing * 4 + 15) & ~15u;
-    static constexpr uint32_t tmem = meta + NF * sizeof(TcMeta);  // tensor-memory base, finished-warp count, ring tail
+    static constexpr uint32_t tmem = meta + 3 * NF * sizeof(TcMeta);  // tensor-memory base, finished-warp count, ring tail
     static constexpr uint32_t done = tmem + 4;
     static constexpr uint32_t tail = tmem + 8;
     static constexpr uint32_t bytes = tmem + 16;
@@ -100,20 +116,10 @@ template <typename T>
 HMFE_TC_D T* sptr(uint32_t off) { return reinterpret_cast<T*>(tc_smem + off); }
 HMFE_TC_D uint32_t saddr(uint32_t off) { return smem_u32(tc_smem) + off; }
 
-// What an FFT warp keeps about an item while its registers hold a transform.  The staging buffer holds the span of the
-// item's four frames, clip positions [P0, P0 + 3 hop + 1024) with P0 = f0 hop - 512, from staging index `a`; positions
-// outside the clip (centre padding, frames beyond the last one) are ZERO there: one fetch path for interior and edge
-// items, and no NaN bit pattern of stale shared memory can reach a transform that packs an existing frame.
-struct Prep {
-    uint32_t item;
-    uint32_t row0;       // first output row of the item
-    int clip;
-    uint32_t packed;     // nvalid | a << 3 | zlo << 5 | zhi << 17: frames that exist (0 = no item), staging index of span
-                         // position 0 (0..3: keeps the bulk copy 16-byte aligned on both sides), span positions [0, zlo)
-                         // and [zhi, span length) lie outside the clip
-    const float* src;    // bulk copy of the frames: global source, 16-byte aligned
-    uint32_t dst_bytes;  // staging index of the first copied float | bytes << 12 (0 bytes: nothing to copy)
-};
+// The staging buffer of an FFT warp holds the span of an item's four frames, clip positions [P0, P0 + 3 hop + 1024) with
+// P0 = f0 hop - 512, from staging index `a`; positions outside the clip (centre padding, frames beyond the last one) are
+// ZERO there: one fetch path for interior and edge items, and no NaN bit pattern of stale shared memory can reach a
+// transform that packs an existing frame.
 constexpr int kStageFloats = 3 + (3 * 512 + kNfft) + 3 + 2;  // 2568: offset a, span at hop 512, round-up of the copy
 static_assert(kStageFloats * 4 <= kRegionBytes - kPowerBytes, "staging area too small");
 
@@ -182,54 +188,63 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, int w, int lane, int n_mels) {
         }
     };
     int64_t clip_cursor = -1;
-    // Everything about an item is worked out while the warp's registers are free (between two transforms), the
-    // copy itself is started later, when the previous item has left the staging buffer.
-    auto locate = [&](uint32_t item) -> Prep {
+    // Everything about an item is worked out while the warp's registers are free (between two transforms) and
+    // parked in the warp's record `rec` in shared memory; the copy itself is started later, when the previous item
+    // has left the staging buffer.
+    TcMeta* recs = sptr<TcMeta>(L::meta) + 3 * w;
+    auto locate = [&](uint32_t item, uint32_t rec) {
         const ItemCtx c = locate_item<FR>(b, n_mels, (int64_t)item, (int64_t)it_end, clip_cursor);
-        Prep p;
-        p.item = item;
-        p.row0 = 0;
-        p.clip = (int)c.clip;
-        p.packed = 0;
-        p.src = b.wav;
-        p.dst_bytes = 0;
-        if (!c.valid) return p;
-        p.row0 = (uint32_t)((c.o - b.out) / n_mels) + (uint32_t)c.f0;
-        const int P0 = c.f0 * hop - kNfft / 2;
-        const int first = max(0, P0), end = min(c.nsamp, P0 + span_len);
-        uint32_t a = 0, zlo = (uint32_t)span_len, zhi = (uint32_t)span_len;
-        if (end > first) {
-            const float* g = c.x + first;
-            const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
-            const int d0 = first - P0 - skip;  // span position of the first copied sample (>= -3)
-            a = (uint32_t)((-d0) & 3);
-            zlo = (uint32_t)(first - P0);
-            zhi = (uint32_t)(end - P0);
-            p.src = g - skip;
-            p.dst_bytes = (uint32_t)((int)a + d0) | ((uint32_t)(((end - first + skip) * 4 + 15) & ~15) << 12);
+        TcMeta m;
+        m.row0 = 0;
+        m.clip = (int)c.clip;
+        m.packed = 0;
+        m.dst_bytes = 0;
+        m.src = b.wav;
+        m.item = item;
+        m.pad_ = 0;
+        if (c.valid) {
+            m.row0 = (uint32_t)((c.o - b.out) / n_mels) + (uint32_t)c.f0;
+            const int P0 = c.f0 * hop - kNfft / 2;
+            const int first = max(0, P0), end = min(c.nsamp, P0 + span_len);
+            uint32_t a = 0, zlo = (uint32_t)span_len, zhi = (uint32_t)span_len;
+            if (end > first) {
+                const float* g = c.x + first;
+                const int skip = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
+                const int d0 = first - P0 - skip;  // span position of the first copied sample (>= -3)
+                a = (uint32_t)((-d0) & 3);
+                zlo = (uint32_t)(first - P0);
+                zhi = (uint32_t)(end - P0);
+                m.src = g - skip;
+                m.dst_bytes = (uint32_t)((int)a + d0) | ((uint32_t)(((end - first + skip) * 4 + 15) & ~15) << 12);
+            }
+            m.packed = (uint32_t)min(4, c.T - c.f0) | (a << 3) | (zlo << 5) | (zhi << 17);
         }
-        p.packed = (uint32_t)min(4, c.T - c.f0) | (a << 3) | (zlo << 5) | (zhi << 17);
-        return p;
+        if (lane == 0) recs[rec] = m;
     };
-    auto start_copy = [&](const Prep& p) {  // lane 0
-        if ((p.packed & 7u) == 0) return;
-        const uint32_t bytes = p.dst_bytes >> 12;
+    auto start_copy = [&](uint32_t rec) {  // lane 0
+        const TcMeta m = recs[rec];
+        if ((m.packed & 7u) == 0) return;
+        const uint32_t bytes = m.dst_bytes >> 12;
         if (bytes) {
             mbar_expect_tx(bar_raw, bytes);
-            bulk_g2s(stage_addr + 4u * (p.dst_bytes & 0xfffu), p.src, bytes, bar_raw);
+            bulk_g2s(stage_addr + 4u * (m.dst_bytes & 0xfffu), m.src, bytes, bar_raw);
         } else {
             mbar_arrive(bar_raw);
         }
     };
+    auto rec_after = [](uint32_t rec) { return rec == 2 ? 0u : rec + 1; };
 
     if (b.stagger_ns > 0) __nanosleep((unsigned)(w * b.stagger_ns));
-    Prep cur = locate(claim());
-    if (lane == 0) start_copy(cur);
-    Prep nxt = locate(next_item(cur.item));
-    uint32_t n_done = 0;
+    uint32_t item = claim(), rec = 0, n_done = 0;
+    locate(item, 0);
+    if (lane == 0) start_copy(0);
+    uint32_t nitem = next_item(item);
+    locate(nitem, 1);
 
-    while (cur.item < it_end) {
-        const uint32_t a = (cur.packed >> 3) & 3u, zlo = (cur.packed >> 5) & 0xfffu, zhi = cur.packed >> 17;
+    while (item < it_end) {
+        __syncwarp();  // lane 0's record
+        const uint32_t packed = recs[rec].packed;
+        const uint32_t a = (packed >> 3) & 3u, zlo = (packed >> 5) & 0xfffu, zhi = packed >> 17;
         float* stage = sptr<float>(region + kPowerBytes) + a;  // span position 0
         wait(bar_raw, n_done & 1, kErrRawWait);
         if (zlo > 0 || zhi < (uint32_t)span_len) {  // edge item: zeros outside the clip (after the copy, which rounds outwards)
@@ -280,7 +295,7 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, int w, int lane, int n_mels) {
                 __syncwarp();
                 // the staging area is free again: start the copy of the next item's frames
                 fence_proxy_async();
-                if (lane == 0) start_copy(nxt);
+                if (lane == 0) start_copy(rec_after(rec));
             }
         }
         {   // separation of the packed frames, power, bf16 (hi, lo) split, B tile rows
@@ -320,14 +335,8 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, int w, int lane, int n_mels) {
         __syncwarp();
         tc_fence_after();     // after the epilogue's tcgen05.ld of this accumulator (its mbarrier arrive was observed)
         if (elect_one()) {
-            TcMeta m;
-            m.row0 = cur.row0;
-            m.clip = cur.clip;
-            m.nvalid = (int)(cur.packed & 7u);
-            m.pad_ = 0;
-            sptr<TcMeta>(L::meta)[w] = m;
             const uint32_t slot = atomicAdd(sptr<uint32_t>(L::tail), 1u) % kRing;
-            sptr<uint32_t>(L::done_who)[slot] = (uint32_t)w;
+            sptr<uint32_t>(L::done_who)[slot] = (uint32_t)w | (rec << 8);
             __threadfence_block();  // meta record and ring entry before the barrier the commits complete
             const uint32_t desc_lo = tile_addr >> 4;
             const uint32_t d_tmem = kTmemD + kDCols * w;  // tensor-memory base is 0 (all 512 columns are ours; checked at start)
@@ -340,8 +349,10 @@ HMFE_TC_D void fft_role(const LogmelBatch& b, int w, int lane, int n_mels) {
         __syncwarp();
         ++n_done;
         // registers are free here: locate the item after the next one
-        cur = nxt;
-        nxt = locate(next_item(cur.item));
+        rec = rec_after(rec);
+        item = nitem;
+        nitem = next_item(item);
+        locate(nitem, rec_after(rec));
     }
     // all of this warp's accumulators have been produced before it reports completion
     wait(bar_full, n_done & 1, kErrFullWait);
@@ -365,11 +376,14 @@ HMFE_TC_D void epilogue_role(const LogmelBatch& b, uint32_t tmem, int q, int lan
     const uint32_t done_seq = saddr(L::done_seq);
     for (uint32_t seq = 0; seq < (1u << 30); ++seq) {
         const uint32_t slot = seq % kRing;
-        if (!mbar_wait(done_seq + 8u * slot, (seq / kRing) & 1u)) break;
-        const uint32_t w = *reinterpret_cast<volatile uint32_t*>(sptr<uint32_t>(L::done_who) + slot);
-        if (w == kSentinel) return;
+        if (!(HMFE_TC_EPI_SPIN ? mbar_spin(done_seq + 8u * slot, (seq / kRing) & 1u) : mbar_wait(done_seq + 8u * slot, (seq / kRing) & 1u))) break;
+        const uint32_t who = *reinterpret_cast<volatile uint32_t*>(sptr<uint32_t>(L::done_who) + slot);
+        if (who == kSentinel) return;
+        const uint32_t w = who & 0xffu;
         tc_fence_after();
-        const TcMeta m = sptr<TcMeta>(L::meta)[w];
+        const uint4 m4 = *reinterpret_cast<const uint4*>(sptr<TcMeta>(L::meta) + 3 * w + (who >> 8));
+        const uint32_t row0 = m4.x, clip = m4.y;
+        const int nvalid = (int)(m4.z & 7u);
         uint32_t v[8];
         tmem_ld8(tmem + kTmemD + kDCols * w + ((uint32_t)(32 * q) << 16), v);
         tmem_wait_ld();
@@ -385,8 +399,8 @@ HMFE_TC_D void epilogue_role(const LogmelBatch& b, uint32_t tmem, int q, int lan
         }
         const float va = fsel ? d[2] : d[0], vb = fsel ? d[3] : d[1];
         const int fa = 2 * fsel, fb = fa + 1;
-        const bool oka = col < n_mels && fa < m.nvalid, okb = col < n_mels && fb < m.nvalid;
-        float* out = b.out + (int64_t)m.row0 * n_mels;
+        const bool oka = col < n_mels && fa < nvalid, okb = col < n_mels && fb < nvalid;
+        float* out = b.out + (int64_t)row0 * n_mels;
         if (oka) out[(int64_t)fa * n_mels + col] = va;
         if (okb) out[(int64_t)fb * n_mels + col] = vb;
         uint32_t hi = 0u, lo = 0x7f800000u;
@@ -402,8 +416,8 @@ HMFE_TC_D void epilogue_role(const LogmelBatch& b, uint32_t tmem, int q, int lan
         hi = __reduce_max_sync(0xffffffffu, hi);  // non-negative floats order like their bit patterns
         lo = __reduce_min_sync(0xffffffffu, lo);
         if (lane == 0) {
-            atomicMax(b.stats + 2 * (int64_t)m.clip, hi);
-            atomicMin(b.stats + 2 * (int64_t)m.clip + 1, lo);
+            atomicMax(b.stats + 2 * (int64_t)clip, hi);
+            atomicMin(b.stats + 2 * (int64_t)clip + 1, lo);
         }
     }
     if (lane == 0) atomicOr(b.status, kErrEpiSpin);

@@ -51,6 +51,14 @@ HMFE_TC_D bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // non-blocking 
         : "memory");
     return ok != 0;
 }
+// A suspend-time hint on try_wait (20 us) was measured: fewer polls, but c1 0.327 -> 0.338 ms (later wake-ups).
+// Busy poll without suspension (latency-critical waiters); false = gave up
+HMFE_TC_D bool mbar_spin(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (kSpinLimit << 4); ++i)
+        if (mbar_test_wait(bar, parity)) return true;
+    return false;
+}
 // false = gave up (protocol error)
 HMFE_TC_D bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;  // the common case: one test, no loop
