@@ -25,6 +25,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "api_common.h"
@@ -628,6 +629,324 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
     }
 }
 
+// ------------------------------------------------------------------------------ overlap, 128-bit rows, pipelined cascade
+// The same pass with the recurrence re-timed: one TICK advances every section by one sample, section s working on
+// the sample section s - 1 finished in the tick before (a systolic cascade; the values travel in the registers
+// p[1..S-1]).  Every section sees the same inputs and does the same operations in the same order as cascade(), so the
+// result is bit-identical; the output of a sample leaves the last section S - 1 ticks after the sample went in.
+// What changes is the shape of the dependency graph: the S section steps of a tick are independent of each other,
+// so a ROLLED loop of four ticks per iteration has all the instruction-level parallelism there is, with nothing to
+// drain or refill at its back edge.  That rolled loop is what lets the shared-memory reads be software-pipelined by
+// hand: ptxas sank the LDS.128 of the unrolled 32-sample block of iir_overlap4_kernel to ~30 instructions before their
+// first use whatever the source said, and ncu showed the first conversion of every float4 waiting on the shared-memory
+// scoreboard (9.5 % of the kernel's stall samples).  Here the float4 of input unit i + 2 is requested, and the one of
+// unit i + 1 converted to double, while the ticks of unit i run.
+// To keep outputs and 16-byte tile columns aligned the pipeline delay is padded to a multiple of four ticks
+// (D = 4 DU; S = 5: exactly 4), and the INPUT side runs DU units ahead: iteration k of the block loop produces the
+// outputs of block k from the input units DU .. 7 + DU of block k, i.e. it needs block k + 1 resident as well.
+template <int S, bool BP>
+struct IirPipe {
+    static constexpr int DU = S > 1 ? (S - 1 + 3) / 4 : 0;  // delay in 4-sample units
+    static constexpr int E = 4 * DU - (S - 1);              // extra single-sample delays behind the last section
+    double z1[S], z2[S], p[S];
+    float dl[E > 0 ? E : 1];
+    HMFE_D void reset() {
+#pragma unroll
+        for (int k = 0; k < S; ++k) z1[k] = z2[k] = p[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < (E > 0 ? E : 1); ++k) dl[k] = 0.0f;
+    }
+    // x enters section 0; returns the output of the sample that entered 4 DU ticks ago (the caller rounds it to float,
+    // like the (float) cast of the other one-pass kernels)
+    HMFE_D double tick(const IirCoef<S>& cf, double x) {
+        double out = 0.0;
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {
+            const double v = s == 0 ? x : p[s];
+            double y;
+            if (BP) {  // b = (1, 0, -1), as in cascade()
+                y = v + z1[s];
+                z1[s] = fma(-cf.a1[s], y, z2[s]);
+                z2[s] = fma(-cf.a2[s], y, -v);
+            } else {
+                y = fma(cf.b0[s], v, z1[s]);
+                z1[s] = fma(cf.b1[s], v, fma(-cf.a1[s], y, z2[s]));
+                z2[s] = fma(cf.b2[s], v, -cf.a2[s] * y);
+            }
+            if (s == S - 1)
+                out = y;
+            else
+                p[s + 1] = y;
+        }
+        if (E > 0) {  // (only for section counts other than 1 and 5) pad the delay to a multiple of four ticks
+            const float f = (float)out;
+            const float g = dl[E - 1];
+#pragma unroll
+            for (int k = E - 1; k > 0; --k) dl[k] = dl[k - 1];
+            dl[0] = f;
+            return (double)g;  // exact: the value was rounded to float on the way in
+        }
+        return out;
+    }
+};
+
+template <int S, bool BP, bool POWER>
+__global__ void __launch_bounds__(kIirWarps * 32, 3) iir_pipe4_kernel(const IirOverlap4Batch b, const IirCoef<S> cf) {
+    using Pipe = IirPipe<S, BP>;
+    constexpr int DU = Pipe::DU;
+    constexpr int kPending = DU > 0 ? kRing - 2 : kRing - 1;  // cp.async groups that may still be in flight at a block's start
+    extern __shared__ __align__(16) unsigned char iir_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float gain = BP ? (float)cf.gain : 1.0f;
+    float(*tile)[kRow4] = reinterpret_cast<float(*)[kRow4]>(iir_smem) + warp * 32;
+    IirRow4* rows = reinterpret_cast<IirRow4*>(iir_smem + (size_t)kIirWarps * 32 * kRow4 * sizeof(float)) + warp * 32;
+    const int64_t g = ((int64_t)blockIdx.x * kIirWarps + warp) * 32 + lane;
+    IirRow4 me{0, 0, 0};
+    int64_t group_base = 0;
+    if (g < b.n_chunks) {
+        int64_t lo = 0, hi = b.n_clips;  // largest clip with chunk_prefix[clip] <= g
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (b.chunk_prefix[mid] <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int64_t j = g - b.chunk_prefix[lo];
+        const int64_t c0 = b.clip_off[lo], n = b.clip_off[lo + 1] - c0;
+        const int s = (int)((c0 + b.align) & 3);
+        const int64_t p0 = j * b.C;  // aligned-coordinate start of this chunk
+        me.base = c0 - s + p0 - b.W;
+        me.lo = (int)max((int64_t)0, (int64_t)s + b.W - p0);
+        me.hi = b.W + (int)min((int64_t)b.C, (int64_t)s + n - p0);
+        if (POWER) group_base = b.group_off[lo] + j * (b.C / b.hop);
+    }
+    rows[lane] = me;
+    __syncwarp();
+    const int hi_self = me.hi;
+    const int valid_len = me.hi - b.W;  // chunk positions [0, valid_len) exist (<= 0 for idle lanes)
+    const int t_end = b.W + b.C;
+    int t_first = me.hi > me.lo ? (me.lo & ~31) : t_end;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, d));
+    const int edge_lo = (me.hi > me.lo && (me.lo & 3)) ? (me.lo >> 5) : -1;
+    const int edge_hi = (me.hi > me.lo && (me.hi & 3)) ? (me.hi >> 5) : -1;
+    const int rsub = lane >> 3, c4 = 4 * (lane & 7);
+    IirRow4 mv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mv[i] = rows[4 * i + rsub];
+
+    auto issue_load = [&](int tb) {  // stream positions [tb, tb + 32) of every row -> column block (tb >> 5) % kRing
+        const int col = 32 * ((tb >> 5) % kRing) + c4;
+        const int t = tb + c4;
+        const bool edge = __any_sync(0xffffffffu, edge_lo == (tb >> 5) || edge_hi == (tb >> 5));
+        if (!edge) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool in = t >= mv[i].lo && t < mv[i].hi;
+                cp_async16(&tile[4 * i + rsub][col], in ? (const void*)(b.x + mv[i].base + t) : (const void*)b.x, in ? 16 : 0);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool in = t + c >= mv[i].lo && t + c < mv[i].hi;
+                    cp_async4(&tile[4 * i + rsub][col + c], in ? (const void*)(b.x + mv[i].base + t + c) : (const void*)b.x,
+                              in ? 4 : 0);
+                }
+        }
+    };
+#pragma unroll 1
+    for (int k = 0; k < kRing; ++k) {
+        if (t_first + 32 * k < t_end) issue_load(t_first + 32 * k);
+        cp_async_commit();
+    }
+
+    // this lane's row: the float4 at stream position t (a multiple of 4).  Positions beyond the end of the stream read
+    // whatever the ring holds: they only reach outputs beyond the end, which are neither stored nor counted.
+    static_assert((kRing & (kRing - 1)) == 0, "the ring offset is a mask");
+    const unsigned my_row = (unsigned)__cvta_generic_to_shared(&tile[lane][0]);
+    auto fetch = [&](int t) -> float4 {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(my_row + 4u * ((unsigned)t & (32u * kRing - 1u))));
+        return v;
+    };
+    Pipe pipe;
+    pipe.reset();
+    double xin[4] = {0.0, 0.0, 0.0, 0.0};       // input unit that enters the pipeline next, converted
+    float4 raw1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // the unit after it
+    int tin = t_first;                           // stream position of the unit in xin
+    if (t_first < t_end) {
+        cp_async_wait<kPending>();
+        __syncwarp();
+        if (DU > 0) {  // prime the pipeline: the first DU input units produce no output
+#pragma unroll 1
+            for (int i = 0; i < DU; ++i) {
+                const float4 v = fetch(tin);
+                pipe.tick(cf, (double)v.x);
+                pipe.tick(cf, (double)v.y);
+                pipe.tick(cf, (double)v.z);
+                pipe.tick(cf, (double)v.w);
+                tin += 4;
+            }
+        }
+        const float4 v = fetch(tin);
+        xin[0] = (double)v.x;
+        xin[1] = (double)v.y;
+        xin[2] = (double)v.z;
+        xin[3] = (double)v.w;
+        raw1 = fetch(tin + 4);
+    }
+
+    float head[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q[4] = {0.0f, 0.0f, 0.0f, 0.0f}, grp = 0.0f;
+    int gidx = 0, pos_in_group = 0;
+#pragma unroll 1
+    for (int tb = t_first; tb < t_end; tb += 32) {
+        cp_async_wait<kPending>();  // blocks tb and (input look-ahead) tb + 32 are resident
+        __syncwarp();
+        const int col0 = 32 * ((tb >> 5) % kRing);
+        const bool emit = tb >= b.W;  // warp uniform
+        bool group_start = false;
+        if (POWER && emit) {
+            if (pos_in_group == b.hop) {  // a group is complete (warp uniform)
+                if (gidx * b.hop < valid_len) {
+                    float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
+                    dst[0] = make_float4(grp, q[0], q[1], q[2]);
+                    dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
+                }
+                ++gidx;
+                pos_in_group = 0;
+                grp = 0.0f;
+            }
+            group_start = pos_in_group == 0;
+            pos_in_group += 32;
+        }
+        // ---- filter: the eight output units of this lane's row.  The rounding / gain / energy / store of unit u - 1
+        // is written between the request for input unit u + 2 and the ticks of unit u, which it does not depend on.
+        const int rem = hi_self - tb;  // outputs at block positions >= rem lie beyond the clip: no energy from them
+        float body = 0.0f;
+        const unsigned out_row = my_row + 4u * (unsigned)col0;
+        auto block = [&](auto emit_c, auto mask_c) {
+            constexpr bool EMIT = decltype(emit_c)::value, MASK = decltype(mask_c)::value;
+            double yq[4];
+            auto ticks = [&]() {
+                yq[0] = pipe.tick(cf, xin[0]);
+                yq[1] = pipe.tick(cf, xin[1]);
+                yq[2] = pipe.tick(cf, xin[2]);
+                yq[3] = pipe.tick(cf, xin[3]);
+            };
+            auto finish = [&](int u) {  // output unit u from yq
+                if (!EMIT) return;
+                float4 o;
+                o.x = (float)yq[0] * gain;
+                o.y = (float)yq[1] * gain;
+                o.z = (float)yq[2] * gain;
+                o.w = (float)yq[3] * gain;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + 16u * (unsigned)u), "f"(o.x), "f"(o.y),
+                             "f"(o.z), "f"(o.w)
+                             : "memory");
+                if (POWER) {
+                    float e0 = o.x, e1 = o.y, e2 = o.z, e3 = o.w;
+                    if (MASK) {
+                        const int r = rem - 4 * u;  // valid outputs of this unit
+                        e0 = r > 0 ? e0 : 0.0f;
+                        e1 = r > 1 ? e1 : 0.0f;
+                        e2 = r > 2 ? e2 : 0.0f;
+                        e3 = r > 3 ? e3 : 0.0f;
+                    }
+                    if (u == 0) {
+                        head[0] = e0 * e0;
+                        head[1] = e1 * e1;
+                        head[2] = e2 * e2;
+                        head[3] = e3 * e3;
+                    } else {
+                        body = fmaf(e0, e0, body);
+                        body = fmaf(e1, e1, body);
+                        body = fmaf(e2, e2, body);
+                        body = fmaf(e3, e3, body);
+                    }
+                }
+            };
+            auto advance = [&](const float4& raw2) {
+                xin[0] = (double)raw1.x;
+                xin[1] = (double)raw1.y;
+                xin[2] = (double)raw1.z;
+                xin[3] = (double)raw1.w;
+                raw1 = raw2;
+                tin += 4;
+            };
+            {
+                const float4 raw2 = fetch(tin + 8);
+                ticks();
+                advance(raw2);
+            }
+#pragma unroll 1
+            for (int u = 1; u < 8; ++u) {
+                const float4 raw2 = fetch(tin + 8);
+                finish(u - 1);
+                ticks();
+                advance(raw2);
+            }
+            finish(7);
+        };
+        // warp-uniform choice (a per-lane branch would run the recurrence twice for a warp that holds the last chunk of a
+        // clip): the masked variant whenever some row ends inside or before this block
+        if (!emit)
+            block(std::false_type{}, std::false_type{});
+        else if (!__any_sync(0xffffffffu, rem < 32))
+            block(std::true_type{}, std::false_type{});
+        else
+            block(std::true_type{}, std::true_type{});
+        if (POWER && emit) {
+            if (group_start) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q[c] = head[c];
+            } else {
+                body += (head[0] + head[1]) + (head[2] + head[3]);
+            }
+            grp += body;
+        }
+        __syncwarp();
+        // ---- store: rows 4*i + rsub, positions tb + c4 .. + 3
+        if (emit) {
+            const int t = tb + c4;
+            const bool edge = __any_sync(0xffffffffu, edge_lo == (tb >> 5) || edge_hi == (tb >> 5));
+            if (!edge) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int olo = max(mv[i].lo, b.W);
+                    if (t >= olo && t < mv[i].hi)
+                        *reinterpret_cast<float4*>(b.y32 + mv[i].base + t) =
+                            *reinterpret_cast<const float4*>(&tile[4 * i + rsub][col0 + c4]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int olo = max(mv[i].lo, b.W);
+                    const float4 v = *reinterpret_cast<const float4*>(&tile[4 * i + rsub][col0 + c4]);
+                    const float* e = reinterpret_cast<const float*>(&v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (t + c >= olo && t + c < mv[i].hi) b.y32[mv[i].base + t + c] = e[c];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- hand the column block to stream block tb + 32 * kRing
+        if (tb + 32 * kRing < t_end) issue_load(tb + 32 * kRing);
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    if (POWER && gidx * b.hop < valid_len) {  // the last group of the chunk
+        float4* dst = reinterpret_cast<float4*>(b.group_energy + (group_base + gidx) * 8);
+        dst[0] = make_float4(grp, q[0], q[1], q[2]);
+        dst[1] = make_float4(q[3], 0.0f, 0.0f, 0.0f);
+    }
+}
+
 // Same for the aligned-coordinate groups of iir_overlap4_kernel: hop block h of a clip whose first
 // sample sits at alignment slot s is {first squares e >= s of group h} + {rest of group h} +
 // {first squares e < s of group h+1}.
@@ -867,8 +1186,32 @@ static int iir_conv_mode() {
     return mode;
 }
 
+// 0 (default): iir_overlap4_kernel; 1: iir_pipe4_kernel, the pipelined cascade (HMFE_IIR_PIPE overrides, for A/B runs).
+// Measured on B200, c2 (1.78 G samples): 3.54 ms against 3.61 ms.  The pipelined form removed what ncu had blamed in the
+// unrolled one (shared-memory scoreboard stalls on the first conversion of every float4: 9.5 % -> 0) and runs 29
+// instead of 27.7 instructions per sample; both end at 51 % of the FP64 pipe, with ~35 % of the warps' time in the
+// per-block load / store / hand-over code that neither form changes.
+static int iir_pipe_mode() {
+    static const int mode = [] {
+        const char* e = getenv("HMFE_IIR_PIPE");
+        return e ? atoi(e) : 0;
+    }();
+    return mode;
+}
+
+template <int S, bool BP, bool POWER>
+static int launch_pipe4(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
+    auto kern = iir_pipe4_kernel<S, BP, POWER>;
+    HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOverlap4Smem));
+    const unsigned grid = (unsigned)((b.n_chunks + kIirWarps * 32 - 1) / (kIirWarps * 32));
+    kern<<<grid, kIirWarps * 32, kOverlap4Smem, st>>>(b, cf);
+    HMFE_CHECK_CUDA(cudaGetLastError());
+    return HMFE_OK;
+}
+
 template <int S, bool BP, bool POWER>
 static int launch_overlap4_k(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
+    if (iir_pipe_mode() != 0 && iir_conv_mode() == 0) return launch_pipe4<S, BP, POWER>(b, cf, st);
     switch (iir_conv_mode()) {
         case 1: return launch_overlap4_c<S, BP, POWER, 1>(b, cf, st);
         case 3: return launch_overlap4_c<S, BP, POWER, 3>(b, cf, st);
