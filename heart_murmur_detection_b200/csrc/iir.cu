@@ -1190,7 +1190,10 @@ static int iir_conv_mode() {
 // Measured on B200, c2 (1.78 G samples): 3.54 ms against 3.61 ms.  The pipelined form removed what ncu had blamed in the
 // unrolled one (shared-memory scoreboard stalls on the first conversion of every float4: 9.5 % -> 0) and runs 29
 // instead of 27.7 instructions per sample; both end at 51 % of the FP64 pipe, with ~35 % of the warps' time in the
-// per-block load / store / hand-over code that neither form changes.
+// per-block load / store / hand-over code that neither form changes.  A third form moved every lane's row with one
+// cp.async.bulk per block and direction (no cross-lane phase at all, 101 registers): 4.36 ms - the bulk-copy instruction
+// takes its operands from uniform registers, so 32 different per-lane copies become a 32-trip ELECT / R2UR / UBLKCP
+// loop per warp (ncu: 31.5 trips per block, 41 % of the stall samples fixed-latency waits in it); removed.
 static int iir_pipe_mode() {
     static const int mode = [] {
         const char* e = getenv("HMFE_IIR_PIPE");

@@ -81,6 +81,21 @@ HMFE_TC_D void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint
                  : "memory");
 }
 
+// shared -> global, completion tracked by the thread's bulk async-groups (no mbarrier)
+HMFE_TC_D void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+HMFE_TC_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of the thread's bulk groups have not finished READING their shared-memory source
+template <int N>
+HMFE_TC_D void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+HMFE_TC_D void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tensor memory
 // one full warp; the base address is written to *dst_smem
 HMFE_TC_D void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
