@@ -441,6 +441,15 @@ logmel_finalize_kernel(const LogmelBatch b, int n_mels, int out_mode, float amin
 
 using namespace hmfe;
 
+namespace hmfe {  // logmel_generic.cu
+bool generic_shape_ok(int n_fft);
+void generic_tables(int n_fft, int n_mels, const std::vector<float>& mel_dense, std::vector<float>& win, std::vector<float>& tw,
+                    std::vector<int>& lo, std::vector<int>& hi);
+int launch_logmel_generic(hmfe_logmel_plan* p, const LogmelBatch& b, int64_t n_frames, cudaStream_t st);
+}  // namespace hmfe
+
+constexpr int kVariantGeneric = 5;  // internal: n_fft != 1024
+
 namespace hmfe {  // logmel_tc.cu
 std::vector<uint32_t> tc_build_a_words(const std::vector<float>& mel_dense, int n_mels, int n_bins);
 bool tc_shape_ok(const hmfe_logmel_plan* p);
@@ -523,7 +532,8 @@ static int run_logmel(hmfe_logmel_plan* p, const LogmelBatch& b, int out_mode, c
         }
         HMFE_CHECK_CUDA(cudaEventRecord(ev[0], st));
     }
-    int rc = p->variant == HMFE_VARIANT_TC       ? launch_logmel_tc(p, b, st)
+    int rc = p->variant == kVariantGeneric       ? launch_logmel_generic(p, b, b.n_frames_total, st)
+             : p->variant == HMFE_VARIANT_TC     ? launch_logmel_tc(p, b, st)
              : p->variant == HMFE_VARIANT_PACKED ? launch_power<f32x2, 12, 1>(p, b, st)
              : p->variant == HMFE_VARIANT_PAIR   ? launch_pair(p, b, st)
                                                  : launch_power<float, 8, 2>(p, b, st);
@@ -546,8 +556,8 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
                             double f_max, int variant) {
     HMFE_REQUIRE(plan != nullptr, "plan is NULL");
     *plan = nullptr;
-    if (n_fft != kNfft) {
-        set_error("n_fft=%d unsupported: the kernel is specialised for n_fft=1024 (src/util.py:482)", n_fft);
+    if (n_fft != kNfft && !generic_shape_ok(n_fft)) {
+        set_error("n_fft=%d unsupported: powers of two from 64 to 4096 (the reference uses 1024, src/util.py:482)", n_fft);
         return HMFE_ERR_UNSUPPORTED;
     }
     HMFE_REQUIRE(hop >= 1 && hop <= 4096, "hop=%d out of range", hop);
@@ -568,6 +578,23 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
     p->variant = variant == HMFE_VARIANT_AUTO ? HMFE_VARIANT_PACKED : variant;
     p->sm_count = device_sm_count();
     p->mel_dense = mel_filterbank_slaney(sample_rate, n_fft, n_mels, f_min, f_max);
+    if (n_fft != kNfft) {  // the plain kernel of logmel_generic.cu, whatever variant was asked for
+        p->variant = kVariantGeneric;
+        std::vector<float> win, tw;
+        std::vector<int> lo, hi;
+        generic_tables(n_fft, n_mels, p->mel_dense, win, tw, lo, hi);
+        int rc = upload_vec(win, &p->d_win);
+        if (rc == HMFE_OK) rc = upload_vec(tw, reinterpret_cast<float**>(&p->d_tw));
+        if (rc == HMFE_OK) rc = upload_vec(p->mel_dense, &p->d_gen_mel);
+        if (rc == HMFE_OK) rc = upload_vec(lo, &p->d_gen_lo);
+        if (rc == HMFE_OK) rc = upload_vec(hi, &p->d_gen_hi);
+        if (rc != HMFE_OK) {
+            hmfe_logmel_plan_destroy(p);
+            return rc;
+        }
+        *plan = p;
+        return HMFE_OK;
+    }
     const int group = (p->variant == HMFE_VARIANT_PACKED || p->variant == HMFE_VARIANT_TC) ? 8 : 16;  // lanes per shared-memory phase (16 B / 8 B elements)
     const BandedMel bm = build_banded(p->mel_dense, n_mels, p->n_bins, group, kBinsPad);
     if (!verify_banded(bm, p->mel_dense, kBinsPad)) {
@@ -620,6 +647,9 @@ void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
     cudaFree(p->d_row);
     cudaFree(p->d_tc_a);
     cudaFree(p->d_tc_status);
+    cudaFree(p->d_gen_mel);
+    cudaFree(p->d_gen_lo);
+    cudaFree(p->d_gen_hi);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     delete p;
 }
@@ -627,6 +657,7 @@ void hmfe_logmel_plan_destroy(hmfe_logmel_plan* p) {
 int hmfe_logmel_plan_set_pad_mode(hmfe_logmel_plan* p, int pad_mode) {
     HMFE_REQUIRE(p, "NULL plan");
     HMFE_REQUIRE(pad_mode == HMFE_PAD_CONSTANT || pad_mode == HMFE_PAD_REFLECT, "bad pad_mode %d", pad_mode);
+    HMFE_REQUIRE(p->variant != kVariantGeneric || pad_mode == HMFE_PAD_CONSTANT, "reflect padding needs n_fft = 1024");
     if (pad_mode == HMFE_PAD_REFLECT && p->variant == HMFE_VARIANT_TC) p->variant = HMFE_VARIANT_PACKED;  // same tables
     if (pad_mode == HMFE_PAD_REFLECT && p->variant != HMFE_VARIANT_PACKED) {
         set_error("reflect padding is built for the default (packed) variant only");
@@ -733,6 +764,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
         b.uniform_T = (int)T;
         b.uniform_items = (int)((T + FR - 1) / FR);
         b.n_items = (int64_t)b.uniform_items * n_clips;
+        b.n_frames_total = T * n_clips;
     } else {
         int64_t* hs = static_cast<int64_t*>(hbuf);
         int64_t* hl = hs + n_clips;
@@ -747,6 +779,7 @@ int hmfe_logmel_batch_views2(hmfe_logmel_plan* p, const float* d_wav, const floa
             hi[i + 1] = hi[i] + (T + FR - 1) / FR;
         }
         b.n_items = hi[n_clips];
+        b.n_frames_total = hf[n_clips];
         int64_t* dc = static_cast<int64_t*>(dbuf);
         b.clip_start = dc;
         b.clip_len = dc + n_clips;
@@ -778,6 +811,10 @@ int hmfe_logmel_batch_device(hmfe_logmel_plan* p, const float* d_wav, const floa
     HMFE_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0,
                  "d_out and d_workspace must be 16-byte aligned");
     HMFE_REQUIRE(p->pad_mode == HMFE_PAD_CONSTANT, "device-planned batches use constant padding");
+    if (p->variant == kVariantGeneric) {
+        set_error("device-planned batches need n_fft = 1024 (use hmfe_logmel_batch_views for other frame lengths)");
+        return HMFE_ERR_UNSUPPORTED;
+    }
     LogmelBatch b{};
     b.wav = d_wav;
     b.wav_alt = d_wav_alt ? d_wav_alt : d_wav;

@@ -29,6 +29,7 @@ struct LogmelBatch {
     unsigned* stats;             // [n_clips][2] : max bits, min bits of the clip's mel power
     unsigned long long* queue;   // next unclaimed work item (dynamic distribution over the warps)
     int64_t n_clips, n_items;
+    int64_t n_frames_total;      // host-planned batches: frames of the whole batch (logmel_generic.cu)
     const int64_t* n_items_dev;  // != NULL: the item count is item_prefix[n_clips] in device memory (device-planned batches)
     int uniform_n, uniform_T, uniform_items;  // > 0 when every clip has the same length
     int hop;
@@ -42,6 +43,14 @@ struct LogmelTables {
     const float* melw;  // [total_trip][32]
     const int* start;   // [n_slots][32]
     const int* row;     // [n_slots][32]
+};
+
+struct GenericTables {  // logmel_generic.cu (n_fft != 1024)
+    const float* win;   // [n_fft] periodic Hann
+    const float2* tw;   // [n_fft / 2] exp(-2 pi i k / n_fft)
+    const float* mel;   // [n_mels][n_fft / 2 + 1]
+    const int* lo;      // [n_mels] first / one past the last non-zero bin of the row
+    const int* hi;
 };
 
 HMFE_D float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -117,6 +126,10 @@ struct hmfe_logmel_plan {
     float *d_win = nullptr, *d_melw = nullptr;
     float2* d_tw = nullptr;
     int *d_start = nullptr, *d_row = nullptr;
+    // n_fft != 1024 (logmel_generic.cu): dense mel basis and the non-zero range of its rows; d_win / d_tw hold the
+    // full Hann window and the n_fft / 2 twiddles in that case
+    float* d_gen_mel = nullptr;
+    int *d_gen_lo = nullptr, *d_gen_hi = nullptr;
     size_t table_smem = 0;
     // tensor-core variant (logmel_tc.cu): mel weights as bf16 (hi, lo) pairs in the tensor-memory A layout, and the
     // status word its bounded waits report protocol errors through

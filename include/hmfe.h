@@ -54,9 +54,11 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 #define HMFE_VARIANT_PAIR 3   /* one complex FFT, FFMA2 across element pairs, 20 warps / SM */
 #define HMFE_VARIANT_TC 4     /* FFT as PACKED; mel projection on the tensor cores (tcgen05.mma, accumulators in tensor
                                  memory, bf16 hi/lo split of weights and powers), frames staged by bulk asynchronous
-                                 copies; warp-specialised (FFT / MMA / epilogue warps).  n_mels <= 64, hop <= 512 */
+                                 copies; warp-specialised (FFT + MMA issue / epilogue warps).  n_mels <= 64, hop <= 512 */
 
-/* n_fft must be 1024 (the only value the reference uses); n_mels a multiple of 32, <= 256. */
+/* n_fft = 1024 (the only value the reference uses) runs the register-resident kernels selected by `variant`; other powers of
+ * two from 64 to 4096 run a plain shared-memory FFT kernel (pre_process_audio_mel_t takes nfft as an argument,
+ * src/util.py:482); anything else is HMFE_ERR_UNSUPPORTED.  n_mels a multiple of 32, <= 256. */
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
                             double f_max, int variant);
 void hmfe_logmel_plan_destroy(hmfe_logmel_plan* plan);

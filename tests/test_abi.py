@@ -37,7 +37,7 @@ def test_argument_validation_without_gpu():
     from heart_murmur_detection_b200 import _lib
 
     h = ctypes.c_void_p()
-    rc = _lib.hmfe_logmel_plan_create(ctypes.byref(h), 16000, 2048, 512, 64, 50.0, 8000.0, 0)
+    rc = _lib.hmfe_logmel_plan_create(ctypes.byref(h), 16000, 1000, 512, 64, 50.0, 8000.0, 0)  # not a power of two
     assert rc == -3 and b"n_fft" in _lib.hmfe_last_error()
     rc = _lib.hmfe_logmel_plan_create(ctypes.byref(h), 16000, 1024, 512, 50, 50.0, 8000.0, 0)
     assert rc == -1
