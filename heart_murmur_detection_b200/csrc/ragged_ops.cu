@@ -240,7 +240,10 @@ struct EntirePlanArgs {
     const int64_t* start_end;  // [n][2] trim indices, clip relative
     int64_t n_clips;
     double sample_rate, input_sec, max_sec;  // max_sec <= 0: no cut
-    int pad, pad_zero;                       // pad: pad short clips; pad_zero: types == "zero" (else "repeat")
+    int pad, pad_zero;                       // pad: pad short clips; pad_zero: types == "zero" (else "repeat"); 2: zero padding,
+                                             // and clips that only get trailing zeros (>= half the length) are NOT copied:
+                                             // out_len keeps their own length, frame_off counts the padded one, and the
+                                             // log-mel fetch reads zeros behind the clip end anyway
     int hop, item_frames;
     int64_t dst_base;  // first element of the padded copies in their buffer
     int alt;           // padded copies live in a second buffer: start = -(offset + 1)
@@ -271,8 +274,16 @@ __global__ void __launch_bounds__(1024) entire_plan_kernel(const EntirePlanArgs 
             len = n;
             if (a.max_sec > 0 && dur > a.max_sec) len = min(len, (long long)(a.max_sec * a.sample_rate));
             padded = (valid && is_short) ? 1 : 0;
-            if (padded) len = L;
-            T = valid ? 1 + len / a.hop : 0;
+            long long len_frames = len;
+            if (padded) {
+                len_frames = L;
+                // _zero_padding with frac >= 0.5: the clip followed by zeros (src/util.py:518-520)
+                if (a.pad_zero == 2 && !((double)n / (double)L < 0.5))
+                    padded = 0;  // a view: out_len = n
+                else
+                    len = L;
+            }
+            T = valid ? 1 + len_frames / a.hop : 0;
             items = (T + a.item_frames - 1) / a.item_frames;
         }
         // block-wide exclusive scans of (T, items, padded)

@@ -39,11 +39,15 @@ class ChunkBatch:
     is_view: np.ndarray | None = None   # [n_chunks] True for straight views (no padding applied)
     filtered: bool = False              # band-pass applied (the reference's data is float64 then)
     alt: torch.Tensor | None = None     # padded copies kept apart from a read-only signal: start s < 0 -> alt[-s-1:]
+    stored: np.ndarray | None = None    # [n_chunks] samples of the chunk that exist in memory; the rest of ``lengths`` is zeros
+                                        # that were never written (zero padding as a view, entire_signal_device)
 
     def samples(self, k: int) -> torch.Tensor:
-        """Device view of chunk k."""
+        """Device view of chunk k (a zero-padded copy when its trailing zeros were never materialised)."""
         s, n = int(self.starts[k]), int(self.lengths[k])
-        return self.work[s : s + n] if s >= 0 else self.alt[-s - 1 : -s - 1 + n]
+        m = n if self.stored is None else int(self.stored[k])
+        x = self.work[s : s + m] if s >= 0 else self.alt[-s - 1 : -s - 1 + m]
+        return x if m == n else torch.cat([x, x.new_zeros(n - m)])
 
     def ref_dtype(self, k: int):
         """dtype the reference produces for chunk k: float64 for untouched views of band-passed
@@ -279,9 +283,9 @@ class DeviceFeatures:
     the rows of the kept recordings back to back (its row count is only an upper bound until ``resolve``);
     ``resolve()`` waits for the small descriptor copy and returns the usual FeatureBatch with host-side offsets."""
 
-    def __init__(self, features, work, alt, h_meta, event, n_clips, total, L, filtered, types, launches, keep_alive):
+    def __init__(self, features, work, alt, h_meta, event, n_clips, total, L, filtered, types, launches, keep_alive, max_len=0):
         self.features, self.work, self.alt = features, work, alt
-        self._h_meta, self._event, self._n, self._total, self._L = h_meta, event, n_clips, total, L
+        self._h_meta, self._event, self._n, self._total, self._L, self._max_len = h_meta, event, n_clips, total, L, max_len
         self._filtered, self._types, self.launches, self._keep = filtered, types, launches, keep_alive
         self._fb = None
 
@@ -298,11 +302,14 @@ class DeviceFeatures:
             nn = se[:, 1] - se[:, 0]
             valid = np.zeros(n, dtype=bool)
             valid[keep] = True
-            padded = (lengths[keep] == self._L) & (nn[keep] < self._L)
+            nk = np.minimum(nn[keep], self._max_len) if self._max_len else nn[keep]
+            padded = nk < self._L                        # short recordings that were kept: chunk length L
+            stored = lengths[keep].copy()                # < L where only trailing zeros were added and nothing was copied
+            chunk_len = np.where(padded, self._L, stored)
             is_view = ~padded
             dup = bool(padded.any()) and self._types != "zero"
-            cb = ChunkBatch(self.work, starts[keep].copy(), lengths[keep].copy(), keep.astype(np.int64), n, valid, se, dup,
-                            self.launches, is_view, self._filtered, self.alt)
+            cb = ChunkBatch(self.work, starts[keep].copy(), chunk_len, keep.astype(np.int64), n, valid, se, dup,
+                            self.launches, is_view, self._filtered, self.alt, stored if bool((stored < chunk_len).any()) else None)
             ro = np.zeros(keep.size + 1, dtype=np.int64)
             np.cumsum(rows[keep], out=ro[1:])
             self._fb = FeatureBatch(self.features, ro, cb, self.launches)
@@ -378,7 +385,7 @@ def entire_signal_device(wav, offsets, input_sec=8, sample_rate=16000, butterwor
             if len(_dev_scratch) > 64:
                 _dev_scratch.pop(next(iter(_dev_scratch)))
         _lib.check(_lib.hmfe_entire_plan_batch(ctx._h, o.ctypes.data_as(C.c_void_p), n, C.c_void_p(se.data_ptr()), int(sample_rate),
-                                               float(input_sec), int(bool(pad)), int(types == "zero"), float(max_sec or 0.0), hop, 4,
+                                               float(input_sec), int(bool(pad)), 2 if types == "zero" else 0, float(max_sec or 0.0), hop, 4,
                                                dst_base, use_alt, C.c_void_p(sc["desc"].data_ptr()),
                                                C.c_void_p(sc["gather"].data_ptr()), fe._stream_ptr()), "hmfe_entire_plan_batch")
         launches += 1
@@ -400,7 +407,8 @@ def entire_signal_device(wav, offsets, input_sec=8, sample_rate=16000, butterwor
         h_meta[2 * n :].copy_(sc["desc"][: 3 * n + 1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-    return DeviceFeatures(out, signal, alt, h_meta, ev, n, total, L, sos is not None, types, launches, (se, sc))
+    return DeviceFeatures(out, signal, alt, h_meta, ev, n, total, L, sos is not None, types, launches, (se, sc),
+                          int(max_sec * sample_rate) if max_sec else 0)
 
 
 def entire_signal_batch(wav, offsets, input_sec=8, sample_rate=16000, butterworth_filter=None, spectrogram=False,

@@ -181,7 +181,10 @@ int hmfe_gather_batch(hmfe_ctx* ctx, const float* d_src, float* d_dst, const hmf
  * (dropped clips get zero rows) and the compact list d_gather[0 .. n_padded) of the padded copies for hmfe_gather_device
  * (room for n records; padded copy k of the batch goes to element dst_base + k * int(input_sec * sample_rate) of the destination;
  * with `alt` the clip start is encoded as -(offset + 1), the second-buffer convention of hmfe_logmel_batch_views2).
- * item_frames = frames per work item of the log-mel variant (4).  All outputs are caller-provided device memory. */
+ * item_frames = frames per work item of the log-mel variant (4).  All outputs are caller-provided device memory.
+ * pad_zero: 0 = _duplicate_padding ("repeat"), 1 = _zero_padding, 2 = _zero_padding without copying the clips that only get
+ * trailing zeros (at least half of input_sec long): clip_len keeps their own length while frame_off counts the padded one -
+ * hmfe_logmel_batch_device reads zeros behind the end of a clip, so the features are the same and the copy is saved. */
 int hmfe_entire_plan_batch(hmfe_ctx* ctx, const int64_t* h_offsets, int64_t n_clips, const int64_t* d_start_end,
                            int sample_rate, double input_sec, int pad, int pad_zero, double max_sec, int hop, int item_frames,
                            int64_t dst_base, int alt, int64_t* d_desc, hmfe_gather_desc* d_gather, void* stream);
