@@ -410,7 +410,7 @@ def bench_c4(dev, rank, n_total=100000, pool=2048, max_len=251, batch=64):
                     "i.e. consecutive batches of 64"}
 
 
-def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=1250, pool_chunks=4, passes=2):
+def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=5000, pool_chunks=2, passes=2):
     """BASELINE config 5, STRONG scaling: the job is fixed (1 M clips); chunks of `chunk` clips are dealt round-robin
     (dist.chunk_rounds), every rank writes its features in place into the global-order tensor and each round is
     completed by one in-place NCCL all-gather on a side stream, overlapped with the next round's kernels.  Input
@@ -421,8 +421,19 @@ def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=1250, po
     from heart_murmur_detection_b200 import dist as hd
     from heart_murmur_detection_b200 import frontend, synth
 
+    chunk = int(os.environ.get("HMFE_C5_CHUNK", chunk))  # clips per rank per round (A/B runs)
     n_samp, T = 8 * SR, 251
     pool = chunk * pool_chunks
+    group = None
+    # The sweep is bound by the all-gather, not by the kernels (N = 8: 36 ms of compute per job), so its collective gets a
+    # communicator of its own with more CTAs than NCCL's default, and 320 MB per rank and round.  Measured at N = 8:
+    # 1 250 clips per round, default CTAs 9.06 M clips/s (509 GB/s into every GPU); 5 000 clips 9.75 M; + 32 CTAs 9.88 M;
+    # + 64 CTAs 10.18 M (572 GB/s).  HMFE_C5_NCCL_CTAS=0 keeps the default communicator.
+    ctas = int(os.environ.get("HMFE_C5_NCCL_CTAS", 64))
+    if world > 1 and ctas > 0:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.min_ctas = opts.config.max_ctas = ctas
+        group = dist.new_group(ranks=list(range(world)), pg_options=opts)
     wav, _ = synth.make_batch(np.full(pool, n_samp, dtype=np.int64), base_seed=77_000_000, device=dev)  # same on every rank
     off = np.arange(chunk + 1, dtype=np.int64) * n_samp
     plan = frontend.logmel_plan(16000, 64, 50, 8000, 1024, 512, variant)
@@ -442,7 +453,7 @@ def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=1250, po
                 ev.record(main)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ev)
-                    hd.all_gather_round_inplace(final, j, rows_chunk)
+                    hd.all_gather_round_inplace(final, j, rows_chunk, group=group)
         main.wait_stream(comm)
 
     def timed(gather):
@@ -483,7 +494,7 @@ def bench_c5(dev, rank, world, variant="auto", n_total=1_000_000, chunk=1250, po
             "rounds": rounds, "chunk_clips": chunk, "pool_clips": pool,
             "gathered_bytes_per_rank": (world - 1) * (n_total // world) * T * 64 * 4,
             "nvlink_rx_gbs_per_gpu": ((world - 1) * (n_total // world) * T * 64 * 4) / (ms * 1e-3) / 1e9 if world > 1 else 0.0,
-            "collective": "none" if world == 1 else "in-place NCCL all_gather_into_tensor per round on a side stream",
+            "collective": "none" if world == 1 else f"in-place NCCL all_gather_into_tensor per round on a side stream, own communicator ({ctas or 'default'} CTAs)",
             "identity_check": {"sampled_clips": int(sample.size), "bit_identical_to_p1_on_every_rank": bool(flag.item()),
                                "how": "gathered rows of sampled global clips == the same clip run alone through the same plan"},
             "passes_timed": passes, "timing": "CUDA events around one whole job, barrier + synchronise both sides, max over ranks, best pass"}
@@ -751,9 +762,14 @@ def main():
     else:
         send = [torch.zeros((max_rows, n_cols), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
     out = send[0]
+    gather_group = None
     if world > 1 and peer_ag is None:
         gathered = [torch.empty((world * max_rows, n_cols), dtype=torch.float32, device=dev) for _ in range(2)]
         comm = torch.cuda.Stream(device=dev)
+        if int(os.environ.get("HMFE_GATHER_NCCL_CTAS", 0)) > 0:  # A/B: a communicator with a fixed CTA count for the step's gather
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.min_ctas = opts.config.max_ctas = int(os.environ["HMFE_GATHER_NCCL_CTAS"])
+            gather_group = dist.new_group(ranks=list(range(world)), pg_options=opts)
         ev_ready = [torch.cuda.Event() for _ in range(2)]
         ev_sent = [torch.cuda.Event() for _ in range(2)]
     step_no = [0]
@@ -774,7 +790,7 @@ def main():
             ev_ready[i].record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev_ready[i])
-                dist.all_gather_into_tensor(gathered[i], send[i])
+                dist.all_gather_into_tensor(gathered[i], send[i], group=gather_group)
                 ev_sent[i].record(comm)
 
     def barrier():
