@@ -54,7 +54,10 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 #define HMFE_VARIANT_PAIR 3   /* one complex FFT, FFMA2 across element pairs, 20 warps / SM */
 #define HMFE_VARIANT_TC 4     /* FFT as PACKED; mel projection on the tensor cores (tcgen05.mma, accumulators in tensor
                                  memory, bf16 hi/lo split of weights and powers), frames staged by bulk asynchronous
-                                 copies; warp-specialised (FFT + MMA issue / epilogue warps).  n_mels <= 64, hop <= 512 */
+                                 copies; warp-specialised (FFT + MMA issue / epilogue warps).  n_mels <= 64, hop <= 512.
+                                 The bulk copies move whole 16-byte granules: up to 12 bytes in front of the first and
+                                 behind the last sample of a clip are READ (never used) when the clip is not 16-byte
+                                 aligned - always inside a granule that holds samples of the buffer */
 
 /* n_fft = 1024 (the only value the reference uses) runs the register-resident kernels selected by `variant`; other powers of
  * two from 64 to 4096 run a plain shared-memory FFT kernel (pre_process_audio_mel_t takes nfft as an argument,
