@@ -1,4 +1,4 @@
-"""A/B of the one-pass band-pass kernel (run on the GPU box): HMFE_IIR_CONV=0|1|3 python tools/iir_ab.py"""
+"""A/B of the one-pass band-pass kernel (run on the GPU box): HMFE_IIR_CONV=0|1|3 python tools/iir_ab.py  (the integer-conversion variants 1 and 3 are compiled only with -DHMFE_IIR_BUILD_CONV_VARIANTS; HMFE_IIR_PIPE=1 selects the pipelined cascade)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
