@@ -48,3 +48,39 @@ def test_banded_mel_lane_assignment(host_check):
     assert rows[(8, 0)]["trip"] == 40 and rows[(8, 0)]["wf"] > rows[(8, 0)]["ideal"]
     assert rows[(8, 16)]["trip"] == 40 and rows[(8, 16)]["wf"] == rows[(8, 16)]["ideal"] == 80
     assert out[3].split() == ["assign", "total", "0", "distinct", "32"]
+
+
+def _bf16_rn(x):
+    """float32 -> bfloat16 (round to nearest even) -> float32, like cvt.rn.bf16x2.f32."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_tensor_core_split_precision():
+    """The arithmetic of HMFE_VARIANT_TC without a GPU (csrc/logmel_tc.cu): weights and powers as bf16 (hi, lo) pairs,
+    mel = W_hi P_hi + W_hi P_lo + W_lo P_hi + W_lo P_lo accumulated in float32, against the float64 product of the float32
+    operands.  This is the bound the GPU test relies on (3e-5 relative per mel bin, 1e-4 of the clip maximum overall) on
+    powers that span the 80 dB the dB stage keeps."""
+    from oracle import frontend as F
+    from oracle import librosa_restated as lr
+
+    W = lr.mel_filterbank(16000, 1024, n_mels=64, fmin=50, fmax=8000).astype(np.float32)[:, :512]
+    w_hi = _bf16_rn(W)
+    w_lo = _bf16_rn(W - w_hi)
+    rng = np.random.default_rng(3)
+    for x in (golden_signal(128000, 5), golden_signal(40001, 4)):
+        _, _, S = F.log_mel(x, f_max=8000, return_parts=True)  # only for the scale of real mel powers
+        P = (rng.random((64, 512)) ** 6 * float(S.max()) * 4).astype(np.float32)  # 64 frames of bin powers, ~100 dB of range
+        p_hi = _bf16_rn(P)
+        p_lo = _bf16_rn(P - p_hi)
+        acc = np.zeros((64, 64), dtype=np.float32)
+        for k0 in range(0, 512, 16):  # K = 16 per MMA, float32 accumulation across the 32 instructions
+            sl = slice(k0, k0 + 16)
+            part = (p_hi[:, sl].astype(np.float64) @ w_hi[:, sl].T.astype(np.float64) + p_lo[:, sl].astype(np.float64) @ w_hi[:, sl].T.astype(np.float64)
+                    + p_hi[:, sl].astype(np.float64) @ w_lo[:, sl].T.astype(np.float64) + p_lo[:, sl].astype(np.float64) @ w_lo[:, sl].T.astype(np.float64))
+            acc = (acc.astype(np.float64) + part).astype(np.float32)
+        exact = P.astype(np.float64) @ W.T.astype(np.float64)
+        rel = np.abs(acc - exact) / np.maximum(exact, 1e-300)
+        assert rel[exact > 0].max() <= 3e-5, rel[exact > 0].max()
+        assert np.abs(acc - exact).max() <= 1e-5 * exact.max()
