@@ -838,7 +838,8 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_pipe4_kernel(const IirO
                 yq[2] = pipe.tick(cf, xin[2]);
                 yq[3] = pipe.tick(cf, xin[3]);
             };
-            auto finish = [&](int u) {  // output unit u from yq
+            auto emit_unit = [&](int u, auto head_c) {  // output unit u from yq; head_c: the unit whose squares are kept apart
+                constexpr bool HEAD = decltype(head_c)::value;
                 if (!EMIT) return;
                 float4 o;
                 o.x = (float)yq[0] * gain;
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_pipe4_kernel(const IirO
                         e2 = r > 2 ? e2 : 0.0f;
                         e3 = r > 3 ? e3 : 0.0f;
                     }
-                    if (u == 0) {
+                    if (HEAD) {
                         head[0] = e0 * e0;
                         head[1] = e1 * e1;
                         head[2] = e2 * e2;
@@ -870,6 +871,8 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_pipe4_kernel(const IirO
                     }
                 }
             };
+            auto finish = [&](int u) { emit_unit(u, std::true_type{}); };        // u == 0
+            auto finish_body = [&](int u) { emit_unit(u, std::false_type{}); };  // u >= 1
             auto advance = [&](const float4& raw2) {
                 xin[0] = (double)raw1.x;
                 xin[1] = (double)raw1.y;
@@ -878,19 +881,31 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_pipe4_kernel(const IirO
                 raw1 = raw2;
                 tin += 4;
             };
+            // units 0 and 1 are peeled (unit 0 has nothing to finish, the finish of unit 0 fills `head`), the other six
+            // run two per trip: no register rotation and half the loop overhead (103 -> 93 instructions per unit)
             {
                 const float4 raw2 = fetch(tin + 8);
                 ticks();
                 advance(raw2);
             }
-#pragma unroll 1
-            for (int u = 1; u < 8; ++u) {
+            {
                 const float4 raw2 = fetch(tin + 8);
-                finish(u - 1);
+                finish(0);
                 ticks();
                 advance(raw2);
             }
-            finish(7);
+#pragma unroll 1
+            for (int u = 2; u < 8; u += 2) {
+                const float4 raw2 = fetch(tin + 8);
+                finish_body(u - 1);
+                ticks();
+                advance(raw2);
+                const float4 raw3 = fetch(tin + 8);
+                finish_body(u);
+                ticks();
+                advance(raw3);
+            }
+            finish_body(7);
         };
         // warp-uniform choice (a per-lane branch would run the recurrence twice for a warp that holds the last chunk of a
         // clip): the masked variant whenever some row ends inside or before this block
