@@ -455,7 +455,9 @@ HMFE_D void cp_async_wait() {
 // so the global-load latency of a block is covered by the filtering of the kRing - 1 blocks before it.
 // The folded band-pass gain is applied to the float32 output (FP32 pipe) instead of the float64 input.
 // Measured on B200 (c2, 1.78 G samples): ring 4 x 3 CTAs/SM 3.55 ms, 3 x 3 3.58, 3 x 4 3.72, 2 x 4 3.73, 2 x 5 3.90.
-template <int S, bool BP, bool POWER, int CONV>
+// GRP: 32-sample blocks per load / store group.  With GRP = 2 a row is fetched and written 256 bytes at a time (two column
+// blocks = half the ring per visit), i.e. half as many visits to every DRAM page; the ring then runs one group ahead.
+template <int S, bool BP, bool POWER, int CONV, int GRP = 1>
 __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const IirOverlap4Batch b, const IirCoef<S> cf) {
     extern __shared__ __align__(16) unsigned char iir_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
     const int hi_self = me.hi;
     const int valid_len = me.hi - b.W;  // chunk positions [0, valid_len) exist (<= 0 for idle lanes)
     const int t_end = b.W + b.C;
-    int t_first = me.hi > me.lo ? (me.lo & ~31) : t_end;
+    int t_first = me.hi > me.lo ? (me.lo & ~(32 * GRP - 1)) : t_end;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, d));
     // 32-sample blocks in which this lane's own row has a clip edge that is not a multiple of 4
@@ -525,18 +527,23 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
         }
     };
 
+    static_assert(kRing % GRP == 0, "the ring holds whole groups");
 #pragma unroll 1
-    for (int k = 0; k < kRing; ++k) {
-        if (t_first + 32 * k < t_end) issue_load(t_first + 32 * k);
+    for (int k = 0; k < kRing; k += GRP) {
+#pragma unroll 1
+        for (int h = 0; h < GRP; ++h)
+            if (t_first + 32 * (k + h) < t_end) issue_load(t_first + 32 * (k + h));
         cp_async_commit();
     }
 
     float body = 0.0f, head[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q[4] = {0.0f, 0.0f, 0.0f, 0.0f}, grp = 0.0f;
     int gidx = 0, pos_in_group = 0;
 #pragma unroll 1
-    for (int tb = t_first; tb < t_end; tb += 32) {
-        cp_async_wait<kRing - 1>();
+    for (int tg = t_first; tg < t_end; tg += 32 * GRP) {
+        cp_async_wait<kRing / GRP - 1>();
         __syncwarp();
+#pragma unroll 1
+      for (int tb = tg; tb < tg + 32 * GRP; tb += 32) {  // (GRP = 1: one trip)
         const int col0 = 32 * ((tb >> 5) % kRing);
         const bool emit = tb >= b.W;  // warp uniform
         bool group_start = false;
@@ -591,8 +598,13 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
         } else if (POWER && emit && group_start) {
             q[0] = q[1] = q[2] = q[3] = 0.0f;
         }
+      }
         __syncwarp();
         // ---- store: rows 4*i + rsub, positions tb + c4 .. + 3
+#pragma unroll 1
+      for (int tb = tg; tb < tg + 32 * GRP; tb += 32) {
+        const int col0 = 32 * ((tb >> 5) % kRing);
+        const bool emit = tb >= b.W;
         if (emit) {
             const int t = tb + c4;
             const bool edge = __any_sync(0xffffffffu, edge_lo == (tb >> 5) || edge_hi == (tb >> 5));
@@ -615,10 +627,13 @@ __global__ void __launch_bounds__(kIirWarps * 32, 3) iir_overlap4_kernel(const I
                         if (t + c >= olo && t + c < mv[i].hi) b.y32[mv[i].base + t + c] = e[c];
                 }
             }
-            __syncwarp();
         }
-        // ---- hand the column block to stream block tb + 32 * kRing
-        if (tb + 32 * kRing < t_end) issue_load(tb + 32 * kRing);
+      }
+        __syncwarp();
+        // ---- hand the column blocks to the stream blocks one ring further
+#pragma unroll 1
+        for (int tb = tg; tb < tg + 32 * GRP; tb += 32)
+            if (tb + 32 * kRing < t_end) issue_load(tb + 32 * kRing);
         cp_async_commit();
     }
     cp_async_wait<0>();
@@ -1180,9 +1195,20 @@ static int run_iir_overlap(hmfe_ctx* ctx, const IirOverlapBatch& b, const double
 
 constexpr size_t kOverlap4Smem = (size_t)kIirWarps * 32 * kRow4 * sizeof(float) + (size_t)kIirWarps * 32 * sizeof(IirRow4);
 
-template <int S, bool BP, bool POWER, int CONV>
+// HMFE_IIR_GROUP: 32-sample blocks per load / store group of iir_overlap4_kernel (1 or 2; default 2).  Measured on B200,
+// c2: 3.60 ms with 128-byte visits per row, 3.46 ms with 256-byte visits - the 57 000 concurrent row streams of this
+// kernel touch a different DRAM page with every visit, and twice the bytes per visit is half the page activations.
+static int iir_group_mode() {
+    static const int mode = [] {
+        const char* e = getenv("HMFE_IIR_GROUP");
+        return e && atoi(e) == 1 ? 1 : 2;
+    }();
+    return mode;
+}
+
+template <int S, bool BP, bool POWER, int CONV, int GRP = 1>
 static int launch_overlap4_c(const IirOverlap4Batch& b, const IirCoef<S>& cf, cudaStream_t st) {
-    auto kern = iir_overlap4_kernel<S, BP, POWER, CONV>;
+    auto kern = iir_overlap4_kernel<S, BP, POWER, CONV, GRP>;
     HMFE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOverlap4Smem));
     const unsigned grid = (unsigned)((b.n_chunks + kIirWarps * 32 - 1) / (kIirWarps * 32));
     kern<<<grid, kIirWarps * 32, kOverlap4Smem, st>>>(b, cf);
@@ -1237,6 +1263,7 @@ static int launch_overlap4_k(const IirOverlap4Batch& b, const IirCoef<S>& cf, cu
         default: break;
     }
 #endif
+    if (iir_group_mode() == 2) return launch_overlap4_c<S, BP, POWER, 0, 2>(b, cf, st);
     return launch_overlap4_c<S, BP, POWER, 0>(b, cf, st);
 }
 
