@@ -561,8 +561,9 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
         return HMFE_ERR_UNSUPPORTED;
     }
     HMFE_REQUIRE(hop >= 1 && hop <= 4096, "hop=%d out of range", hop);
-    HMFE_REQUIRE(n_mels >= 32 && n_mels % 32 == 0 && n_mels <= 32 * kMaxSlots, "n_mels=%d must be a multiple of 32 <= %d",
-                 n_mels, 32 * kMaxSlots);
+    HMFE_REQUIRE(n_mels >= 4 && n_mels % 4 == 0 && n_mels <= 32 * kMaxSlots, "n_mels=%d must be a multiple of 4 <= %d", n_mels,
+                 32 * kMaxSlots);
+    const bool plain = n_fft != kNfft || n_mels % 32 != 0;  // the register-resident kernels: n_fft 1024, mel bands by 32
     HMFE_REQUIRE(sample_rate > 0 && f_min >= 0 && f_max > f_min && f_max <= 0.5 * sample_rate + 1e-9,
                  "bad frequency range [%g, %g] for sr=%d", f_min, f_max, sample_rate);
     HMFE_REQUIRE(variant >= 0 && variant <= 4, "bad variant %d", variant);
@@ -578,7 +579,7 @@ int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft,
     p->variant = variant == HMFE_VARIANT_AUTO ? HMFE_VARIANT_PACKED : variant;
     p->sm_count = device_sm_count();
     p->mel_dense = mel_filterbank_slaney(sample_rate, n_fft, n_mels, f_min, f_max);
-    if (n_fft != kNfft) {  // the plain kernel of logmel_generic.cu, whatever variant was asked for
+    if (plain) {  // the plain kernel of logmel_generic.cu, whatever variant was asked for
         p->variant = kVariantGeneric;
         std::vector<float> win, tw;
         std::vector<int> lo, hi;

@@ -61,7 +61,8 @@ typedef struct hmfe_logmel_plan hmfe_logmel_plan;
 
 /* n_fft = 1024 (the only value the reference uses) runs the register-resident kernels selected by `variant`; other powers of
  * two from 64 to 4096 run a plain shared-memory FFT kernel (pre_process_audio_mel_t takes nfft as an argument,
- * src/util.py:482); anything else is HMFE_ERR_UNSUPPORTED.  n_mels a multiple of 32, <= 256. */
+ * src/util.py:482); anything else is HMFE_ERR_UNSUPPORTED.  n_mels a multiple of 4, <= 256; the register-resident kernels
+ * take multiples of 32 (the reference uses 64), other counts run the plain kernel too. */
 int hmfe_logmel_plan_create(hmfe_logmel_plan** plan, int sample_rate, int n_fft, int hop, int n_mels, double f_min,
                             double f_max, int variant);
 void hmfe_logmel_plan_destroy(hmfe_logmel_plan* plan);

@@ -90,6 +90,10 @@ def test_other_frame_lengths_match_oracle(nfft, hop):
     assert np.abs(got - F.log_mel(x, f_max=8000, nfft=nfft, hop=hop)).max() <= NORM_TOL
     with pytest.raises(Exception):
         LogMelPlan(f_max=8000, nfft=1000)
+    # mel band counts that are not a multiple of 32 (librosa's 40 / 80 / 100) take the same kernel, also at n_fft = 1024
+    for n_mels, nf in ((40, 1024), (80, nfft), (100, 1024)):
+        plan = LogMelPlan(f_max=8000, n_mels=n_mels, nfft=nf, hop=hop)
+        _check(plan, [golden_signal(n, seed=60 + i) for i, n in enumerate((48000, 7777, 65440))], hop=hop)
 
 
 def test_default_fmax_2000_and_other_hop():
